@@ -1,0 +1,297 @@
+"""CPU ORACLE bindings (test infrastructure — see oracle/pk_oracle.hpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package.  physkit_b200 never does; its product path fails loudly without the CUDA library.
+
+Shapes are given as a list of specs shared with tests/scenes.py and physkit_b200:
+    ("aabb", min3, max3) | ("obb", half3) | ("sphere", r) | ("hull", verts[n,3])
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpk_oracle.so")
+
+KIND_AABB, KIND_OBB, KIND_SPHERE, KIND_HULL = 0, 1, 2, 3
+
+SHAPE_DTYPE = np.dtype(
+    [
+        ("kind", np.int32),
+        ("vert_off", np.uint32),
+        ("nverts", np.uint32),
+        ("_pad", np.uint32),
+        ("a", np.float64, 3),
+        ("b", np.float64, 3),
+        ("lmin", np.float64, 3),
+        ("lmax", np.float64, 3),
+    ],
+    align=True,
+)
+assert SHAPE_DTYPE.itemsize == 112
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/libpk_oracle.so with the committed Makefile (g++ only)."""
+    src = [os.path.join(_HERE, f) for f in ("pk_oracle.hpp", "pk_oracle_c.cpp", "Makefile")]
+    if (
+        force
+        or not os.path.exists(_LIB_PATH)
+        or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
+    ):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        L.pko_shape_local_aabb.argtypes = [vp, vp]
+        L.pko_bounds.argtypes = [vp, vp, vp, vp, u64, vp]
+        L.pko_support.argtypes = [vp, vp, vp, vp, u32, vp, vp]
+        L.pko_gjk_epa_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp, i32]
+        L.pko_gjk_epa_pairs.restype = u64
+        L.pko_bvh_create.restype = vp
+        L.pko_bvh_destroy.argtypes = [vp]
+        L.pko_bvh_add.argtypes = [vp, u32, vp]
+        L.pko_bvh_add.restype = u32
+        L.pko_bvh_remove.argtypes = [vp, u32]
+        L.pko_bvh_update.argtypes = [vp, u32, vp, vp]
+        L.pko_bvh_update.restype = i32
+        L.pko_bvh_bounds.argtypes = [vp, u32, vp]
+        L.pko_bvh_data.argtypes = [vp, u32]
+        L.pko_bvh_data.restype = u32
+        L.pko_bvh_validate.argtypes = [vp]
+        L.pko_bvh_validate.restype = i32
+        L.pko_bvh_query.argtypes = [vp, vp, vp, u64, u64]
+        L.pko_bvh_query.restype = u64
+        L.pko_bp_create.restype = vp
+        L.pko_bp_destroy.argtypes = [vp]
+        L.pko_bp_add.argtypes = [vp, u32, vp, i32]
+        L.pko_bp_remove.argtypes = [vp, u32]
+        L.pko_bp_update.argtypes = [vp, u32, vp, vp]
+        L.pko_bp_update.restype = i32
+        L.pko_bp_calculate.argtypes = [vp]
+        L.pko_bp_pairs.argtypes = [vp, vp, u64]
+        L.pko_bp_pairs.restype = u64
+        L.pko_bp_stored.argtypes = [vp, u32, vp]
+        L.pko_world_create.restype = vp
+        L.pko_world_destroy.argtypes = [vp]
+        L.pko_world_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64]
+        L.pko_world_step.restype = u64
+        L.pko_world_pairs.argtypes = [vp, vp, u64]
+        L.pko_world_pairs.restype = u64
+        L.pko_world_stored.argtypes = [vp, u32, vp]
+        L.pko_query_pairs.argtypes = [vp, u64, vp, u64]
+        L.pko_query_pairs.restype = u64
+        L.pko_brute_pairs.argtypes = [vp, u64, vp, u64]
+        L.pko_brute_pairs.restype = u64
+        L.pko_max_threads.restype = i32
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class ShapeTable:
+    """Flat shape table + shared vertex pool in the layout of pko_shape_desc."""
+
+    def __init__(self, specs):
+        self.specs = list(specs)
+        verts = []
+        off = 0
+        tab = np.zeros(len(self.specs), dtype=SHAPE_DTYPE)
+        for i, s in enumerate(self.specs):
+            k = s[0]
+            if k == "aabb":
+                tab[i]["kind"] = KIND_AABB
+                tab[i]["a"] = np.asarray(s[1], dtype=np.float64)
+                tab[i]["b"] = np.asarray(s[2], dtype=np.float64)
+            elif k == "obb":
+                tab[i]["kind"] = KIND_OBB
+                tab[i]["a"] = np.asarray(s[1], dtype=np.float64)
+            elif k == "sphere":
+                tab[i]["kind"] = KIND_SPHERE
+                tab[i]["a"][0] = float(s[1])
+            elif k == "hull":
+                v = _f64(s[1]).reshape(-1, 3)
+                tab[i]["kind"] = KIND_HULL
+                tab[i]["vert_off"] = off
+                tab[i]["nverts"] = len(v)
+                verts.append(v)
+                off += len(v)
+            else:
+                raise ValueError(k)
+        self.verts = np.concatenate(verts) if verts else np.zeros((1, 3))
+        self.verts = np.ascontiguousarray(self.verts, dtype=np.float64)
+        self.tab = tab
+        L = lib()
+        for i in range(len(tab)):
+            L.pko_shape_local_aabb(C.c_void_p(tab.ctypes.data + i * SHAPE_DTYPE.itemsize), _p(self.verts))
+
+    def local_aabb(self, i):
+        return np.concatenate([self.tab[i]["lmin"], self.tab[i]["lmax"]])
+
+
+def _table(shapes):
+    return shapes if isinstance(shapes, ShapeTable) else ShapeTable(shapes)
+
+
+def bounds(shapes, pos, quat, shape_id):
+    """mesh::instance::bounds() per body → [n,6]."""
+    t = _table(shapes)
+    pos = _f64(pos, (-1, 3))
+    quat = _f64(quat, (-1, 4))
+    sid = np.ascontiguousarray(shape_id, dtype=np.uint32)
+    out = np.empty((len(pos), 6))
+    lib().pko_bounds(_p(t.tab), _p(pos), _p(quat), _p(sid), len(pos), _p(out))
+    return out
+
+
+def support(shapes, pos, quat, shape_index, direction):
+    t = _table(shapes)
+    pos = _f64(pos, (3,))
+    quat = _f64(quat, (4,))
+    d = _f64(direction, (3,))
+    out = np.empty(3)
+    lib().pko_support(_p(t.tab), _p(t.verts), _p(pos), _p(quat), int(shape_index), _p(d), _p(out))
+    return out
+
+
+def gjk_epa_pairs(shapes, pos, quat, shape_id, pair_a, pair_b, stats=False, nthreads=1):
+    """gjk_epa(body a, body b) per pair → (hit[n] u8, contact[n,10], stats[n,8] | None)."""
+    t = _table(shapes)
+    pos = _f64(pos, (-1, 3))
+    quat = _f64(quat, (-1, 4))
+    sid = np.ascontiguousarray(shape_id, dtype=np.uint32)
+    pa = np.ascontiguousarray(pair_a, dtype=np.uint32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.uint32)
+    n = len(pa)
+    out = np.zeros((n, 10))
+    hit = np.zeros(n, dtype=np.uint8)
+    st = np.zeros((n, 8), dtype=np.int32) if stats else None
+    lib().pko_gjk_epa_pairs(
+        _p(t.tab), _p(t.verts), _p(pos), _p(quat), _p(sid), _p(pa), _p(pb), n, _p(out), _p(hit), _p(st), int(nthreads)
+    )
+    return hit, out, st
+
+
+def gjk_epa(shape_a, pose_a, shape_b, pose_b):
+    """One pair from two (spec, (pos, quat_xyzw)) → None | dict(normal, world_a, world_b, depth)."""
+    pos = np.array([pose_a[0], pose_b[0]], dtype=np.float64)
+    quat = np.array([pose_a[1], pose_b[1]], dtype=np.float64)
+    hit, out, _ = gjk_epa_pairs([shape_a, shape_b], pos, quat, [0, 1], [0], [1])
+    if not hit[0]:
+        return None
+    o = out[0]
+    return dict(normal=o[0:3].copy(), world_a=o[3:6].copy(), world_b=o[6:9].copy(), depth=float(o[9]))
+
+
+def query_pairs(boxes6):
+    """Static-pose pair set through the faithful dynamic_bvh (add all, query all)."""
+    b = _f64(boxes6, (-1, 6))
+    n = lib().pko_query_pairs(_p(b), len(b), None, 0)
+    out = np.empty(n, dtype=np.uint64)
+    lib().pko_query_pairs(_p(b), len(b), _p(out), n)
+    return out
+
+
+def brute_pairs(boxes6):
+    b = _f64(boxes6, (-1, 6))
+    n = lib().pko_brute_pairs(_p(b), len(b), None, 0)
+    out = np.empty(n, dtype=np.uint64)
+    lib().pko_brute_pairs(_p(b), len(b), _p(out), n)
+    return out
+
+
+def max_threads():
+    return int(lib().pko_max_threads())
+
+
+class DynamicBVH:
+    """dynamic_bvh (bvh.h:270-535) handle."""
+
+    def __init__(self):
+        self.h = lib().pko_bvh_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().pko_bvh_destroy(self.h)
+            self.h = None
+
+    def add(self, obj_id, box6):
+        return int(lib().pko_bvh_add(self.h, int(obj_id), _p(_f64(box6, (6,)))))
+
+    def remove_leaf(self, leaf):
+        lib().pko_bvh_remove(self.h, int(leaf))
+
+    def update_leaf(self, leaf, box6, disp3):
+        return bool(lib().pko_bvh_update(self.h, int(leaf), _p(_f64(box6, (6,))), _p(_f64(disp3, (3,)))))
+
+    def bounds(self, leaf):
+        out = np.empty(6)
+        lib().pko_bvh_bounds(self.h, int(leaf), _p(out))
+        return out
+
+    def data(self, leaf):
+        return int(lib().pko_bvh_data(self.h, int(leaf)))
+
+    def validate(self):
+        return bool(lib().pko_bvh_validate(self.h))
+
+    def query_aabb(self, box6, stop_after=0, cap=1 << 16):
+        out = np.empty(cap, dtype=np.uint32)
+        n = lib().pko_bvh_query(self.h, _p(_f64(box6, (6,))), _p(out), cap, int(stop_after))
+        return out[: min(n, cap)].copy()
+
+
+class World:
+    """The collision stage of world::step_impl (src/world.cpp:30-46) on flat body arrays."""
+
+    def __init__(self, shapes):
+        self.t = _table(shapes)
+        self.h = lib().pko_world_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().pko_world_destroy(self.h)
+            self.h = None
+
+    def step(self, pos, quat, disp, shape_id, flags):
+        pos = _f64(pos, (-1, 3))
+        quat = _f64(quat, (-1, 4))
+        disp = _f64(disp, (-1, 3))
+        sid = np.ascontiguousarray(shape_id, dtype=np.uint32)
+        fl = np.ascontiguousarray(flags, dtype=np.uint8)
+        moved = lib().pko_world_step(self.h, _p(self.t.tab), _p(pos), _p(quat), _p(disp), _p(sid), _p(fl), len(pos))
+        return int(moved)
+
+    def pairs(self):
+        n = lib().pko_world_pairs(self.h, None, 0)
+        out = np.empty(n, dtype=np.uint64)
+        lib().pko_world_pairs(self.h, _p(out), n)
+        return out
+
+    def stored(self, body):
+        out = np.empty(6)
+        lib().pko_world_stored(self.h, int(body), _p(out))
+        return out

@@ -1,0 +1,367 @@
+// pk_oracle_c.cpp — C ABI over pk_oracle.hpp for ctypes.  CPU ORACLE: test infrastructure only
+// (see the header of pk_oracle.hpp).  Nothing in physkit_b200/ may link or load this.
+#include "pk_oracle.hpp"
+
+#include <atomic>
+#include <cstdio>
+#include <thread>
+
+using namespace pko;
+
+extern "C"
+{
+
+// Mirrors pk_shape_* of include/pk_collide.h (the product ABI) so the same scene arrays can be fed
+// to both sides.
+struct pko_shape_desc
+{
+    int32_t kind;      // shape_kind
+    uint32_t vert_off; // HULL: first vertex (in units of vertices) in the shared vertex pool
+    uint32_t nverts;   // HULL
+    uint32_t _pad;
+    double a[3];    // AABB: min | OBB: half extents | SPHERE: a[0] = radius
+    double b[3];    // AABB: max
+    double lmin[3]; // local AABB (what mesh::bounds() would be, mesh.h:191,248)
+    double lmax[3];
+};
+
+static inline v3 ld3(const double *p) { return {p[0], p[1], p[2]}; }
+static inline quat ldq(const double *p) { return {p[0], p[1], p[2], p[3]}; } // x,y,z,w
+static inline void st3(double *o, v3 v)
+{
+    o[0] = v.x;
+    o[1] = v.y;
+    o[2] = v.z;
+}
+
+// Fill lmin/lmax from the shape parameters.
+void pko_shape_local_aabb(pko_shape_desc *s, const double *verts)
+{
+    switch (s->kind)
+    {
+    case KIND_AABB:
+        for (int k = 0; k < 3; ++k) s->lmin[k] = s->a[k], s->lmax[k] = s->b[k];
+        break;
+    case KIND_OBB:
+        for (int k = 0; k < 3; ++k) s->lmin[k] = -s->a[k], s->lmax[k] = s->a[k];
+        break;
+    case KIND_SPHERE:
+        for (int k = 0; k < 3; ++k) s->lmin[k] = -s->a[0], s->lmax[k] = s->a[0];
+        break;
+    default:
+    {
+        aabb bx = aabb_from_points(reinterpret_cast<const v3 *>(verts) + s->vert_off, s->nverts);
+        st3(s->lmin, bx.min);
+        st3(s->lmax, bx.max);
+    }
+    }
+}
+
+static inline aabb body_bounds(const pko_shape_desc &s, const double *pos, const double *q)
+{
+    aabb local{ld3(s.lmin), ld3(s.lmax)};
+    if (s.kind == KIND_AABB) return local; // pose-less shape (gjk_epa(aabb, …) instantiations only)
+    return instance_bounds(local, ld3(pos), ldq(q));
+}
+
+static inline shape make_shape(const pko_shape_desc &s, const double *verts, const double *pos,
+                               const double *q)
+{
+    shape sh{};
+    sh.kind = s.kind;
+    switch (s.kind)
+    {
+    case KIND_AABB:
+        sh.a = ld3(s.a);
+        sh.b = ld3(s.b);
+        break;
+    case KIND_OBB:
+        sh.a = ld3(pos);
+        sh.b = ld3(s.a);
+        sh.q = ldq(q);
+        break;
+    case KIND_SPHERE:
+        sh.a = ld3(pos);
+        sh.b = v3{s.a[0], 0, 0};
+        break;
+    default:
+        sh.a = ld3(pos);
+        sh.q = ldq(q);
+        sh.verts = reinterpret_cast<const v3 *>(verts) + s.vert_off;
+        sh.nverts = s.nverts;
+    }
+    return sh;
+}
+
+// mesh::instance::bounds() for every body → out6[n] = (min xyz, max xyz).
+void pko_bounds(const pko_shape_desc *shapes, const double *pos, const double *quat_xyzw,
+                const uint32_t *shape_id, uint64_t n, double *out6)
+{
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        aabb b = body_bounds(shapes[shape_id[i]], pos + 3 * i, quat_xyzw + 4 * i);
+        st3(out6 + 6 * i, b.min);
+        st3(out6 + 6 * i + 3, b.max);
+    }
+}
+
+// Single support query (tests/obb/obb_test.cpp:142-159, tests/mesh/main.cpp:890-899,1660-1710).
+void pko_support(const pko_shape_desc *shapes, const double *verts, const double *pos,
+                 const double *quat_xyzw, uint32_t shape_id, const double *dir, double *out3)
+{
+    shape s = make_shape(shapes[shape_id], verts, pos, quat_xyzw);
+    st3(out3, support(s, ld3(dir)));
+}
+
+// gjk_epa(a = body pair_a[k], b = body pair_b[k]) for every k.
+//   out10[k] = normal(3) world_a(3) world_b(3) depth ; hit[k] ∈ {0,1} ; stats8[k] optional.
+// nthreads > 1 uses std::thread workers over independent pairs (courtesy all-cores figure; the reference
+// itself is single-threaded: collision_phases.h:251 "TODO: parallelize").
+uint64_t pko_gjk_epa_pairs(const pko_shape_desc *shapes, const double *verts, const double *pos,
+                           const double *quat_xyzw, const uint32_t *shape_id, const uint32_t *pair_a,
+                           const uint32_t *pair_b, uint64_t npairs, double *out10, uint8_t *hit,
+                           int32_t *stats8, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<uint64_t> next{0};
+    std::atomic<uint64_t> nhit{0};
+    constexpr uint64_t chunk = 256;
+    auto worker = [&]()
+    {
+        uint64_t local_hits = 0;
+        for (;;)
+        {
+            uint64_t k0 = next.fetch_add(chunk);
+            if (k0 >= npairs) break;
+            uint64_t k1 = std::min(npairs, k0 + chunk);
+            for (uint64_t k = k0; k < k1; ++k)
+            {
+                uint32_t ia = pair_a[k], ib = pair_b[k];
+                shape a = make_shape(shapes[shape_id[ia]], verts, pos + 3 * ia, quat_xyzw + 4 * ia);
+                shape b = make_shape(shapes[shape_id[ib]], verts, pos + 3 * ib, quat_xyzw + 4 * ib);
+                gjk_stats st;
+                auto r = gjk_epa(a, b, &st);
+                if (hit) hit[k] = r ? 1 : 0;
+                if (out10)
+                {
+                    double *o = out10 + 10 * k;
+                    if (r)
+                    {
+                        st3(o, r->normal);
+                        st3(o + 3, r->world_a);
+                        st3(o + 6, r->world_b);
+                        o[9] = r->depth;
+                    }
+                    else
+                        for (int j = 0; j < 10; ++j) o[j] = 0.0;
+                }
+                if (stats8)
+                {
+                    int32_t *s = stats8 + 8 * k;
+                    s[0] = st.gjk_iters;
+                    s[1] = st.epa_iters;
+                    s[2] = st.epa_faces;
+                    s[3] = st.epa_verts;
+                    s[4] = st.epa_heap_max;
+                    s[5] = st.epa_horizon_max;
+                    s[6] = st.epa_stack_max;
+                    s[7] = st.exit_code;
+                }
+                if (r) ++local_hits;
+            }
+        }
+        nhit += local_hits;
+    };
+    if (nthreads == 1)
+        worker();
+    else
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+        for (auto &t : pool) t.join();
+    }
+    return nhit.load();
+}
+
+// ------------------------------- dynamic_bvh handle API ---------------------------------------
+void *pko_bvh_create() { return new dynamic_bvh(); }
+void pko_bvh_destroy(void *t) { delete static_cast<dynamic_bvh *>(t); }
+uint32_t pko_bvh_add(void *t, uint32_t id, const double *box6)
+{
+    return static_cast<dynamic_bvh *>(t)->add(id, aabb{ld3(box6), ld3(box6 + 3)});
+}
+void pko_bvh_remove(void *t, uint32_t leaf) { static_cast<dynamic_bvh *>(t)->remove_leaf(leaf); }
+int pko_bvh_update(void *t, uint32_t leaf, const double *box6, const double *disp3)
+{
+    return static_cast<dynamic_bvh *>(t)->update_leaf(leaf, aabb{ld3(box6), ld3(box6 + 3)}, ld3(disp3)) ? 1 : 0;
+}
+void pko_bvh_bounds(void *t, uint32_t leaf, double *out6)
+{
+    const aabb &b = static_cast<dynamic_bvh *>(t)->bounds(leaf);
+    st3(out6, b.min);
+    st3(out6 + 3, b.max);
+}
+uint32_t pko_bvh_data(void *t, uint32_t leaf) { return static_cast<dynamic_bvh *>(t)->data(leaf); }
+int pko_bvh_validate(void *t) { return static_cast<dynamic_bvh *>(t)->validate() ? 1 : 0; }
+// Collect up to cap ids in callback order; stop_after > 0 makes the callback return false after
+// that many hits (early termination, tests/dynamic_bvh/main.cpp:262-277).
+uint64_t pko_bvh_query(void *t, const double *box6, uint32_t *out, uint64_t cap, uint64_t stop_after)
+{
+    uint64_t n = 0;
+    static_cast<dynamic_bvh *>(t)->query_aabb(aabb{ld3(box6), ld3(box6 + 3)},
+                                              [&](uint32_t id)
+                                              {
+                                                  if (n < cap) out[n] = id;
+                                                  ++n;
+                                                  return !(stop_after && n >= stop_after);
+                                              });
+    return n;
+}
+
+// ------------------------------- broad_phase handle API ---------------------------------------
+void *pko_bp_create() { return new broad_phase(); }
+void pko_bp_destroy(void *b) { delete static_cast<broad_phase *>(b); }
+void pko_bp_add(void *b, uint32_t id, const double *box6, int is_static)
+{
+    static_cast<broad_phase *>(b)->add(id, aabb{ld3(box6), ld3(box6 + 3)}, is_static != 0);
+}
+void pko_bp_remove(void *b, uint32_t id) { static_cast<broad_phase *>(b)->remove(id); }
+int pko_bp_update(void *b, uint32_t id, const double *box6, const double *disp3)
+{
+    return static_cast<broad_phase *>(b)->update_node(id, aabb{ld3(box6), ld3(box6 + 3)}, ld3(disp3)) ? 1 : 0;
+}
+void pko_bp_calculate(void *b) { static_cast<broad_phase *>(b)->calculate_pairs(); }
+uint64_t pko_bp_pairs(void *b, uint64_t *out, uint64_t cap)
+{
+    auto v = static_cast<broad_phase *>(b)->sorted_pairs();
+    for (uint64_t i = 0; i < v.size() && i < cap; ++i) out[i] = v[i];
+    return v.size();
+}
+void pko_bp_stored(void *b, uint32_t id, double *out6)
+{
+    const aabb &bx = static_cast<broad_phase *>(b)->stored(id);
+    st3(out6, bx.min);
+    st3(out6 + 3, bx.max);
+}
+
+// ------------------------------- world-level collision stage ----------------------------------
+// The three ★ calls of world::step_impl (src/world.cpp:30-46) driven from flat body arrays with the
+// same meaning as pk_bodies_upload (include/pk_collide.h): flags bit0 = static, bit1 = alive.
+// A body that becomes alive is create_rigid()'d (core/world.h:202-208: broad.add with the exact
+// instance bounds, not marked moved); a body that stops being alive is remove_rigid()'d.
+struct pko_world
+{
+    broad_phase bp;
+    std::vector<uint8_t> alive;
+    std::vector<uint8_t> stat;
+};
+void *pko_world_create() { return new pko_world(); }
+void pko_world_destroy(void *w) { delete static_cast<pko_world *>(w); }
+
+// Returns the number of leaves re-inserted this step (size of M_moved before calculate_pairs).
+uint64_t pko_world_step(void *wp, const pko_shape_desc *shapes, const double *pos,
+                        const double *quat_xyzw, const double *disp, const uint32_t *shape_id,
+                        const uint8_t *flags, uint64_t n)
+{
+    pko_world &w = *static_cast<pko_world *>(wp);
+    if (w.alive.size() < n)
+    {
+        w.alive.resize(n, 0);
+        w.stat.resize(n, 0);
+    }
+    // flush_commands(): destroy first, then create (core/world.h:369-374; order between the two
+    // does not matter for disjoint slots).
+    for (uint64_t i = 0; i < w.alive.size(); ++i)
+    {
+        bool now = i < n && (flags[i] & 2);
+        if (w.alive[i] && !now)
+        {
+            w.bp.remove(static_cast<uint32_t>(i));
+            w.alive[i] = 0;
+        }
+    }
+    std::vector<uint8_t> fresh(n, 0);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        if ((flags[i] & 2) && !w.alive[i])
+        {
+            aabb b = body_bounds(shapes[shape_id[i]], pos + 3 * i, quat_xyzw + 4 * i);
+            w.bp.add(static_cast<uint32_t>(i), b, flags[i] & 1);
+            w.alive[i] = 1;
+            w.stat[i] = flags[i] & 1;
+            fresh[i] = 1;
+        }
+    }
+    // step_impl loop A (src/world.cpp:22-34): every dynamic body calls update_node — including
+    // one created this very step (its true box equals its stored box, so nothing moves).
+    uint64_t moved = 0;
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        if (!w.alive[i] || w.stat[i]) continue;
+        aabb b = body_bounds(shapes[shape_id[i]], pos + 3 * i, quat_xyzw + 4 * i);
+        if (w.bp.update_node(static_cast<uint32_t>(i), b, ld3(disp + 3 * i))) ++moved;
+    }
+    w.bp.calculate_pairs();
+    return moved;
+}
+uint64_t pko_world_pairs(void *wp, uint64_t *out, uint64_t cap)
+{
+    return pko_bp_pairs(&static_cast<pko_world *>(wp)->bp, out, cap);
+}
+void pko_world_stored(void *wp, uint32_t id, double *out6)
+{
+    pko_bp_stored(&static_cast<pko_world *>(wp)->bp, id, out6);
+}
+
+// ------------------------------- static-pose ("query") mode -----------------------------------
+// The way tests/dynamic_bvh/main.cpp:600-635 drives the tree: tree.add(i, exact box) for all i,
+// then query_aabb(box_i) for all i; the pair set is {(i<j) : reported}.  Returns the pair count;
+// writes sorted keys.
+uint64_t pko_query_pairs(const double *boxes6, uint64_t n, uint64_t *out, uint64_t cap)
+{
+    dynamic_bvh tree(2 * n + 16);
+    std::vector<uint32_t> leaf(n);
+    for (uint64_t i = 0; i < n; ++i)
+        leaf[i] = tree.add(static_cast<uint32_t>(i), aabb{ld3(boxes6 + 6 * i), ld3(boxes6 + 6 * i + 3)});
+    std::vector<uint64_t> keys;
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        tree.query_aabb(tree.bounds(leaf[i]),
+                        [&](uint32_t j)
+                        {
+                            if (j > i) keys.push_back(make_pair_key(static_cast<uint32_t>(i), j));
+                            return true;
+                        });
+    }
+    std::sort(keys.begin(), keys.end());
+    for (uint64_t i = 0; i < keys.size() && i < cap; ++i) out[i] = keys[i];
+    return keys.size();
+}
+
+// Brute-force O(n²) reference of the same set, straight from aabb::intersects (bounds.h:87-92).
+uint64_t pko_brute_pairs(const double *boxes6, uint64_t n, uint64_t *out, uint64_t cap)
+{
+    uint64_t cnt = 0;
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        aabb bi{ld3(boxes6 + 6 * i), ld3(boxes6 + 6 * i + 3)};
+        for (uint64_t j = i + 1; j < n; ++j)
+        {
+            aabb bj{ld3(boxes6 + 6 * j), ld3(boxes6 + 6 * j + 3)};
+            if (bi.intersects(bj))
+            {
+                if (cnt < cap) out[cnt] = make_pair_key(static_cast<uint32_t>(i), static_cast<uint32_t>(j));
+                ++cnt;
+            }
+        }
+    }
+    return cnt;
+}
+
+int pko_max_threads()
+{
+    unsigned n = std::thread::hardware_concurrency();
+    return n ? static_cast<int>(n) : 1;
+}
+
+} // extern "C"
