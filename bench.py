@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — collision stage (broadphase + GJK/EPA) throughput on BASELINE config C3.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--side S]
+
+Workload (BASELINE.json configs[2], "C3"): side³ bodies (default 100³ = 1 M) on a jittered lattice,
+even ids analytic spheres, odd ids OBBs, physkit::world pair semantics (fat AABBs).  A "step" is one
+pass of the hot path: bounds/fat update → LBVH build → self-overlap traversal → pair sort → GJK → EPA.
+N > 1 (torchrun, one rank per GPU): every rank rebuilds the tree, traverses its own slice of the
+sorted leaves, runs GJK/EPA on its own pairs, then ONE all-gather of contact records (NCCL).
+
+Prints one JSON line (rank 0).  `value` = candidate-pair tests per second with inputs resident in
+HBM; `e2e` = the same through pk_bodies_update_pose + pk_collide with pinned HOST buffers (H2D poses,
+D2H pair keys + contacts inside the timed region).  --impl reference times the CPU oracle port
+(oracle/, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "colliding-pair tests/sec (collision stage: LBVH broadphase + GJK/EPA), 1M-body C3 scene"
+UNIT = "pair tests/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle-reason sampling during the timed region (recipe's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_scene(side):
+    from scenes import scene_c3
+
+    return scene_c3(side=side)
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(side_sample, nthreads, steps=1, warmup=0):
+    """Oracle port of the reference's collision stage on a bounded C3 sample: faithful incremental
+    dynamic_bvh broadphase (1 thread, as in the reference) + gjk_epa per active pair (nthreads)."""
+    import oracle
+
+    sc = make_scene(side_sample)
+    w = oracle.World(sc.shapes)
+    p0 = sc.pos
+    p1 = sc.pos + 0.05
+    zero = np.zeros_like(p0)
+    w.step(p0, sc.quat, zero, sc.shape_id, sc.flags)  # create_rigid for all (no pairs yet)
+    w.step(p1, sc.quat, zero, sc.shape_id, sc.flags)  # every leaf re-inserted → pair set forms
+    times, pairs = [], 0
+    for s in range(warmup + steps):
+        pos = p0 if s % 2 == 0 else p1
+        t0 = time.perf_counter()
+        w.step(pos, sc.quat, zero, sc.shape_id, sc.flags)
+        keys = w.pairs()
+        pa = (keys >> np.uint64(32)).astype(np.uint32)
+        pb = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        t1 = time.perf_counter()
+        hit, out, _ = oracle.gjk_epa_pairs(sc.shapes, pos, sc.quat, sc.shape_id, pa, pb, nthreads=nthreads)
+        t2 = time.perf_counter()
+        if s >= warmup:
+            times.append((t1 - t0, t2 - t1))
+            pairs = len(keys)
+    tb = float(np.mean([t[0] for t in times]))
+    tn = float(np.mean([t[1] for t in times]))
+    return dict(bodies=sc.n, pairs=pairs, s_broad=tb, s_narrow=tn, pairs_per_s=pairs / (tb + tn), contacts=int(hit.sum()))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle
+
+    oracle.build()
+    cores = oracle.max_threads()
+    side = args.ref_side
+    r = cpu_sample(side, cores, steps=args.steps, warmup=args.warmup)
+    ms = 1e3 * (r["s_broad"] + r["s_narrow"])
+    sample = (f"C3 generator at side={side} ({r['bodies']} bodies, {r['pairs']} pairs/step): faithful dynamic_bvh "
+              f"broadphase on 1 thread ({1e3 * r['s_broad']:.1f} ms) + gjk_epa on {cores} threads ({1e3 * r['s_narrow']:.1f} ms)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["pairs_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3 bounded sample: {r['bodies']}-body jittered lattice, spheres+OBBs, world-mode pairs",
+                   "bodies": r["bodies"], "pairs_per_step": r["pairs"]},
+        "cpu_baseline": {"value": r["pairs_per_s"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": r["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+STAGE_BYTES_DOC = {
+    # algorithmic bytes per unit (SURVEY §8d / DESIGN.md §roofline)
+    "bounds_fat": ("body", 180), "morton": ("body", 56), "body_sort": ("body", 68), "leaves": ("body", 20),
+    "hierarchy_ropes": ("body", 148), "overlap": ("body+pair", (176, 8)), "pair_sort": ("pair", 144),
+    "gjk": ("pair", 153), "hit_scan": ("pair", 5), "epa": ("hit", 232), "compact": ("hit", 0),
+}
+
+
+def stage_bytes(name, n, pairs, hits):
+    unit, b = STAGE_BYTES_DOC[name]
+    if unit == "body":
+        return n * b
+    if unit == "pair":
+        return pairs * b
+    if unit == "hit":
+        return hits * b
+    return n * b[0] + pairs * b[1]
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    import physkit_b200 as pk
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the collision library has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: F811
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sc = make_scene(args.side)
+    n = sc.n
+    est_pairs = int(16.5 * n / world) + 4096
+    max_pairs = int(est_pairs * 1.3)
+    max_contacts = int(max_pairs * 0.25) + 4096
+    ctx = pk.Context(n, max_pairs, mode=pk.MODE_WORLD, device=local_rank, max_shapes=len(sc.shapes),
+                     max_contacts=max_contacts, shard_rank=rank, shard_count=world)
+    ctx.add_shapes(sc.shapes)
+    ctx.resize(n)
+    # per-step inputs live in pinned host memory (what a host engine would hand over every step)
+    h_pos = [ctx.pinned_empty((n, 3), np.float64) for _ in range(2)]
+    h_quat = ctx.pinned_empty((n, 4), np.float64)
+    h_disp = ctx.pinned_empty((n, 3), np.float64)
+    h_pos[0][:] = sc.pos
+    h_pos[1][:] = sc.pos + 0.05
+    h_quat[:] = sc.quat
+    h_disp[:] = 0.0
+    ctx.upload(h_pos[0], h_quat, h_disp, sc.shape_id, sc.flags)
+    r0 = ctx.collide_resident()
+    assert r0.num_pairs == 0, "first step must yield no pairs (reference first-step quirk)"
+    ctx.update_pose(h_pos[1], None, None)
+    r1 = ctx.collide_resident()
+    log(f"[rank {rank}] bodies {n}  pairs {r1.num_pairs}  contacts {r1.num_contacts}  moved {r1.num_moved}  "
+        f"device ms {r1.ms_total:.3f}")
+
+    send = None
+    if world > 1:
+        from physkit_b200.exchange import allgather_records
+
+        send = torch.empty(max_contacts * 88, dtype=torch.uint8, device=f"cuda:{local_rank}")
+
+    def exchange():
+        if world == 1:
+            return None
+        ptr, cnt = ctx.contacts_device()
+        if cnt:
+            ctx.d2d(send.data_ptr(), ptr, cnt * 88)
+        g, counts = allgather_records(send, cnt)
+        return g
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- resident (kernel-path) timing --------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.collide_resident()
+        exchange()
+    sampler = ClockSampler(local_rank)
+    stage_acc = {}
+    launches = 0
+    dev_ms = 0.0
+    sync_all()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = ctx.collide_resident()
+        exchange()
+        st, ln = ctx.stage_times()
+        for k, v in st.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        launches += ln
+        dev_ms += res.ms_total
+    sync_all()
+    t1 = time.perf_counter()
+    clocks = sampler.stop()
+    wall_ms = 1e3 * (t1 - t0) / args.steps
+    pairs, hits, contacts = int(res.num_pairs), int(res.gjk_hits), int(res.num_contacts)
+
+    # ---- end-to-end timing: host poses in, pair keys + contacts out ------------------------------
+    for s in range(min(args.warmup, 3)):
+        ctx.update_pose(h_pos[s % 2], None, h_disp)
+        ctx.collide()
+    sync_all()
+    e0 = time.perf_counter()
+    for s in range(args.steps):
+        ctx.update_pose(h_pos[s % 2], h_quat, h_disp)
+        res_e = ctx.collide()
+        exchange()
+    sync_all()
+    e1 = time.perf_counter()
+    e2e_ms = 1e3 * (e1 - e0) / args.steps
+    h2d = n * (3 + 4 + 3) * 8
+    d2h = int(res_e.num_pairs) * 8 + int(res_e.num_contacts) * 88
+
+    # ---- reduce over ranks (max time, sum pairs) ---------------------------------------------------
+    tot_pairs, tot_contacts, max_wall, max_e2e = pairs, contacts, wall_ms, e2e_ms
+    if world > 1:
+        t = torch.tensor([pairs, contacts], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot_pairs, tot_contacts = int(t[0].item()), int(t[1].item())
+        m = torch.tensor([wall_ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        max_wall, max_e2e = float(m[0].item()), float(m[1].item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        stages = {k: v / args.steps for k, v in stage_acc.items()}
+        table = []
+        for k, ms in stages.items():
+            if k == "fetch_d2h" or ms <= 0:
+                continue
+            b = stage_bytes(k, n, pairs, hits)
+            table.append((k, ms, b, b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0))
+        table.sort(key=lambda x: -x[1])
+        log("stage                 ms/step   alg.MB   GB/s   frac-of-peak")
+        for k, ms, b, gbs in table:
+            log(f"  {k:18s} {ms:8.3f} {b / 1e6:9.1f} {gbs:7.1f}   {gbs / peak:6.3f}")
+        dom = table[0]
+        total_bytes = sum(t[2] for t in table)
+        dev_step_ms = dev_ms / args.steps
+        roofline = {
+            "bound": "hbm", "kernel": dom[0], "achieved": dom[3], "peak": peak, "unit": "GB/s", "frac": dom[3] / peak,
+            "traffic": None, "peak_source": peak_src,
+            "kernel_ms": dom[1], "kernel_share_of_step": dom[1] / max(dev_step_ms, 1e-9),
+            "whole_step": {"alg_bytes": total_bytes, "device_ms": dev_step_ms,
+                           "achieved": total_bytes / (dev_step_ms * 1e-3) / 1e9, "frac": total_bytes / (dev_step_ms * 1e-3) / 1e9 / peak},
+            "stages_ms": {k: round(v, 4) for k, v in stages.items()},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            import oracle
+
+            oracle.build()
+            c = cpu_sample(args.cpu_side, 1, steps=1, warmup=0)
+            cpu = {"value": c["pairs_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": (f"C3 generator at side={args.cpu_side} ({c['bodies']} bodies, {c['pairs']} pairs): one steady-state "
+                              f"world step of the oracle port, faithful dynamic_bvh broadphase {1e3 * c['s_broad']:.1f} ms + "
+                              f"gjk_epa {1e3 * c['s_narrow']:.1f} ms, single thread like the reference")}
+        line = {
+            "metric": METRIC, "value": tot_pairs / (max_wall * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_wall, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3: {n}-body jittered lattice (side {args.side}), analytic spheres + OBBs, world-mode fat-AABB pairs",
+                       "bodies": n, "pairs_per_step": tot_pairs, "contacts_per_step": tot_contacts,
+                       "sharding": "pairs by sorted-leaf range, tree rebuilt per rank, one all-gather of contacts" if world > 1 else "none",
+                       "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush",
+                       "timing": "wall clock around K synchronous steps bracketed by barrier+synchronize, max over ranks; "
+                                 "per-kernel times from CUDA events on the library's stream",
+                       "poses": "alternate P0/P1 inside the fat boxes (resting pile: no re-insertions after warm-up)"},
+            "device_ms_per_step": dev_step_ms,
+            "e2e": {"value": tot_pairs / (max_e2e * 1e-3), "unit": UNIT, "ms_per_step": max_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=100, help="C3 lattice side (bodies = side^3)")
+    ap.add_argument("--cpu-side", type=int, default=50, help="lattice side of the cpu_baseline sample")
+    ap.add_argument("--ref-side", type=int, default=40, help="lattice side of the --impl reference sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        log(f"bench.py: --gpus {args.gpus} without torchrun: running rank 0 of 1 (launch with torch.distributed.run for N>1)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+/* pk_collide.h — C ABI of the B200-native collision stage for PhysKit.
+ *
+ * This library replaces, as a drop-in for that path only, the three collision calls of
+ * physkit::world::step_impl (reference src/world.cpp:30-46):
+ *
+ *   broad_phase().update_node(handle, obj.instance().bounds(), vel*dt)     collision_phases.h:371-375
+ *   broad_phase().calculate_pairs(narrow_phase(), get_node_handle)         collision_phases.h:377-436
+ *   narrow_phase().calculate(get_object, on_beg, on_end)  →  gjk_epa()     collision_phases.h:244-263
+ *                                                                           src/collision.cpp:512-518
+ *
+ * PhysKit has no FFI of its own; its extension point is the pure virtual world_base::step_impl
+ * (core/world.h:340).  INTEGRATION.md shows the gpu_world subclass a maintainer would add on top of
+ * this header.  Everything is plain pointers and sizes; no C++/torch types cross the boundary.
+ *
+ * Conventions
+ *   - all reals are IEEE double (reference float_t = double, algebra/types.h:8); results are
+ *     bit-identical to the reference arithmetic restated in oracle/pk_oracle.hpp (no FMA contraction)
+ *   - quaternions are x,y,z,w in memory (Eigen coeffs order, lin_alg.h:388)
+ *   - body id = index into the body arrays = the reference's arena slot index (core/world.h:205-206)
+ *   - pair key = (min_id << 32) | max_id                       (collision_phases.h:63-69)
+ *   - gjk_epa is always called as (a = lower id, b = higher id) (collision_phases.h:252-259)
+ *   - every function returns PK_OK (0) or a negative pk_status; nothing throws or aborts
+ *   - one ctx = one device + one CUDA stream; a ctx is not re-entrant, distinct ctxs are independent
+ *   - there is NO CPU fallback: without a CUDA device pk_create fails with PK_E_NO_DEVICE
+ */
+#ifndef PK_COLLIDE_H
+#define PK_COLLIDE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_ABI_VERSION 1
+
+typedef enum pk_status
+{
+    PK_OK = 0,
+    PK_E_INVALID = -1,       /* bad argument */
+    PK_E_NO_DEVICE = -2,     /* no usable CUDA device (never falls back to the CPU) */
+    PK_E_CUDA = -3,          /* CUDA runtime error; pk_last_error() has the text */
+    PK_E_OOM = -4,           /* device or pinned allocation failed */
+    PK_E_PAIR_OVERFLOW = -5, /* candidate pairs exceed pk_config.max_pairs; result.pairs_required set */
+    PK_E_EPA_OVERFLOW = -6,  /* an EPA polytope exceeded the per-pair scratch (result.epa_overflow) */
+    PK_E_STATE = -7          /* call order violated (e.g. results requested before pk_collide) */
+} pk_status;
+
+/* Pair-set semantics. */
+typedef enum pk_mode
+{
+    /* physkit::world behaviour: persistent fat AABBs (0.1 m margin + displacement, src/bvh.cpp:483-508),
+     * a pair exists iff the stored boxes intersect and one member was re-inserted since both exist
+     * (collision_phases.h:377-436).  The first step after creation yields no pairs. */
+    PK_MODE_WORLD = 0,
+    /* dynamic_bvh used directly (tests/dynamic_bvh/main.cpp:600-635): exact boxes, every
+     * intersecting (i<j) pair.  Stateless. */
+    PK_MODE_QUERY = 1
+} pk_mode;
+
+typedef struct pk_config
+{
+    int32_t device;        /* CUDA device ordinal */
+    int32_t mode;          /* pk_mode */
+    uint32_t max_bodies;   /* capacity of the body arrays */
+    uint32_t max_shapes;   /* capacity of the shape table */
+    uint64_t max_pairs;    /* capacity of the candidate-pair list */
+    uint64_t max_contacts; /* capacity of the contact list (0 = max_pairs) */
+    uint64_t max_hull_vertices; /* total vertices over all hull shapes */
+    uint32_t num_worlds;   /* >1: bodies carry a world id, pairs only form inside a world (0/1 = single) */
+    uint32_t shard_rank;   /* pair sharding of one world across ranks: this ctx traverses the */
+    uint32_t shard_count;  /*   sorted-leaf slice [rank*N/count, (rank+1)*N/count); 0/1 = whole scene */
+    uint32_t flags;        /* reserved, 0 */
+} pk_config;
+
+typedef struct pk_ctx pk_ctx;
+
+/* 88-byte contact record = collision_info (collision.h:52-59) + its pair key.
+ * normal points from B to A; depth = EPA face distance (src/collision.cpp:448-453). */
+typedef struct pk_contact
+{
+    uint64_t key;
+    double normal[3];
+    double world_a[3];
+    double world_b[3];
+    double depth;
+} pk_contact;
+
+typedef struct pk_step_result
+{
+    uint64_t num_pairs;      /* candidate pairs produced by the broadphase (this shard) */
+    uint64_t num_contacts;   /* pairs for which gjk_epa returned a value */
+    uint64_t num_moved;      /* leaves re-inserted this step (|M_moved|, collision_phases.h:374) */
+    uint64_t pairs_required; /* on PK_E_PAIR_OVERFLOW: the capacity that would have sufficed */
+    uint64_t epa_overflow;   /* pairs whose EPA polytope overflowed the scratch (0 in normal use) */
+    uint64_t gjk_hits;       /* pairs whose GJK simplex enclosed the origin (≥ num_contacts) */
+    float ms_broadphase;     /* device time of the stages, CUDA events on the ctx stream */
+    float ms_narrowphase;
+    float ms_total;
+    uint32_t step_index;     /* epoch counter of this ctx */
+} pk_step_result;
+
+/* Per-kernel device times of the last pk_collide (CUDA events), for bench.py's roofline line. */
+#define PK_NUM_STAGES 12
+typedef struct pk_stage_times
+{
+    float ms[PK_NUM_STAGES];
+    const char *name[PK_NUM_STAGES];
+    uint32_t launches; /* kernels launched by the last pk_collide */
+} pk_stage_times;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int pk_abi_version(void);
+int pk_create(const pk_config *cfg, pk_ctx **out);
+int pk_destroy(pk_ctx *ctx);
+const char *pk_strerror(int status);
+const char *pk_last_error(pk_ctx *ctx);
+
+/* ---- shapes (SupportShape models, collision.h:35-38) ------------------------------------------
+ * Each returns the new shape id.  Inputs are copied; the caller keeps ownership. */
+int pk_shape_box(pk_ctx *ctx, const double half[3], uint32_t *id);       /* obb::support bounds.h:539-548 */
+int pk_shape_sphere(pk_ctx *ctx, double radius, uint32_t *id);           /* bounding_sphere::support bounds.h:328-329 */
+int pk_shape_hull(pk_ctx *ctx, const double *xyz, uint32_t nverts, uint32_t *id); /* mesh::support mesh.cpp:341-358 */
+int pk_shape_aabb(pk_ctx *ctx, const double min[3], const double max[3], uint32_t *id); /* aabb::support bounds.h:164-174; pose-less */
+/* Bulk variant: n boxes / spheres in one H2D copy. kind: 1 = box (par = half xyz), 2 = sphere (par[0] = r). */
+int pk_shapes_bulk(pk_ctx *ctx, const int32_t *kind, const double *par3, uint32_t n, uint32_t *first_id);
+
+/* ---- bodies ---------------------------------------------------------------------------------
+ * flags bit0 = static (never updated, never queries: src/world.cpp:24), bit1 = alive.
+ * A body whose alive bit rises is create_rigid()'d (exact box, not marked moved: core/world.h:202-208,
+ * collision_phases.h:342-346); one whose alive bit falls is remove_rigid()'d.
+ * disp = vel*dt, the predictive expansion passed to update_node (src/world.cpp:30-31).
+ * world_id may be NULL when num_worlds <= 1. */
+int pk_bodies_resize(pk_ctx *ctx, uint32_t n);
+int pk_bodies_upload(pk_ctx *ctx, const double *pos_xyz, const double *quat_xyzw, const double *disp_xyz,
+                     const uint32_t *shape_id, const uint8_t *flags, const uint32_t *world_id,
+                     uint32_t first, uint32_t count);
+/* Pose-only refresh (the per-step H2D of a running world). Any pointer may be NULL = unchanged. */
+int pk_bodies_update_pose(pk_ctx *ctx, const double *pos_xyz, const double *quat_xyzw, const double *disp_xyz,
+                          uint32_t first, uint32_t count);
+
+/* ---- the collision stage --------------------------------------------------------------------
+ * pk_collide_resident: run broadphase + narrowphase on the state already in HBM; only the counters
+ *   come back to the host.  Results stay on the device.
+ * pk_fetch_results:    D2H of pair keys and contact records into ctx-owned pinned memory.
+ * pk_collide:          both (what gpu_world::step_impl calls).
+ * Pairs are sorted ascending by key; contacts are sorted by key as well. */
+int pk_collide_resident(pk_ctx *ctx, pk_step_result *out);
+int pk_fetch_results(pk_ctx *ctx);
+int pk_collide(pk_ctx *ctx, pk_step_result *out);
+int pk_pairs(pk_ctx *ctx, const uint64_t **keys, uint64_t *n);
+int pk_contacts(pk_ctx *ctx, const pk_contact **recs, uint64_t *n);
+/* Device-side views for a caller that exchanges results itself (NCCL all-gather of contacts). */
+int pk_pairs_device(pk_ctx *ctx, const void **dptr, uint64_t *n);
+int pk_contacts_device(pk_ctx *ctx, const void **dptr, uint64_t *n);
+/* Stored (fat) boxes of the broadphase, [count][6] = min xyz, max xyz (dynamic_bvh::bounds, bvh.h:452-456). */
+int pk_stored_bounds(pk_ctx *ctx, double *out6, uint32_t first, uint32_t count);
+int pk_stage_times_get(pk_ctx *ctx, pk_stage_times *out);
+/* CUDA stream of the ctx as a void* (cudaStream_t) so a host can order its own work after it. */
+int pk_stream(pk_ctx *ctx, void **stream);
+
+/* ---- narrowphase only: gjk_epa over an explicit pair list (BASELINE config C4) ----------------
+ * pair_a/pair_b index the uploaded bodies; out[k] / hit[k] are written for every k (host pointers).
+ * out[k].key = make_pair_key as given (a<<32|b, NOT min/max: argument order is the caller's). */
+int pk_gjk_epa_batch(pk_ctx *ctx, const uint32_t *pair_a, const uint32_t *pair_b, uint64_t n,
+                     pk_contact *out, uint8_t *hit);
+/* Same with the pair list and outputs resident in HBM (device pointers); returns device ms. */
+int pk_gjk_epa_batch_device(pk_ctx *ctx, const uint32_t *d_pair_a, const uint32_t *d_pair_b, uint64_t n,
+                            pk_contact *d_out, uint8_t *d_hit, float *ms);
+
+/* Raw device allocation helpers so a host language without CUDA bindings can stage buffers. */
+int pk_device_alloc(pk_ctx *ctx, size_t bytes, void **dptr);
+int pk_device_free(pk_ctx *ctx, void *dptr);
+int pk_memcpy_h2d(pk_ctx *ctx, void *dst, const void *src, size_t bytes);
+int pk_memcpy_d2h(pk_ctx *ctx, void *dst, const void *src, size_t bytes);
+int pk_memcpy_d2d(pk_ctx *ctx, void *dst, const void *src, size_t bytes); /* e.g. contacts → an NCCL send buffer */
+/* Page-locked host memory for the per-step pose arrays (makes pk_bodies_upload a true async DMA). */
+int pk_host_alloc(pk_ctx *ctx, size_t bytes, void **hptr);
+int pk_host_free(pk_ctx *ctx, void *hptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PK_COLLIDE_H */

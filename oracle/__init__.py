@@ -186,9 +186,9 @@ def gjk_epa_pairs(shapes, pos, quat, shape_id, pair_a, pair_b, stats=False, nthr
     pa = np.ascontiguousarray(pair_a, dtype=np.uint32)
     pb = np.ascontiguousarray(pair_b, dtype=np.uint32)
     n = len(pa)
-    out = np.zeros((n, 10))
-    hit = np.zeros(n, dtype=np.uint8)
-    st = np.zeros((n, 8), dtype=np.int32) if stats else None
+    out = np.empty((n, 10))  # every row is written by the C side
+    hit = np.empty(n, dtype=np.uint8)
+    st = np.empty((n, 8), dtype=np.int32) if stats else None
     lib().pko_gjk_epa_pairs(
         _p(t.tab), _p(t.verts), _p(pos), _p(quat), _p(sid), _p(pa), _p(pb), n, _p(out), _p(hit), _p(st), int(nthreads)
     )

@@ -1,0 +1,971 @@
+// pk_api.cu — context, memory and the C ABI of include/pk_collide.h.
+//
+// One ctx = one device, one stream.  All hot-path state lives in HBM for the lifetime of the ctx
+// (SoA body arrays, shape table, LBVH, pair keys, simplices, EPA slabs, contacts); a step touches
+// the host only to read two counters.  There is no CPU implementation of any stage in this file:
+// if no CUDA device is usable pk_create fails and every other entry point needs a ctx.
+#include "../../include/pk_collide.h"
+
+#include "pk_broadphase.cuh"
+#include "pk_common.cuh"
+#include "pk_narrowphase.cuh"
+#include "pk_sort.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace pk;
+
+namespace
+{
+
+enum Stage
+{
+    ST_BOUNDS = 0,
+    ST_MORTON,
+    ST_BODY_SORT,
+    ST_LEAVES,
+    ST_HIERARCHY,
+    ST_OVERLAP,
+    ST_PAIR_SORT,
+    ST_GJK,
+    ST_SCAN,
+    ST_EPA,
+    ST_COMPACT,
+    ST_FETCH,
+    ST_COUNT
+};
+static_assert(ST_COUNT == PK_NUM_STAGES, "stage table out of sync with pk_collide.h");
+const char *const kStageNames[ST_COUNT] = {"bounds_fat", "morton",    "body_sort", "leaves",  "hierarchy_ropes", "overlap",
+                                           "pair_sort",  "gjk",       "hit_scan",  "epa",     "compact",         "fetch_d2h"};
+
+// counters in device memory (unsigned long long each)
+enum Counter
+{
+    C_PAIRS = 0,
+    C_MOVED,
+    C_HITS,
+    C_EPA_CURSOR,
+    C_VALID,
+    C_EPA_OVERFLOW,
+    C_SCAN_TOTAL,
+    C_COUNT = 8
+};
+
+} // namespace
+
+struct pk_ctx
+{
+    pk_config cfg{};
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int sm_count = 0;
+
+    // shapes
+    std::vector<ShapeRec> h_shapes;
+    std::vector<double> h_verts;
+    bool shapes_dirty = false;
+    ShapeRec *d_shapes = nullptr;
+    double *d_verts = nullptr;
+
+    // bodies
+    uint32_t n_bodies = 0;
+    std::vector<uint8_t> h_flags;
+    uint32_t n_alive = 0;
+    bool alive_dirty = true;
+    double *d_pos = nullptr, *d_quat = nullptr, *d_disp = nullptr;
+    uint32_t *d_shape_id = nullptr, *d_world = nullptr;
+    uint8_t *d_flags = nullptr;
+    bool have_world = false;
+    BodyState st{};
+
+    // broadphase
+    uint32_t *d_scene = nullptr;
+    unsigned long long *d_counters = nullptr;
+    unsigned long long *h_counters = nullptr; // pinned
+    uint64_t *d_bkeys[2] = {nullptr, nullptr};
+    uint32_t *d_bvals[2] = {nullptr, nullptr};
+    uint32_t *d_tile_hist = nullptr, *d_digit_total = nullptr;
+    size_t tile_hist_entries = 0;
+    LeafRec *d_leaves = nullptr;
+    NodeF *d_nodes = nullptr;
+    uint32_t *d_right = nullptr, *d_range_last = nullptr, *d_root = nullptr;
+    int32_t *d_merge_flag = nullptr;
+    uint64_t *d_pkeys[2] = {nullptr, nullptr};
+    uint64_t *d_pairs_sorted = nullptr; // points into d_pkeys
+
+    // narrowphase
+    uint64_t max_contacts = 0;
+    uint8_t *d_hit = nullptr;
+    uint32_t *d_out_index = nullptr, *d_scan_tiles = nullptr;
+    SimplexRec *d_simplices = nullptr;
+    ContactRec *d_contacts[2] = {nullptr, nullptr};
+    ContactRec *d_contacts_final = nullptr;
+    uint8_t *d_valid = nullptr;
+    uint32_t *d_valid_index = nullptr;
+    unsigned char *d_slabs = nullptr;
+    uint32_t epa_blocks = 0;
+
+    // results
+    int32_t epoch = 0;
+    bool have_results = false, fetched = false;
+    uint64_t num_pairs = 0, num_contacts = 0;
+    uint64_t *h_pairs = nullptr;
+    size_t h_pairs_cap = 0;
+    pk_contact *h_contacts = nullptr;
+    size_t h_contacts_cap = 0;
+
+    cudaEvent_t ev[ST_COUNT + 1]{};
+    float stage_ms[ST_COUNT]{};
+    uint32_t launches = 0;
+};
+
+namespace
+{
+
+#define PK_CUDA(call)                                                                                     \
+    do                                                                                                    \
+    {                                                                                                     \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+        {                                                                                                 \
+            ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return (e__ == cudaErrorMemoryAllocation) ? PK_E_OOM : PK_E_CUDA;                             \
+        }                                                                                                 \
+    } while (0)
+
+template <typename T> int dev_alloc(pk_ctx *ctx, T **p, size_t count)
+{
+    if (count == 0) count = 1;
+    PK_CUDA(cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T)));
+    return PK_OK;
+}
+#define PK_TRY(expr)              \
+    do                            \
+    {                             \
+        int s__ = (expr);         \
+        if (s__ != PK_OK) return s__; \
+    } while (0)
+
+inline uint32_t div_up(uint64_t a, uint64_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
+
+int bits_for(uint64_t n) // bits needed to represent values < n
+{
+    int b = 1;
+    while (b < 64 && (1ull << b) < n) ++b;
+    return b;
+}
+
+// LSD radix sort over the listed byte shifts; returns the index (0/1) of the buffer holding the result.
+int radix_sort(pk_ctx *ctx, uint64_t *keys[2], uint32_t *vals[2], uint64_t n, const std::vector<int> &shifts, int *result)
+{
+    int cur = 0;
+    uint32_t ntiles = div_up(n, SORT_TILE);
+    if (static_cast<size_t>(ntiles) * 256 > ctx->tile_hist_entries)
+    {
+        ctx->last_error = "radix sort scratch too small";
+        return PK_E_STATE;
+    }
+    for (int shift : shifts)
+    {
+        radix_hist_kernel<<<ntiles, SORT_THREADS, 0, ctx->stream>>>(keys[cur], n, shift, ctx->d_tile_hist, ntiles);
+        radix_scan_kernel<<<256, SORT_THREADS, 0, ctx->stream>>>(ctx->d_tile_hist, ntiles, ctx->d_digit_total);
+        if (vals)
+            radix_scatter_kernel<true><<<ntiles, SORT_THREADS, 0, ctx->stream>>>(
+                keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
+        else
+            radix_scatter_kernel<false><<<ntiles, SORT_THREADS, 0, ctx->stream>>>(
+                keys[cur], nullptr, keys[cur ^ 1], nullptr, n, shift, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
+        ctx->launches += 3;
+        cur ^= 1;
+    }
+    PK_CUDA(cudaGetLastError());
+    *result = cur;
+    return PK_OK;
+}
+
+int upload_shapes(pk_ctx *ctx)
+{
+    if (!ctx->shapes_dirty) return PK_OK;
+    if (!ctx->h_shapes.empty())
+        PK_CUDA(cudaMemcpyAsync(ctx->d_shapes, ctx->h_shapes.data(), ctx->h_shapes.size() * sizeof(ShapeRec),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->h_verts.empty())
+        PK_CUDA(cudaMemcpyAsync(ctx->d_verts, ctx->h_verts.data(), ctx->h_verts.size() * sizeof(double),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream)); // host vectors may be reallocated by the next pk_shape_*
+    ctx->shapes_dirty = false;
+    return PK_OK;
+}
+
+int add_shape(pk_ctx *ctx, const ShapeRec &r, uint32_t *id)
+{
+    if (!ctx || !id) return PK_E_INVALID;
+    if (ctx->h_shapes.size() >= ctx->cfg.max_shapes)
+    {
+        ctx->last_error = "shape table full (pk_config.max_shapes)";
+        return PK_E_INVALID;
+    }
+    *id = static_cast<uint32_t>(ctx->h_shapes.size());
+    ctx->h_shapes.push_back(r);
+    ctx->shapes_dirty = true;
+    return PK_OK;
+}
+
+BodyArrays body_arrays(pk_ctx *ctx)
+{
+    BodyArrays b;
+    b.shapes = ctx->d_shapes;
+    b.verts = ctx->d_verts;
+    b.pos = ctx->d_pos;
+    b.quat = ctx->d_quat;
+    b.shape_id = ctx->d_shape_id;
+    return b;
+}
+
+// GJK → scan → EPA over npairs pairs given either as sorted keys or as explicit index arrays.
+// Leaves contacts (slot order = pair order among GJK hits) in ctx->d_contacts[0], validity in d_valid.
+int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, const uint32_t *d_b, uint64_t npairs,
+                    bool timed)
+{
+    if (timed) cudaEventRecord(ctx->ev[ST_GJK], ctx->stream);
+    if (npairs)
+    {
+        gjk_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit,
+                                                                 ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts);
+        ctx->launches += 1;
+    }
+    if (timed) cudaEventRecord(ctx->ev[ST_SCAN], ctx->stream);
+    if (npairs)
+    {
+        uint32_t nt = div_up(npairs, SCAN_TILE);
+        flag_tile_sum_kernel<<<nt, 256, 0, ctx->stream>>>(ctx->d_hit, npairs, ctx->d_scan_tiles);
+        tile_sum_scan_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_scan_tiles, nt, ctx->d_counters + C_SCAN_TOTAL);
+        flag_scan_apply_kernel<<<nt, 256, 0, ctx->stream>>>(ctx->d_hit, npairs, ctx->d_scan_tiles, ctx->d_out_index);
+        ctx->launches += 3;
+    }
+    if (timed) cudaEventRecord(ctx->ev[ST_EPA], ctx->stream);
+    if (npairs)
+    {
+        epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
+            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
+            ctx->d_out_index, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs, ctx->d_counters + C_EPA_CURSOR,
+            ctx->d_counters + C_VALID);
+        ctx->launches += 1;
+    }
+    if (timed) cudaEventRecord(ctx->ev[ST_COMPACT], ctx->stream);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+int read_counters(pk_ctx *ctx)
+{
+    PK_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, C_COUNT * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+
+} // namespace
+
+extern "C"
+{
+
+int pk_abi_version(void) { return PK_ABI_VERSION; }
+
+const char *pk_strerror(int status)
+{
+    switch (status)
+    {
+    case PK_OK: return "ok";
+    case PK_E_INVALID: return "invalid argument";
+    case PK_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case PK_E_CUDA: return "CUDA runtime error";
+    case PK_E_OOM: return "out of device or pinned memory";
+    case PK_E_PAIR_OVERFLOW: return "candidate pair / contact capacity exceeded";
+    case PK_E_EPA_OVERFLOW: return "EPA polytope scratch exceeded";
+    case PK_E_STATE: return "call order violated";
+    default: return "unknown status";
+    }
+}
+
+const char *pk_last_error(pk_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int pk_destroy(pk_ctx *ctx)
+{
+    if (!ctx) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void *dev[] = {ctx->d_shapes,      ctx->d_verts,        ctx->d_pos,         ctx->d_quat,         ctx->d_disp,
+                   ctx->d_shape_id,    ctx->d_world,        ctx->d_flags,       ctx->st.stored,      ctx->st.last_move,
+                   ctx->st.create,     ctx->st.alive,       ctx->d_scene,       ctx->d_counters,     ctx->d_bkeys[0],
+                   ctx->d_bkeys[1],    ctx->d_bvals[0],     ctx->d_bvals[1],    ctx->d_tile_hist,    ctx->d_digit_total,
+                   ctx->d_leaves,      ctx->d_nodes,        ctx->d_right,       ctx->d_range_last,   ctx->d_root,
+                   ctx->d_merge_flag,  ctx->d_pkeys[0],     ctx->d_pkeys[1],    ctx->d_hit,          ctx->d_out_index,
+                   ctx->d_scan_tiles,  ctx->d_simplices,    ctx->d_contacts[0], ctx->d_contacts[1],  ctx->d_valid,
+                   ctx->d_valid_index, ctx->d_slabs};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_pairs) cudaFreeHost(ctx->h_pairs);
+    if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PK_OK;
+}
+
+int pk_create(const pk_config *cfg, pk_ctx **out)
+{
+    if (!cfg || !out) return PK_E_INVALID;
+    *out = nullptr;
+    if (cfg->max_bodies == 0 || cfg->max_pairs == 0 || cfg->max_shapes == 0) return PK_E_INVALID;
+    if (cfg->mode != PK_MODE_WORLD && cfg->mode != PK_MODE_QUERY) return PK_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev)
+        return PK_E_NO_DEVICE;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return PK_E_NO_DEVICE;
+    pk_ctx *ctx = new (std::nothrow) pk_ctx();
+    if (!ctx) return PK_E_OOM;
+    ctx->cfg = *cfg;
+    if (ctx->cfg.num_worlds == 0) ctx->cfg.num_worlds = 1;
+    if (ctx->cfg.shard_count == 0) ctx->cfg.shard_count = 1;
+    if (ctx->cfg.shard_rank >= ctx->cfg.shard_count)
+    {
+        delete ctx;
+        return PK_E_INVALID;
+    }
+    ctx->max_contacts = cfg->max_contacts ? cfg->max_contacts : cfg->max_pairs;
+    auto fail = [&](int s)
+    {
+        pk_destroy(ctx);
+        return s;
+    };
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(PK_E_NO_DEVICE);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(PK_E_CUDA);
+    for (auto &e : ctx->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return fail(PK_E_CUDA);
+
+    const size_t nb = cfg->max_bodies;
+    const size_t np = cfg->max_pairs;
+    const size_t nc = ctx->max_contacts;
+    int s;
+#define A(ptr, count)                                   \
+    if ((s = dev_alloc(ctx, &(ptr), (count))) != PK_OK) \
+    return fail(s)
+    A(ctx->d_shapes, cfg->max_shapes);
+    A(ctx->d_verts, cfg->max_hull_vertices * 3 + 2);
+    A(ctx->d_pos, nb * 3);
+    A(ctx->d_quat, nb * 4);
+    A(ctx->d_disp, nb * 3);
+    A(ctx->d_shape_id, nb);
+    A(ctx->d_world, nb);
+    A(ctx->d_flags, nb);
+    A(ctx->st.stored, nb * 6);
+    A(ctx->st.last_move, nb);
+    A(ctx->st.create, nb);
+    A(ctx->st.alive, nb);
+    A(ctx->d_scene, 8);
+    A(ctx->d_counters, C_COUNT);
+    A(ctx->d_bkeys[0], nb);
+    A(ctx->d_bkeys[1], nb);
+    A(ctx->d_bvals[0], nb);
+    A(ctx->d_bvals[1], nb);
+    ctx->tile_hist_entries = static_cast<size_t>(div_up(std::max(nb, np), SORT_TILE)) * 256;
+    A(ctx->d_tile_hist, ctx->tile_hist_entries);
+    A(ctx->d_digit_total, 256);
+    A(ctx->d_leaves, nb);
+    A(ctx->d_nodes, 2 * nb);
+    A(ctx->d_right, nb);
+    A(ctx->d_range_last, nb);
+    A(ctx->d_root, 1);
+    A(ctx->d_merge_flag, nb);
+    A(ctx->d_pkeys[0], np);
+    A(ctx->d_pkeys[1], np);
+    A(ctx->d_hit, np + 16);
+    A(ctx->d_out_index, np);
+    A(ctx->d_scan_tiles, div_up(np, SCAN_TILE) + 1);
+    A(ctx->d_simplices, nc);
+    A(ctx->d_contacts[0], nc);
+    A(ctx->d_contacts[1], nc);
+    A(ctx->d_valid, nc + 16);
+    A(ctx->d_valid_index, nc);
+    // persistent EPA grid: enough resident threads to fill the machine, never more than the work
+    {
+        uint64_t want_threads = static_cast<uint64_t>(ctx->sm_count) * 5 * EPA_THREADS;
+        uint64_t need_threads = ((nc + EPA_THREADS - 1) / EPA_THREADS) * EPA_THREADS;
+        uint64_t threads = std::min(want_threads, std::max<uint64_t>(need_threads, EPA_THREADS));
+        ctx->epa_blocks = static_cast<uint32_t>(threads / EPA_THREADS);
+        A(ctx->d_slabs, threads * EPA_SLAB_BYTES);
+    }
+#undef A
+    if (cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_counters), C_COUNT * sizeof(unsigned long long),
+                      cudaHostAllocDefault) != cudaSuccess)
+        return fail(PK_E_OOM);
+    cudaMemsetAsync(ctx->st.alive, 0, nb, ctx->stream);
+    cudaMemsetAsync(ctx->d_flags, 0, nb, ctx->stream);
+    cudaMemsetAsync(ctx->d_world, 0, nb * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(ctx->d_disp, 0, nb * 3 * sizeof(double), ctx->stream);
+    cudaMemsetAsync(ctx->d_hit, 0, np + 16, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(PK_E_CUDA);
+    ctx->h_flags.assign(nb, 0);
+    *out = ctx;
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ shapes
+int pk_shape_box(pk_ctx *ctx, const double half[3], uint32_t *id)
+{
+    if (!ctx || !half) return PK_E_INVALID;
+    ShapeRec r{};
+    r.kind = KIND_OBB;
+    for (int k = 0; k < 3; ++k) r.a[k] = half[k];
+    return add_shape(ctx, r, id);
+}
+
+int pk_shape_sphere(pk_ctx *ctx, double radius, uint32_t *id)
+{
+    if (!ctx) return PK_E_INVALID;
+    ShapeRec r{};
+    r.kind = KIND_SPHERE;
+    r.a[0] = radius;
+    return add_shape(ctx, r, id);
+}
+
+int pk_shape_aabb(pk_ctx *ctx, const double mn[3], const double mx[3], uint32_t *id)
+{
+    if (!ctx || !mn || !mx) return PK_E_INVALID;
+    ShapeRec r{};
+    r.kind = KIND_AABB;
+    for (int k = 0; k < 3; ++k) r.a[k] = mn[k], r.b[k] = mx[k];
+    return add_shape(ctx, r, id);
+}
+
+int pk_shape_hull(pk_ctx *ctx, const double *xyz, uint32_t nverts, uint32_t *id)
+{
+    if (!ctx || !xyz || nverts == 0) return PK_E_INVALID;
+    size_t off = ctx->h_verts.size() / 3;
+    if (off + nverts > ctx->cfg.max_hull_vertices)
+    {
+        ctx->last_error = "hull vertex pool full (pk_config.max_hull_vertices)";
+        return PK_E_INVALID;
+    }
+    ShapeRec r{};
+    r.kind = KIND_HULL;
+    r.vert_off = static_cast<uint32_t>(off);
+    r.nverts = nverts;
+    // aabb::from_points (bounds.h:33-49): the mesh-local box that instance::bounds() rotates
+    for (int k = 0; k < 3; ++k) r.a[k] = r.b[k] = xyz[k];
+    for (uint32_t i = 1; i < nverts; ++i)
+        for (int k = 0; k < 3; ++k)
+        {
+            r.a[k] = std::min(r.a[k], xyz[3 * i + k]);
+            r.b[k] = std::max(r.b[k], xyz[3 * i + k]);
+        }
+    int s = add_shape(ctx, r, id);
+    if (s != PK_OK) return s;
+    ctx->h_verts.insert(ctx->h_verts.end(), xyz, xyz + 3ull * nverts);
+    return PK_OK;
+}
+
+int pk_shapes_bulk(pk_ctx *ctx, const int32_t *kind, const double *par3, uint32_t n, uint32_t *first_id)
+{
+    if (!ctx || !kind || !par3) return PK_E_INVALID;
+    if (ctx->h_shapes.size() + n > ctx->cfg.max_shapes)
+    {
+        ctx->last_error = "shape table full (pk_config.max_shapes)";
+        return PK_E_INVALID;
+    }
+    if (first_id) *first_id = static_cast<uint32_t>(ctx->h_shapes.size());
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        ShapeRec r{};
+        if (kind[i] == KIND_OBB)
+        {
+            r.kind = KIND_OBB;
+            for (int k = 0; k < 3; ++k) r.a[k] = par3[3 * i + k];
+        }
+        else if (kind[i] == KIND_SPHERE)
+        {
+            r.kind = KIND_SPHERE;
+            r.a[0] = par3[3 * i];
+        }
+        else
+            return PK_E_INVALID;
+        ctx->h_shapes.push_back(r);
+    }
+    ctx->shapes_dirty = true;
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ bodies
+int pk_bodies_resize(pk_ctx *ctx, uint32_t n)
+{
+    if (!ctx || n > ctx->cfg.max_bodies) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    if (n < ctx->n_bodies)
+    {
+        // bodies beyond n are destroyed
+        std::fill(ctx->h_flags.begin() + n, ctx->h_flags.begin() + ctx->n_bodies, 0);
+        PK_CUDA(cudaMemsetAsync(ctx->d_flags + n, 0, ctx->n_bodies - n, ctx->stream));
+        PK_CUDA(cudaMemsetAsync(ctx->st.alive + n, 0, ctx->n_bodies - n, ctx->stream));
+    }
+    ctx->n_bodies = n;
+    ctx->alive_dirty = true;
+    return PK_OK;
+}
+
+int pk_bodies_upload(pk_ctx *ctx, const double *pos, const double *quat, const double *disp, const uint32_t *shape_id,
+                     const uint8_t *flags, const uint32_t *world_id, uint32_t first, uint32_t count)
+{
+    if (!ctx || !pos || !quat || !shape_id || !flags) return PK_E_INVALID;
+    if (static_cast<uint64_t>(first) + count > ctx->n_bodies) return PK_E_INVALID;
+    if (count == 0) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    for (uint32_t i = 0; i < count; ++i)
+        if ((flags[i] & FLAG_ALIVE) && shape_id[i] >= ctx->h_shapes.size())
+        {
+            ctx->last_error = "shape id out of range";
+            return PK_E_INVALID;
+        }
+    cudaStream_t s = ctx->stream;
+    PK_CUDA(cudaMemcpyAsync(ctx->d_pos + 3ull * first, pos, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(ctx->d_quat + 4ull * first, quat, 4ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (disp)
+        PK_CUDA(cudaMemcpyAsync(ctx->d_disp + 3ull * first, disp, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(ctx->d_shape_id + first, shape_id, count * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(ctx->d_flags + first, flags, count, cudaMemcpyHostToDevice, s));
+    if (world_id)
+    {
+        PK_CUDA(cudaMemcpyAsync(ctx->d_world + first, world_id, count * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        ctx->have_world = true;
+    }
+    std::memcpy(ctx->h_flags.data() + first, flags, count);
+    ctx->alive_dirty = true;
+    return PK_OK;
+}
+
+int pk_bodies_update_pose(pk_ctx *ctx, const double *pos, const double *quat, const double *disp, uint32_t first,
+                          uint32_t count)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (static_cast<uint64_t>(first) + count > ctx->n_bodies) return PK_E_INVALID;
+    if (count == 0) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t s = ctx->stream;
+    if (pos)
+        PK_CUDA(cudaMemcpyAsync(ctx->d_pos + 3ull * first, pos, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (quat)
+        PK_CUDA(cudaMemcpyAsync(ctx->d_quat + 4ull * first, quat, 4ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (disp)
+        PK_CUDA(cudaMemcpyAsync(ctx->d_disp + 3ull * first, disp, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ the stage
+int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
+{
+    if (!ctx) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    PK_TRY(upload_shapes(ctx));
+    ctx->have_results = false;
+    ctx->fetched = false;
+    ctx->launches = 0;
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = ctx->n_bodies;
+    const int mode_query = ctx->cfg.mode == PK_MODE_QUERY;
+    if (ctx->alive_dirty)
+    {
+        uint32_t c = 0;
+        for (uint32_t i = 0; i < n; ++i) c += (ctx->h_flags[i] & FLAG_ALIVE) ? 1u : 0u;
+        ctx->n_alive = c;
+        ctx->alive_dirty = false;
+    }
+    const uint32_t m = ctx->n_alive;
+    WorldTiling wt;
+    wt.num_worlds = ctx->cfg.num_worlds;
+    wt.grid = 1;
+    while (static_cast<uint64_t>(wt.grid) * wt.grid * wt.grid < wt.num_worlds) ++wt.grid;
+    const uint32_t *d_world = (ctx->cfg.num_worlds > 1 && ctx->have_world) ? ctx->d_world : nullptr;
+
+    cudaEventRecord(ctx->ev[ST_BOUNDS], s);
+    scene_reset_kernel<<<1, 32, 0, s>>>(ctx->d_scene, ctx->d_counters, C_COUNT);
+    ctx->launches += 1;
+    if (n)
+    {
+        bounds_fat_kernel<<<div_up(n, 256), 256, 0, s>>>(ctx->d_shapes, ctx->d_pos, ctx->d_quat, ctx->d_disp, ctx->d_shape_id,
+                                                         ctx->d_flags, n, mode_query, ctx->epoch, ctx->st, ctx->d_scene,
+                                                         ctx->d_counters + C_MOVED);
+        ctx->launches += 1;
+    }
+    cudaEventRecord(ctx->ev[ST_MORTON], s);
+    uint64_t npairs = 0;
+    int pair_buf = 0;
+    if (m >= 2)
+    {
+        morton_kernel<<<div_up(n, 256), 256, 0, s>>>(ctx->st.stored, ctx->st.alive, d_world, n, ctx->d_scene, wt,
+                                                     ctx->d_bkeys[0], ctx->d_bvals[0]);
+        ctx->launches += 1;
+        cudaEventRecord(ctx->ev[ST_BODY_SORT], s);
+        int bres = 0;
+        PK_TRY(radix_sort(ctx, ctx->d_bkeys, ctx->d_bvals, n, {0, 8, 16, 24}, &bres));
+        cudaEventRecord(ctx->ev[ST_LEAVES], s);
+        leaf_kernel<<<div_up(m, 256), 256, 0, s>>>(ctx->d_bvals[bres], m, ctx->st.stored, ctx->st.last_move, ctx->st.create,
+                                                   d_world, ctx->d_scene, wt, ctx->d_leaves, ctx->d_nodes, ctx->d_merge_flag);
+        cudaEventRecord(ctx->ev[ST_HIERARCHY], s);
+        hierarchy_kernel<<<div_up(m, 256), 256, 0, s>>>(ctx->d_bkeys[bres], m, ctx->d_nodes, ctx->d_right, ctx->d_range_last,
+                                                        ctx->d_merge_flag, ctx->d_root);
+        rope_kernel<<<div_up(2ull * m - 1, 256), 256, 0, s>>>(m, ctx->d_nodes, ctx->d_right, ctx->d_range_last);
+        cudaEventRecord(ctx->ev[ST_OVERLAP], s);
+        uint32_t p_begin = static_cast<uint32_t>(static_cast<uint64_t>(m) * ctx->cfg.shard_rank / ctx->cfg.shard_count);
+        uint32_t p_end = static_cast<uint32_t>(static_cast<uint64_t>(m) * (ctx->cfg.shard_rank + 1) / ctx->cfg.shard_count);
+        if (p_end > p_begin)
+            overlap_kernel<<<div_up(p_end - p_begin, 128), 128, 0, s>>>(ctx->d_nodes, ctx->d_leaves, m, p_begin, p_end, mode_query,
+                                                                       ctx->d_pkeys[0], ctx->cfg.max_pairs,
+                                                                       ctx->d_counters + C_PAIRS);
+        ctx->launches += 4;
+        PK_CUDA(cudaGetLastError());
+        cudaEventRecord(ctx->ev[ST_PAIR_SORT], s);
+        PK_TRY(read_counters(ctx));
+        npairs = ctx->h_counters[C_PAIRS];
+        if (npairs > ctx->cfg.max_pairs)
+        {
+            if (out)
+            {
+                std::memset(out, 0, sizeof(*out));
+                out->pairs_required = npairs;
+                out->num_moved = ctx->h_counters[C_MOVED];
+                out->step_index = static_cast<uint32_t>(ctx->epoch);
+            }
+            ctx->last_error = "candidate pairs exceed pk_config.max_pairs";
+            ctx->epoch += 1; // the fat-box state has advanced; the step cannot be replayed
+            return PK_E_PAIR_OVERFLOW;
+        }
+        if (npairs)
+        {
+            int idbits = bits_for(n);
+            std::vector<int> shifts;
+            for (int b = 0; b < idbits; b += 8) shifts.push_back(b);
+            for (int b = 0; b < idbits; b += 8) shifts.push_back(32 + b);
+            PK_TRY(radix_sort(ctx, ctx->d_pkeys, nullptr, npairs, shifts, &pair_buf));
+        }
+    }
+    else
+    {
+        for (int k = ST_BODY_SORT; k <= ST_PAIR_SORT; ++k) cudaEventRecord(ctx->ev[k], s);
+    }
+    ctx->d_pairs_sorted = ctx->d_pkeys[pair_buf];
+    PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true));
+    PK_TRY(read_counters(ctx));
+    uint64_t hits = ctx->h_counters[C_HITS];
+    uint64_t valid = ctx->h_counters[C_VALID];
+    uint64_t over = ctx->h_counters[C_EPA_OVERFLOW];
+    int status = PK_OK;
+    if (hits > ctx->max_contacts)
+    {
+        ctx->last_error = "GJK hits exceed pk_config.max_contacts";
+        status = PK_E_PAIR_OVERFLOW;
+        hits = ctx->max_contacts;
+    }
+    ctx->d_contacts_final = ctx->d_contacts[0];
+    if (status == PK_OK && valid != hits)
+    {
+        // some GJK hits ended without a value in EPA (degenerate pad / exhausted heap / overflow)
+        uint32_t nt = div_up(hits, SCAN_TILE);
+        flag_tile_sum_kernel<<<nt, 256, 0, s>>>(ctx->d_valid, hits, ctx->d_scan_tiles);
+        tile_sum_scan_kernel<<<1, 256, 0, s>>>(ctx->d_scan_tiles, nt, nullptr);
+        flag_scan_apply_kernel<<<nt, 256, 0, s>>>(ctx->d_valid, hits, ctx->d_scan_tiles, ctx->d_valid_index);
+        compact_records_kernel<<<div_up(hits, 256), 256, 0, s>>>(ctx->d_valid, ctx->d_valid_index, hits,
+                                                                 reinterpret_cast<const unsigned char *>(ctx->d_contacts[0]),
+                                                                 reinterpret_cast<unsigned char *>(ctx->d_contacts[1]),
+                                                                 static_cast<int>(sizeof(ContactRec)));
+        ctx->launches += 4;
+        ctx->d_contacts_final = ctx->d_contacts[1];
+        PK_CUDA(cudaGetLastError());
+    }
+    cudaEventRecord(ctx->ev[ST_FETCH], s);
+    cudaEventRecord(ctx->ev[ST_COUNT], s);
+    PK_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < ST_COUNT; ++k)
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[k], ctx->ev[k + 1]);
+        ctx->stage_ms[k] = ms;
+    }
+    ctx->num_pairs = npairs;
+    ctx->num_contacts = (status == PK_OK) ? valid : 0;
+    ctx->have_results = status == PK_OK;
+    if (out)
+    {
+        std::memset(out, 0, sizeof(*out));
+        out->num_pairs = npairs;
+        out->num_contacts = ctx->num_contacts;
+        out->num_moved = ctx->h_counters[C_MOVED];
+        out->epa_overflow = over;
+        out->gjk_hits = ctx->h_counters[C_HITS];
+        float bp = 0.f, np_ms = 0.f;
+        for (int k = ST_BOUNDS; k <= ST_PAIR_SORT; ++k) bp += ctx->stage_ms[k];
+        for (int k = ST_GJK; k <= ST_COMPACT; ++k) np_ms += ctx->stage_ms[k];
+        out->ms_broadphase = bp;
+        out->ms_narrowphase = np_ms;
+        out->ms_total = bp + np_ms;
+        out->step_index = static_cast<uint32_t>(ctx->epoch);
+    }
+    ctx->epoch += 1;
+    if (status == PK_OK && over)
+    {
+        ctx->last_error = "EPA polytope exceeded the per-pair scratch for some pairs";
+        status = PK_E_EPA_OVERFLOW;
+    }
+    return status;
+}
+
+int pk_fetch_results(pk_ctx *ctx)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (!ctx->have_results) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    cudaEventRecord(ctx->ev[ST_FETCH], ctx->stream);
+    if (ctx->num_pairs > ctx->h_pairs_cap)
+    {
+        if (ctx->h_pairs) cudaFreeHost(ctx->h_pairs);
+        ctx->h_pairs = nullptr;
+        size_t cap = std::min<size_t>(ctx->cfg.max_pairs, std::max<size_t>(ctx->num_pairs * 5 / 4, 1024));
+        PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pairs), cap * sizeof(uint64_t), cudaHostAllocDefault));
+        ctx->h_pairs_cap = cap;
+    }
+    if (ctx->num_contacts > ctx->h_contacts_cap)
+    {
+        if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
+        ctx->h_contacts = nullptr;
+        size_t cap = std::min<size_t>(ctx->max_contacts, std::max<size_t>(ctx->num_contacts * 5 / 4, 1024));
+        PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_contacts), cap * sizeof(pk_contact), cudaHostAllocDefault));
+        ctx->h_contacts_cap = cap;
+    }
+    if (ctx->num_pairs)
+        PK_CUDA(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs_sorted, ctx->num_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    if (ctx->num_contacts)
+        PK_CUDA(cudaMemcpyAsync(ctx->h_contacts, ctx->d_contacts_final, ctx->num_contacts * sizeof(pk_contact),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev[ST_COUNT], ctx->stream);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->stage_ms[ST_FETCH], ctx->ev[ST_FETCH], ctx->ev[ST_COUNT]);
+    ctx->fetched = true;
+    return PK_OK;
+}
+
+int pk_collide(pk_ctx *ctx, pk_step_result *out)
+{
+    int s = pk_collide_resident(ctx, out);
+    if (s != PK_OK && s != PK_E_EPA_OVERFLOW) return s;
+    int f = pk_fetch_results(ctx);
+    return f != PK_OK ? f : s;
+}
+
+int pk_pairs(pk_ctx *ctx, const uint64_t **keys, uint64_t *n)
+{
+    if (!ctx || !keys || !n) return PK_E_INVALID;
+    if (!ctx->have_results || !ctx->fetched) return PK_E_STATE;
+    *keys = ctx->h_pairs;
+    *n = ctx->num_pairs;
+    return PK_OK;
+}
+
+int pk_contacts(pk_ctx *ctx, const pk_contact **recs, uint64_t *n)
+{
+    if (!ctx || !recs || !n) return PK_E_INVALID;
+    if (!ctx->have_results || !ctx->fetched) return PK_E_STATE;
+    *recs = ctx->h_contacts;
+    *n = ctx->num_contacts;
+    return PK_OK;
+}
+
+int pk_pairs_device(pk_ctx *ctx, const void **dptr, uint64_t *n)
+{
+    if (!ctx || !dptr || !n) return PK_E_INVALID;
+    if (!ctx->have_results) return PK_E_STATE;
+    *dptr = ctx->d_pairs_sorted;
+    *n = ctx->num_pairs;
+    return PK_OK;
+}
+
+int pk_contacts_device(pk_ctx *ctx, const void **dptr, uint64_t *n)
+{
+    if (!ctx || !dptr || !n) return PK_E_INVALID;
+    if (!ctx->have_results) return PK_E_STATE;
+    *dptr = ctx->d_contacts_final;
+    *n = ctx->num_contacts;
+    return PK_OK;
+}
+
+int pk_stored_bounds(pk_ctx *ctx, double *out6, uint32_t first, uint32_t count)
+{
+    if (!ctx || !out6) return PK_E_INVALID;
+    if (static_cast<uint64_t>(first) + count > ctx->n_bodies) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    PK_CUDA(cudaMemcpyAsync(out6, ctx->st.stored + 6ull * first, 6ull * count * sizeof(double), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+
+int pk_stage_times_get(pk_ctx *ctx, pk_stage_times *out)
+{
+    if (!ctx || !out) return PK_E_INVALID;
+    for (int k = 0; k < ST_COUNT; ++k)
+    {
+        out->ms[k] = ctx->stage_ms[k];
+        out->name[k] = kStageNames[k];
+    }
+    out->launches = ctx->launches;
+    return PK_OK;
+}
+
+int pk_stream(pk_ctx *ctx, void **stream)
+{
+    if (!ctx || !stream) return PK_E_INVALID;
+    *stream = ctx->stream;
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ gjk_epa batch
+
+int pk_gjk_epa_batch_device(pk_ctx *ctx, const uint32_t *d_a, const uint32_t *d_b, uint64_t n, pk_contact *d_out,
+                            uint8_t *d_hit, float *ms)
+{
+    if (!ctx || !d_a || !d_b || !d_out || !d_hit) return PK_E_INVALID;
+    if (n > ctx->cfg.max_pairs) return PK_E_PAIR_OVERFLOW;
+    cudaSetDevice(ctx->cfg.device);
+    PK_TRY(upload_shapes(ctx));
+    cudaStream_t s = ctx->stream;
+    ctx->launches = 0;
+    cudaEventRecord(ctx->ev[ST_BOUNDS], s);
+    scene_reset_kernel<<<1, 32, 0, s>>>(ctx->d_scene, ctx->d_counters, C_COUNT);
+    PK_TRY(run_narrowphase(ctx, nullptr, d_a, d_b, n, true));
+    if (n)
+        expand_contacts_kernel<<<div_up(n, 256), 256, 0, s>>>(ctx->d_hit, ctx->d_out_index, ctx->d_valid, ctx->d_contacts[0],
+                                                             d_a, d_b, n, reinterpret_cast<ContactRec *>(d_out), d_hit);
+    ctx->launches += 2;
+    cudaEventRecord(ctx->ev[ST_COUNT], s);
+    PK_TRY(read_counters(ctx));
+    PK_CUDA(cudaGetLastError());
+    if (ms) cudaEventElapsedTime(ms, ctx->ev[ST_BOUNDS], ctx->ev[ST_COUNT]);
+    cudaEventElapsedTime(&ctx->stage_ms[ST_GJK], ctx->ev[ST_GJK], ctx->ev[ST_SCAN]);
+    cudaEventElapsedTime(&ctx->stage_ms[ST_SCAN], ctx->ev[ST_SCAN], ctx->ev[ST_EPA]);
+    cudaEventElapsedTime(&ctx->stage_ms[ST_EPA], ctx->ev[ST_EPA], ctx->ev[ST_COMPACT]);
+    if (ctx->h_counters[C_HITS] > ctx->max_contacts)
+    {
+        ctx->last_error = "GJK hits exceed pk_config.max_contacts";
+        return PK_E_PAIR_OVERFLOW;
+    }
+    if (ctx->h_counters[C_EPA_OVERFLOW])
+    {
+        ctx->last_error = "EPA polytope exceeded the per-pair scratch for some pairs";
+        return PK_E_EPA_OVERFLOW;
+    }
+    return PK_OK;
+}
+
+int pk_gjk_epa_batch(pk_ctx *ctx, const uint32_t *pair_a, const uint32_t *pair_b, uint64_t n, pk_contact *out, uint8_t *hit)
+{
+    if (!ctx || !pair_a || !pair_b || !out || !hit) return PK_E_INVALID;
+    if (n > ctx->cfg.max_pairs) return PK_E_PAIR_OVERFLOW;
+    if (n == 0) return PK_OK;
+    for (uint64_t k = 0; k < n; ++k)
+        if (pair_a[k] >= ctx->n_bodies || pair_b[k] >= ctx->n_bodies) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    uint32_t *d_a = nullptr, *d_b = nullptr;
+    ContactRec *d_out = nullptr;
+    uint8_t *d_h = nullptr;
+    int status = PK_OK;
+    auto cleanup = [&]()
+    {
+        if (d_a) cudaFree(d_a);
+        if (d_b) cudaFree(d_b);
+        if (d_out) cudaFree(d_out);
+        if (d_h) cudaFree(d_h);
+    };
+    if ((status = dev_alloc(ctx, &d_a, n)) != PK_OK || (status = dev_alloc(ctx, &d_b, n)) != PK_OK ||
+        (status = dev_alloc(ctx, &d_out, n)) != PK_OK || (status = dev_alloc(ctx, &d_h, n)) != PK_OK)
+    {
+        cleanup();
+        return status;
+    }
+    cudaMemcpyAsync(d_a, pair_a, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_b, pair_b, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    status = pk_gjk_epa_batch_device(ctx, d_a, d_b, n, reinterpret_cast<pk_contact *>(d_out), d_h, nullptr);
+    if (status == PK_OK || status == PK_E_EPA_OVERFLOW)
+    {
+        cudaMemcpyAsync(out, d_out, n * sizeof(pk_contact), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(hit, d_h, n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) status = PK_E_CUDA;
+    }
+    cleanup();
+    return status;
+}
+
+// ------------------------------------------------------------------------------------ raw memory helpers
+int pk_device_alloc(pk_ctx *ctx, size_t bytes, void **dptr)
+{
+    if (!ctx || !dptr) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    PK_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return PK_OK;
+}
+int pk_device_free(pk_ctx *ctx, void *dptr)
+{
+    if (!ctx) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaFree(dptr));
+    return PK_OK;
+}
+int pk_memcpy_h2d(pk_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    PK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+int pk_memcpy_d2h(pk_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    PK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+
+int pk_memcpy_d2d(pk_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    PK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+int pk_host_alloc(pk_ctx *ctx, size_t bytes, void **hptr)
+{
+    if (!ctx || !hptr) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    PK_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return PK_OK;
+}
+int pk_host_free(pk_ctx *ctx, void *hptr)
+{
+    if (!ctx) return PK_E_INVALID;
+    PK_CUDA(cudaFreeHost(hptr));
+    return PK_OK;
+}
+
+} // extern "C"

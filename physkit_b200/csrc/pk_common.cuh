@@ -1,0 +1,167 @@
+// pk_common.cuh — device-side algebra, shape records and support functions.
+//
+// Every translation unit of this library is compiled with -fmad=false: the reference is built
+// with plain -O3 for x86-64 (CMakeLists.txt:126-132 → SSE2, no FMA), so a*b+c must round twice
+// for results to be bit-identical.  Operation order follows Eigen's fixed-size double kernels as
+// used by include/physkit/algebra/lin_alg.h (citations relative to /root/reference).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pk
+{
+
+constexpr int KIND_AABB = 0;   // aabb::support            bounds.h:164-174 (pose-less)
+constexpr int KIND_OBB = 1;    // obb::support             bounds.h:539-548
+constexpr int KIND_SPHERE = 2; // bounding_sphere::support bounds.h:328-329
+constexpr int KIND_HULL = 3;   // mesh::instance::support  src/mesh.cpp:442-448, 341-358
+
+constexpr uint8_t FLAG_STATIC = 1;
+constexpr uint8_t FLAG_ALIVE = 2;
+
+struct d3
+{
+    double x, y, z;
+};
+
+#define PK_HD __host__ __device__ __forceinline__
+
+PK_HD d3 make_d3(double x, double y, double z) { return d3{x, y, z}; }
+PK_HD d3 operator+(d3 a, d3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+PK_HD d3 operator-(d3 a, d3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+PK_HD d3 operator-(d3 a) { return {-a.x, -a.y, -a.z}; }
+PK_HD d3 operator*(d3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+PK_HD d3 operator*(double s, d3 a) { return {s * a.x, s * a.y, s * a.z}; }
+// Eigen 3-vector redux with SSE2 packets: (x0 + x1) + x2   (lin_alg.h:212-213, :229)
+PK_HD double dot(d3 a, d3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+PK_HD double sqnorm(d3 a) { return (a.x * a.x + a.y * a.y) + a.z * a.z; }
+// Eigen cross3 (lin_alg.h:215-219)
+PK_HD d3 cross(d3 a, d3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+// Eigen normalized(): z > 0 ? v / sqrt(z) : v, true division (lin_alg.h:232-240)
+PK_HD d3 normalized(d3 a)
+{
+    double z = sqnorm(a);
+    if (z > 0.0)
+    {
+        double s = sqrt(z);
+        return {a.x / s, a.y / s, a.z / s};
+    }
+    return a;
+}
+PK_HD double dmin(double a, double b) { return (b < a) ? b : a; } // std::min
+PK_HD double dmax(double a, double b) { return (a < b) ? b : a; } // std::max
+
+struct dq
+{
+    double x, y, z, w; // Eigen coeffs order (lin_alg.h:388)
+};
+PK_HD dq conjugate(dq q) { return {-q.x, -q.y, -q.z, q.w}; }
+// Eigen _transformVector (lin_alg.h:493-499): uv = qv×v; uv += uv; v + w·uv + qv×uv (left-assoc)
+PK_HD d3 rotate(dq q, d3 v)
+{
+    d3 qv{q.x, q.y, q.z};
+    d3 uv = cross(qv, v);
+    uv = uv + uv;
+    d3 c = cross(qv, uv);
+    return {(v.x + q.w * uv.x) + c.x, (v.y + q.w * uv.y) + c.y, (v.z + q.w * uv.z) + c.z};
+}
+
+// 64-byte device shape record.
+//   AABB  : a = min,  b = max                       (local box = a,b)
+//   OBB   : a = half                                (local box = ±a)
+//   SPHERE: a.x = r                                 (local box = ±r)
+//   HULL  : a = local min, b = local max, vertices  (aabb::from_points, mesh.h:191)
+struct alignas(16) ShapeRec
+{
+    double a[3];
+    double b[3];
+    int32_t kind;
+    uint32_t vert_off;
+    uint32_t nverts;
+    uint32_t _pad;
+};
+static_assert(sizeof(ShapeRec) == 64, "ShapeRec must be one 64-byte line");
+
+// What a support query needs for one body, in registers.
+struct ShapeView
+{
+    int kind;
+    uint32_t nverts;
+    const double *verts; // HULL: xyz triples (3 doubles per vertex), 16-byte aligned start
+    d3 p;                // AABB: min | others: position / centre
+    d3 h;                // AABB: max | OBB: half | SPHERE: h.x = r
+    dq q;                // OBB / HULL
+};
+
+__device__ __forceinline__ ShapeView load_shape(const ShapeRec *__restrict__ shapes, const double *__restrict__ verts,
+                                               const double *__restrict__ pos, const double *__restrict__ quat,
+                                               const uint32_t *__restrict__ shape_id, uint32_t body)
+{
+    ShapeView v;
+    const ShapeRec *s = shapes + shape_id[body];
+    // 64-byte record as four 16-byte loads
+    const double2 *sp = reinterpret_cast<const double2 *>(s);
+    double2 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2);
+    int4 s3 = __ldg(reinterpret_cast<const int4 *>(sp + 3));
+    v.kind = s3.x;
+    v.nverts = static_cast<uint32_t>(s3.z);
+    v.verts = verts + 3ull * static_cast<uint32_t>(s3.y);
+    if (v.kind == KIND_AABB)
+    {
+        v.p = {s0.x, s0.y, s1.x};
+        v.h = {s1.y, s2.x, s2.y};
+        v.q = {0, 0, 0, 1};
+    }
+    else
+    {
+        v.p = {pos[3ull * body], pos[3ull * body + 1], pos[3ull * body + 2]};
+        v.h = {s0.x, s0.y, s1.x};
+        const double2 *qp = reinterpret_cast<const double2 *>(quat + 4ull * body);
+        double2 q0 = __ldg(qp), q1 = __ldg(qp + 1);
+        v.q = {q0.x, q0.y, q1.x, q1.y};
+    }
+    return v;
+}
+
+// Farthest point of the shape along d.
+__device__ __forceinline__ d3 support(const ShapeView &s, d3 d)
+{
+    if (s.kind == KIND_OBB)
+    {
+        d3 l = rotate(conjugate(s.q), d);
+        d3 sh{(l.x >= 0 ? 1.0 : -1.0) * s.h.x, (l.y >= 0 ? 1.0 : -1.0) * s.h.y, (l.z >= 0 ? 1.0 : -1.0) * s.h.z};
+        return s.p + rotate(s.q, sh);
+    }
+    if (s.kind == KIND_SPHERE) return s.p + s.h.x * normalized(d);
+    if (s.kind == KIND_AABB) return {d.x >= 0 ? s.h.x : s.p.x, d.y >= 0 ? s.h.y : s.p.y, d.z >= 0 ? s.h.z : s.p.z};
+    // HULL: linear scan, strict '>' so the lowest index wins ties (src/mesh.cpp:350)
+    d3 l = rotate(conjugate(s.q), d);
+    const double *v = s.verts;
+    uint32_t best = 0;
+    double best_dot = (v[0] * l.x + v[1] * l.y) + v[2] * l.z;
+    for (uint32_t i = 1; i < s.nverts; ++i)
+    {
+        double t = (v[3 * i] * l.x + v[3 * i + 1] * l.y) + v[3 * i + 2] * l.z;
+        if (t > best_dot)
+        {
+            best_dot = t;
+            best = i;
+        }
+    }
+    d3 bv{v[3 * best], v[3 * best + 1], v[3 * best + 2]};
+    return rotate(s.q, bv) + s.p;
+}
+
+// 88-byte contact record, mirrors pk_contact of include/pk_collide.h.
+struct ContactRec
+{
+    uint64_t key;
+    double normal[3];
+    double world_a[3];
+    double world_b[3];
+    double depth;
+};
+static_assert(sizeof(ContactRec) == 88, "ContactRec must match pk_contact");
+
+} // namespace pk

@@ -1,0 +1,248 @@
+"""GPU parity: LBVH broadphase + full collision stage vs the CPU oracle, through the C ABI.
+
+Bar: the candidate pair set is bit-exact as a sorted (i,j) list; stored (fat) boxes are
+bit-identical; contacts are bit-identical."""
+import numpy as np
+import pytest
+
+import oracle
+import physkit_b200 as pk
+from scenes import Scene, SplitMix64, scene_c1, scene_c2, scene_c3
+
+pytestmark = pytest.mark.gpu
+
+
+def _split(keys):
+    return (keys >> np.uint64(32)).astype(np.uint32), (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
+def _check_contacts(sc, pos, quat, keys, contacts):
+    from gpu_util import contacts_equal_bitwise
+
+    pa, pb = _split(keys)
+    hit_ref, out_ref, _ = oracle.gjk_epa_pairs(sc.shapes, pos, quat, sc.shape_id, pa, pb, nthreads=8)
+    m = hit_ref.astype(bool)
+    assert np.array_equal(contacts["key"], keys[m])
+    contacts_equal_bitwise(contacts, np.ones(len(contacts), np.uint8), np.ones(len(contacts), np.uint8), out_ref[m])
+
+
+@pytest.mark.parametrize("n", [2, 3, 17, 1000, 20_000])
+def test_query_mode_pairs_exact(n):
+    """BASELINE C2 shape (random OBBs), static-pose mode: pair set == faithful dynamic_bvh + == brute force."""
+    from gpu_util import make_context
+
+    sc = scene_c2(n, extent=50.0 * (max(n, 64) / 100_000.0) ** (1 / 3) * 0.6)
+    ctx = make_context(sc, max_pairs=max(64, 40 * n))
+    res = ctx.collide()
+    keys = ctx.pairs()
+    boxes = oracle.bounds(sc.shapes, sc.pos, sc.quat, sc.shape_id)
+    assert np.array_equal(ctx.stored_bounds(0, n).view(np.uint64), boxes.view(np.uint64))
+    want = oracle.query_pairs(boxes)
+    assert res.num_pairs == len(want)
+    assert np.array_equal(keys, want)
+    if n <= 1000:
+        assert np.array_equal(keys, oracle.brute_pairs(boxes))
+    _check_contacts(sc, sc.pos, sc.quat, keys, ctx.contacts())
+    ctx.close()
+
+
+def test_query_mode_c2_full_size():
+    """BASELINE config C2 at full size: 100 k randomly posed OBBs in a 100 m cube, exact match."""
+    from gpu_util import make_context
+
+    sc = scene_c2(100_000)
+    ctx = make_context(sc, max_pairs=2_000_000)
+    res = ctx.collide()
+    keys = ctx.pairs()
+    boxes = oracle.bounds(sc.shapes, sc.pos, sc.quat, sc.shape_id)
+    want = oracle.query_pairs(boxes)
+    assert np.array_equal(keys, want)
+    assert res.num_pairs > 100_000
+    _check_contacts(sc, sc.pos, sc.quat, keys, ctx.contacts())
+    ctx.close()
+
+
+def test_degenerate_inputs():
+    """Empty scene, one body, coincident boxes, zero-volume boxes, corner touch (inclusive)."""
+    ctx = pk.Context(64, 4096, mode=pk.MODE_QUERY, max_shapes=64)
+    ids = ctx.add_shapes([("obb", (0.5, 0.5, 0.5)), ("obb", (0.5, 0.5, 0.0))])
+    ctx.resize(0)
+    assert ctx.collide().num_pairs == 0 and len(ctx.pairs()) == 0
+    I = [0.0, 0.0, 0.0, 1.0]
+    ctx.resize(1)
+    ctx.upload([[0, 0, 0]], [I], None, [ids[0]], [2])
+    assert ctx.collide().num_pairs == 0
+    # 5 coincident boxes → all 10 pairs (tests/dynamic_bvh/main.cpp:704-718)
+    ctx.resize(5)
+    ctx.upload(np.zeros((5, 3)), [I] * 5, None, [ids[0]] * 5, [2] * 5)
+    assert ctx.collide().num_pairs == 10
+    # corner touch counts (tests/mesh/main.cpp:118-120); flat box (main.cpp:687-702)
+    ctx.resize(3)
+    ctx.upload([[0, 0, 0], [1, 1, 1], [0.2, 0.2, 0.5]], [I] * 3, None, [ids[0], ids[0], ids[1]], [2] * 3)
+    ctx.collide()
+    assert list(ctx.pairs()) == [(0 << 32) | 1, (0 << 32) | 2, (1 << 32) | 2]
+    # dead bodies never pair
+    ctx.upload([[0, 0, 0], [1, 1, 1], [0.2, 0.2, 0.5]], [I] * 3, None, [ids[0], ids[0], ids[1]], [2, 0, 2])
+    ctx.collide()
+    assert list(ctx.pairs()) == [(0 << 32) | 2]
+    ctx.close()
+
+
+def test_pair_overflow_is_reported():
+    ctx = pk.Context(64, 4, mode=pk.MODE_QUERY, max_shapes=4)
+    sid = ctx.add_shape(("obb", (0.5, 0.5, 0.5)))
+    ctx.resize(8)
+    ctx.upload(np.zeros((8, 3)), [[0, 0, 0, 1.0]] * 8, None, [sid] * 8, [2] * 8)
+    with pytest.raises(pk.PkError) as e:
+        ctx.collide()
+    assert e.value.status == -5
+    assert ctx.result.pairs_required == 28
+    ctx.close()
+
+
+def _world_replay(sc, steps, mutate, max_pairs, **ctxkw):
+    """Drive oracle.World (faithful incremental broadphase) and the GPU ctx with the same inputs."""
+    from gpu_util import make_context
+
+    ctx = make_context(sc, max_pairs=max_pairs, mode=pk.MODE_WORLD, **ctxkw)
+    w = oracle.World(sc.shapes)
+    pos, quat, flags = sc.pos.copy(), sc.quat.copy(), sc.flags.copy()
+    total = 0
+    for step in range(steps):
+        disp = mutate(step, pos, quat, flags)
+        moved = w.step(pos, quat, disp, sc.shape_id, flags)
+        ctx.upload(pos, quat, disp, sc.shape_id, flags)
+        res = ctx.collide()
+        keys = ctx.pairs()
+        want = w.pairs()
+        assert res.num_moved == moved, f"step {step}"
+        assert np.array_equal(keys, want), f"step {step}: {len(keys)} vs {len(want)}"
+        alive = np.nonzero(flags & 2)[0]
+        got_boxes = ctx.stored_bounds(0, sc.n)
+        for i in alive[:: max(1, len(alive) // 64)]:
+            assert np.array_equal(got_boxes[i].view(np.uint64), w.stored(int(i)).view(np.uint64))
+        if step % 7 == 3 and len(keys):
+            _check_contacts(sc, pos, quat, keys, ctx.contacts())
+        total += len(keys)
+        dyn = ((flags & 1) == 0) & ((flags & 2) != 0)
+        pos += disp * dyn[:, None]
+    ctx.close()
+    return total
+
+
+def test_world_mode_replay_c1_style():
+    """BASELINE C1 shape: ground + lattice of 8-vertex box hulls falling under gravity (no solver:
+    contact response is out of scope, bodies interpenetrate), 60 steps at 60 Hz.  Step 1 must yield
+    zero pairs (first-step quirk), bodies are created and destroyed mid-run."""
+    sc = scene_c1(side=6, spacing=1.05)
+    n = sc.n
+    rng = SplitMix64(3)
+    vel = np.zeros((n, 3))
+    late = np.zeros(n, dtype=bool)
+    late[5::9] = True
+    sc.flags[late] = 0
+    dt = 1.0 / 60.0
+
+    def mutate(step, pos, quat, flags):
+        if step == 5:
+            flags[late] = 2
+        if step == 12:
+            flags[7:60:6] = 0
+        if step == 20:
+            flags[7:60:6] = 2
+        dyn = (flags & 1) == 0
+        vel[dyn, 1] -= 9.81 * dt
+        if step % 4 == 0:
+            vel[dyn] += rng.uniform(-0.3, 0.3, n, 3)[dyn]
+        return vel * dt
+
+    total = _world_replay(sc, 60, mutate, max_pairs=200_000)
+    assert total > 1000
+
+
+def test_world_mode_first_step_has_no_pairs():
+    from gpu_util import make_context
+
+    sc = scene_c3(side=8)
+    ctx = make_context(sc, max_pairs=100_000, mode=pk.MODE_WORLD)
+    assert ctx.collide().num_pairs == 0  # collision_phases.h:342-346 + src/world.cpp:30
+    ctx.update_pose(sc.pos + 0.01)
+    res = ctx.collide()
+    assert res.num_moved == sc.n and res.num_pairs > 0
+    ctx.close()
+
+
+def test_world_mode_c3_style_mixed_shapes():
+    """C3 shapes (analytic spheres + OBBs) in world mode with random drift."""
+    sc = scene_c3(side=12)
+    rng = SplitMix64(9)
+
+    def mutate(step, pos, quat, flags):
+        return rng.uniform(-0.08, 0.08, sc.n, 3)
+
+    total = _world_replay(sc, 12, mutate, max_pairs=400_000)
+    assert total > 10_000
+
+
+def test_batched_worlds_do_not_interact():
+    """BASELINE C5 shape: independent worlds in one ctx; pairs only form inside a world and equal
+    the per-world oracle result (ids offset)."""
+    from gpu_util import make_context
+
+    nw = 9
+    base = scene_c1(side=4, spacing=0.95)
+    per = base.n
+    pos = np.concatenate([base.pos + SplitMix64(100 + k).uniform(-0.02, 0.02, per, 3) for k in range(nw)])
+    quat = np.tile(base.quat, (nw, 1))
+    sid = np.tile(base.shape_id, nw)
+    flags = np.tile(base.flags, nw)
+    wid = np.repeat(np.arange(nw, dtype=np.uint32), per)
+    sc = Scene(base.shapes, pos, quat, sid, flags)
+    ctx = make_context(sc, max_pairs=400_000, mode=pk.MODE_WORLD, num_worlds=nw, world_id_array=wid)
+    worlds = [oracle.World(base.shapes) for _ in range(nw)]
+    p = pos.copy()
+    for step in range(4):
+        disp = np.full((len(p), 3), 0.0)
+        disp[:, 1] = -0.05 * step
+        ctx.upload(p, quat, disp, sid, flags, wid)
+        ctx.collide()
+        keys = ctx.pairs()
+        want = []
+        for k, w in enumerate(worlds):
+            sl = slice(k * per, (k + 1) * per)
+            w.step(p[sl], quat[sl], disp[sl], base.shape_id, base.flags)
+            kk = w.pairs()
+            a, b = _split(kk)
+            want.append(((a.astype(np.uint64) + np.uint64(k * per)) << np.uint64(32)) | (b.astype(np.uint64) + np.uint64(k * per)))
+        want = np.sort(np.concatenate(want))
+        assert np.array_equal(keys, want), f"step {step}"
+        p = p + disp * ((flags & 1) == 0)[:, None]
+    assert len(keys) > 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_pair_sharding_partitions_the_set(shards):
+    """One large world, pairs partitioned across ranks by sorted-leaf range: the shards are disjoint
+    and their union is the full set; contacts likewise."""
+    from gpu_util import make_context
+
+    sc = scene_c3(side=14)
+    full = make_context(sc, max_pairs=600_000)
+    full.collide()
+    keys_full, con_full = full.pairs(), full.contacts()
+    full.close()
+    parts, cparts = [], []
+    for r in range(shards):
+        ctx = make_context(sc, max_pairs=600_000, shard_rank=r, shard_count=shards)
+        ctx.collide()
+        parts.append(ctx.pairs())
+        cparts.append(ctx.contacts())
+        ctx.close()
+    allk = np.concatenate(parts)
+    assert len(allk) == len(keys_full) and len(np.unique(allk)) == len(allk)
+    assert np.array_equal(np.sort(allk), keys_full)
+    allc = np.concatenate(cparts)
+    allc = allc[np.argsort(allc["key"], kind="stable")]
+    assert np.array_equal(allc.view(np.uint8), con_full.view(np.uint8))
+    assert min(len(p) for p in parts) > 0.3 * len(keys_full) / shards  # no empty / degenerate shard

@@ -1,0 +1,156 @@
+"""GPU parity: batched GJK/EPA (pk_gjk_epa_batch) vs the CPU oracle, through the C ABI.
+
+Bar (BASELINE.json north_star): hit/no-hit exact outside a 1e-6 m margin, depth & normal within 1e-5
+relative.  The library is built without FMA contraction and follows the reference's operation
+order, so these tests hold it to the stronger bar of BIT-IDENTICAL results."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from kat_cases import EPA_CASES, GJK_CASES, run_epa_case
+from scenes import random_pairs_scene, scene_c3, scene_c4
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu_gjk():
+    from gpu_util import GpuGjk
+
+    g = GpuGjk()
+    yield g
+    g.close()
+
+
+def _ref(a, b):
+    return oracle.gjk_epa(a[0], (a[1], a[2]), b[0], (b[1], b[2]))
+
+
+def _same(r_gpu, r_ref):
+    if r_ref is None or r_gpu is None:
+        return r_ref is None and r_gpu is None
+    for k in ("normal", "world_a", "world_b"):
+        if not np.array_equal(np.asarray(r_gpu[k]).view(np.uint64), np.asarray(r_ref[k]).view(np.uint64)):
+            return False
+    return np.float64(r_gpu["depth"]).view(np.uint64) == np.float64(r_ref["depth"]).view(np.uint64)
+
+
+@pytest.mark.parametrize("case", GJK_CASES, ids=[c[0] for c in GJK_CASES])
+def test_gjk_kat_gpu(gpu_gjk, case):
+    """Reference tests/gjk/gjk_test.cpp through the CUDA path; also bit-identical to the oracle."""
+    _, a, b, expect, swapped = case
+    r = gpu_gjk(a, b)
+    assert (r is not None) == expect
+    assert _same(r, _ref(a, b))
+    if swapped:
+        r2 = gpu_gjk(b, a)
+        assert (r2 is not None) == expect
+        assert _same(r2, _ref(b, a))
+
+
+@pytest.mark.parametrize("case", EPA_CASES, ids=[c[0] for c in EPA_CASES])
+def test_epa_kat_gpu(gpu_gjk, case):
+    """Reference tests/epa/epa_test.cpp through the CUDA path; also bit-identical to the oracle."""
+    _, a, b, chk = case
+    run_epa_case(gpu_gjk, a, b, chk)
+    assert _same(gpu_gjk(a, b), _ref(a, b))
+
+
+def _batch_vs_oracle(sc, pa, pb, max_contacts=0):
+    from gpu_util import contacts_equal_bitwise, make_context
+
+    ctx = make_context(sc, max_pairs=max(len(pa), 16))
+    try:
+        hit, out = ctx.gjk_epa_batch(pa, pb)
+    finally:
+        ctx.close()
+    hit_ref, out_ref, st = oracle.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb, stats=True, nthreads=8)
+    contacts_equal_bitwise(out, hit, hit_ref, out_ref)
+    assert np.array_equal(out["key"], (pa.astype(np.uint64) << np.uint64(32)) | pb.astype(np.uint64))
+    return hit, out, st
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_pairs_all_shape_kinds_bit_exact(seed):
+    """Differential test the reference lacks: 20k random pairs over aabb/obb/sphere/hull."""
+    sc, pa, pb = random_pairs_scene(20_000, seed)
+    hit, out, st = _batch_vs_oracle(sc, pa, pb)
+    assert 0.2 < hit.mean() < 0.9
+    n = out["normal"][hit.astype(bool)]
+    assert np.allclose(np.sqrt((n * n).sum(axis=1)), 1.0, atol=1e-6)
+    # every exit path of the reference was exercised somewhere in the three seeds' union
+    assert (st[:, 7] == 1).any()
+
+
+def test_tolerance_bar_of_north_star():
+    """The stated bar, spelled out: depth and normal within 1e-5 relative (trivially met when the
+    bit-exact test passes; kept so the tolerance is written in a test)."""
+    sc, pa, pb = random_pairs_scene(5_000, 21, kinds=("obb", "sphere"))
+    from gpu_util import make_context
+
+    ctx = make_context(sc, max_pairs=len(pa))
+    hit, out = ctx.gjk_epa_batch(pa, pb)
+    ctx.close()
+    hit_ref, out_ref, _ = oracle.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb)
+    assert np.array_equal(hit, hit_ref)
+    m = hit.astype(bool)
+    assert np.all(np.abs(out["depth"][m] - out_ref[m, 9]) <= 1e-5 * np.abs(out_ref[m, 9]) + 1e-300)
+    assert np.all(np.abs(out["normal"][m] - out_ref[m, 0:3]) <= 1e-5)
+
+
+def test_c3_style_sphere_box_pairs_bit_exact():
+    """C3 shapes (analytic spheres + OBBs on a jittered lattice): candidate pairs from the oracle's
+    broadphase, narrowphase on the GPU."""
+    sc = scene_c3(side=16)
+    boxes = oracle.bounds(sc.shapes, sc.pos, sc.quat, sc.shape_id)
+    boxes[:, :3] -= 0.1
+    boxes[:, 3:] += 0.1
+    keys = oracle.query_pairs(boxes)
+    pa = (keys >> np.uint64(32)).astype(np.uint32)
+    pb = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    hit, out, st = _batch_vs_oracle(sc, pa, pb)
+    assert len(keys) > 30_000 and hit.sum() > 3_000
+    assert st[:, 1].max() == 64  # the 64-iteration best-guess exit is exercised
+
+
+def test_c4_style_hull_pairs_bit_exact():
+    """C4: convex hulls with 32–256 vertices, ≈50 % intersecting."""
+    sc, pa, pb = scene_c4(n_pairs=6_000, n_hulls=64)
+    hit, out, st = _batch_vs_oracle(sc, pa, pb)
+    assert 0.3 < hit.mean() < 0.7
+
+
+def test_mtv_property_on_gpu_results():
+    """epa_test.cpp:33-47 as a property over random OBB pairs: moving A by normal·(depth+1e-3)
+    separates the shapes (checked with the GPU itself)."""
+    from gpu_util import make_context
+
+    sc, pa, pb = random_pairs_scene(4_000, 5, kinds=("obb",))
+    ctx = make_context(sc, max_pairs=len(pa))
+    hit, out = ctx.gjk_epa_batch(pa, pb)
+    m = hit.astype(bool)
+    # skip best-guess (non-converged) results: the reference makes no promise for them
+    _, _, st = oracle.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb, stats=True)
+    m &= st[:, 7] == 1
+    pos2 = sc.pos.copy()
+    pos2[pa[m]] += out["normal"][m] * (out["depth"][m][:, None] + 1e-3)
+    ctx.upload(pos2, sc.quat, sc.disp, sc.shape_id, sc.flags)
+    hit2, _ = ctx.gjk_epa_batch(pa, pb)
+    ctx.close()
+    assert m.sum() > 500
+    assert hit2[m].sum() == 0
+
+
+def test_empty_and_single_pair_batches():
+    from gpu_util import make_context
+
+    sc, pa, pb = random_pairs_scene(4, 3)
+    ctx = make_context(sc, max_pairs=16)
+    hit, out = ctx.gjk_epa_batch(pa[:0], pb[:0])
+    assert len(hit) == 0
+    hit, out = ctx.gjk_epa_batch(pa[:1], pb[:1])
+    ref_hit, ref_out, _ = oracle.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa[:1], pb[:1])
+    assert np.array_equal(hit, ref_hit)
+    ctx.close()
