@@ -79,7 +79,11 @@ def test_random_pairs_all_shape_kinds_bit_exact(seed):
     hit, out, st = _batch_vs_oracle(sc, pa, pb)
     assert 0.2 < hit.mean() < 0.9
     n = out["normal"][hit.astype(bool)]
-    assert np.allclose(np.sqrt((n * n).sum(axis=1)), 1.0, atol=1e-6)
+    ln = np.sqrt((n * n).sum(axis=1))
+    # a degenerate EPA face has normal 0 / distance 0 in the reference (collision.cpp:284-287) and can be
+    # returned as the "closest" face; everything else must be unit length
+    assert np.all((np.abs(ln - 1.0) < 1e-6) | (ln == 0.0))
+    assert (ln == 0.0).mean() < 0.25
     # every exit path of the reference was exercised somewhere in the three seeds' union
     assert (st[:, 7] == 1).any()
 
