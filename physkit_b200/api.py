@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libpk_collide.so")
+_LIB_PATH = os.environ.get("PK_COLLIDE_LIB") or os.path.join(_HERE, "libpk_collide.so")
 
 MODE_WORLD, MODE_QUERY = 0, 1
 PK_OK = 0

@@ -41,10 +41,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.normpath(d)) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """out/defines build an experiment variant next to the product library (select it at run time with
+    PK_COLLIDE_LIB=<path>); the product itself is always physkit_b200/libpk_collide.so with no defines."""
+    target = LIB if out is None else os.path.join(HERE, out)
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:
@@ -53,8 +56,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed ({r.returncode}); see {log}")
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    args = [a for a in sys.argv[1:] if a != "--force"]
+    out = None
+    defines = []
+    while args:
+        a = args.pop(0)
+        if a == "--out":
+            out = args.pop(0)
+        elif a == "--define":
+            defines.append(args.pop(0))
+    print(build(force="--force" in sys.argv, verbose=out is None, out=out, defines=defines))

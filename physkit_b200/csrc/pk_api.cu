@@ -400,7 +400,10 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     A(ctx->d_valid_index, nc);
     // persistent EPA grid: enough resident threads to fill the machine, never more than the work
     {
-        uint64_t want_threads = static_cast<uint64_t>(ctx->sm_count) * 5 * EPA_THREADS;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_kernel, EPA_THREADS, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+        uint64_t want_threads = static_cast<uint64_t>(ctx->sm_count) * per_sm * EPA_THREADS;
         uint64_t need_threads = ((nc + EPA_THREADS - 1) / EPA_THREADS) * EPA_THREADS;
         uint64_t threads = std::min(want_threads, std::max<uint64_t>(need_threads, EPA_THREADS));
         ctx->epa_blocks = static_cast<uint32_t>(threads / EPA_THREADS);

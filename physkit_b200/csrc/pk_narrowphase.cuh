@@ -20,8 +20,8 @@ namespace pk
 
 constexpr int EPA_MAX_FACES = 768; // reference: unbounded (InlinedVector spills); overflow is flagged
 constexpr int EPA_MAX_VERTS = 68;  // 4 + 64 iterations
-constexpr int EPA_MAX_HORIZON = 64;
-constexpr int EPA_MAX_STACK = 64;
+constexpr int EPA_MAX_HORIZON = 32; // reference InlinedVector<…,32> inline capacity; observed max 10
+constexpr int EPA_MAX_STACK = 32;   // observed max 4
 constexpr int EPA_THREADS = 64;
 
 struct SupportPt
@@ -292,16 +292,25 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
 
 // ---------------------------------------------------------------------------------------------
 // EPA polytope in a per-thread HBM slab.
+//
+// The kernel is bound by the latency of dependent loads into the slab, not by bandwidth or FP64
+// issue (ncu r1: 72 % of stall samples long_scoreboard, FP64 pipe 4.5 %).  The layout and the code
+// below are therefore organised so that every step issues all the loads it will need at once:
+//   * a face is ONE 48-byte record (normal, distance, vertices, adjacency, obsolete flag)
+//   * heap entries carry a copy of the face distance, so sifting never touches the face array;
+//     sift-up prefetches the whole ancestor chain (its indices do not depend on loaded data)
+//   * linking new faces never re-reads what was just written: the adjacency of the new faces is
+//     built in registers and each record is stored once
 // ---------------------------------------------------------------------------------------------
-struct alignas(16) FaceTopo
+struct alignas(16) FaceRec
 {
+    double nx, ny, nz, dist;
     uint16_t adj[3];
-    uint16_t _pad0;
     uint8_t v[3];
     uint8_t obsolete;
-    uint32_t _pad1;
+    uint8_t _pad[6];
 };
-static_assert(sizeof(FaceTopo) == 16, "FaceTopo is half a sector");
+static_assert(sizeof(FaceRec) == 48, "FaceRec is three 16-byte words");
 
 struct alignas(16) HeapEnt
 {
@@ -311,21 +320,28 @@ struct alignas(16) HeapEnt
 };
 
 constexpr uint16_t EPA_NULL = 0xFFFFu;
-constexpr size_t EPA_SLAB_BYTES = static_cast<size_t>(EPA_MAX_FACES) * (32 + sizeof(FaceTopo) + sizeof(HeapEnt)) +
+constexpr int EPA_HEAP_LEVELS = 10; // 2^10 > EPA_MAX_FACES
+constexpr size_t EPA_SLAB_BYTES = static_cast<size_t>(EPA_MAX_FACES) * (sizeof(FaceRec) + sizeof(HeapEnt)) +
                                   static_cast<size_t>(EPA_MAX_VERTS) * 48;
+
+// second 16-byte word group of a FaceRec as loaded/stored in one transaction
+struct FaceTail
+{
+    uint16_t adj[3];
+    uint8_t v[3];
+    uint8_t obsolete;
+};
 
 struct EpaSlab
 {
-    double4 *fnd;    // normal xyz, distance
-    FaceTopo *topo;  // vertices, adjacency, obsolete
-    HeapEnt *heap;   // binary heap, min distance at the root
-    double *verts;   // pa xyz, pb xyz per polytope vertex
+    FaceRec *faces;
+    HeapEnt *heap; // binary heap, min distance at the root
+    double *verts; // pa xyz, pb xyz per polytope vertex
     __device__ __forceinline__ explicit EpaSlab(unsigned char *base)
     {
-        fnd = reinterpret_cast<double4 *>(base);
-        topo = reinterpret_cast<FaceTopo *>(base + static_cast<size_t>(EPA_MAX_FACES) * 32);
-        heap = reinterpret_cast<HeapEnt *>(base + static_cast<size_t>(EPA_MAX_FACES) * (32 + sizeof(FaceTopo)));
-        verts = reinterpret_cast<double *>(base + static_cast<size_t>(EPA_MAX_FACES) * (32 + sizeof(FaceTopo) + sizeof(HeapEnt)));
+        faces = reinterpret_cast<FaceRec *>(base);
+        heap = reinterpret_cast<HeapEnt *>(base + static_cast<size_t>(EPA_MAX_FACES) * sizeof(FaceRec));
+        verts = reinterpret_cast<double *>(base + static_cast<size_t>(EPA_MAX_FACES) * (sizeof(FaceRec) + sizeof(HeapEnt)));
     }
     __device__ __forceinline__ d3 vp(int i) const
     {
@@ -340,17 +356,72 @@ struct EpaSlab
         v[1] = make_double2(s.pa.z, s.pb.x);
         v[2] = make_double2(s.pb.y, s.pb.z);
     }
+    __device__ __forceinline__ double4 load_nd(int f) const
+    {
+        const double2 *q = reinterpret_cast<const double2 *>(faces + f);
+        double2 a = q[0], b = q[1];
+        return make_double4(a.x, a.y, b.x, b.y);
+    }
+    __device__ __forceinline__ FaceTail load_tail(int f) const
+    {
+        uint4 w = *reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(faces + f) + 32);
+        FaceTail t;
+        t.adj[0] = static_cast<uint16_t>(w.x & 0xFFFFu);
+        t.adj[1] = static_cast<uint16_t>(w.x >> 16);
+        t.adj[2] = static_cast<uint16_t>(w.y & 0xFFFFu);
+        t.v[0] = static_cast<uint8_t>((w.y >> 16) & 0xFFu);
+        t.v[1] = static_cast<uint8_t>(w.y >> 24);
+        t.v[2] = static_cast<uint8_t>(w.z & 0xFFu);
+        t.obsolete = static_cast<uint8_t>((w.z >> 8) & 0xFFu);
+        return t;
+    }
+    __device__ __forceinline__ void store_tail(int f, const FaceTail &t)
+    {
+        uint4 w;
+        w.x = static_cast<uint32_t>(t.adj[0]) | (static_cast<uint32_t>(t.adj[1]) << 16);
+        w.y = static_cast<uint32_t>(t.adj[2]) | (static_cast<uint32_t>(t.v[0]) << 16) | (static_cast<uint32_t>(t.v[1]) << 24);
+        w.z = static_cast<uint32_t>(t.v[2]) | (static_cast<uint32_t>(t.obsolete) << 8);
+        w.w = 0;
+        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(faces + f) + 32) = w;
+    }
+    __device__ __forceinline__ void store_nd(int f, d3 n, double dist)
+    {
+        double2 *q = reinterpret_cast<double2 *>(faces + f);
+        q[0] = make_double2(n.x, n.y);
+        q[1] = make_double2(n.z, dist);
+    }
+    __device__ __forceinline__ void set_adj(int f, int e, uint16_t to) { faces[f].adj[e] = to; }
+    __device__ __forceinline__ void set_obsolete(int f) { faces[f].obsolete = 1; }
 };
 
-// libstdc++ std::__push_heap with comp(a,b) = dist[a] > dist[b]  (collision.cpp:390-395)
-__device__ __forceinline__ void heap_sift_up(HeapEnt *h, int hole, int top, HeapEnt value)
+// libstdc++ std::__push_heap with comp(a,b) = dist[a] > dist[b]  (collision.cpp:390-395).
+// The ancestor chain of `hole` is hole→(hole-1)/2→…→0; its indices are known up front, so all
+// ancestors are loaded together and the comparisons run on registers.
+__device__ __forceinline__ void heap_sift_up(HeapEnt *h, int hole, HeapEnt value)
 {
-    int parent = (hole - 1) / 2;
-    while (hole > top && h[parent].dist > value.dist)
+    HeapEnt anc[EPA_HEAP_LEVELS];
     {
-        h[hole] = h[parent];
-        hole = parent;
-        parent = (hole - 1) / 2;
+        int p = hole;
+#pragma unroll
+        for (int l = 0; l < EPA_HEAP_LEVELS; ++l)
+        {
+            if (p > 0)
+            {
+                p = (p - 1) / 2;
+                anc[l] = h[p];
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < EPA_HEAP_LEVELS; ++l)
+    {
+        if (hole > 0 && anc[l].dist > value.dist)
+        {
+            h[hole] = anc[l];
+            hole = (hole - 1) / 2;
+        }
+        else
+            break;
     }
     h[hole] = value;
 }
@@ -360,7 +431,7 @@ __device__ __forceinline__ void heap_push(HeapEnt *h, int &size, uint32_t face, 
     e.dist = dist;
     e.face = face;
     e._pad = 0;
-    heap_sift_up(h, size, 0, e);
+    heap_sift_up(h, size, e);
     ++size;
 }
 // libstdc++ std::pop_heap (→ __pop_heap → __adjust_heap) followed by back()/pop_back()
@@ -379,8 +450,14 @@ __device__ __forceinline__ uint32_t heap_pop(HeapEnt *h, int &size)
     while (child < (len - 1) / 2)
     {
         child = 2 * (child + 1);
-        if (h[child].dist > h[child - 1].dist) child--;
-        h[hole] = h[child];
+        HeapEnt r = h[child], l = h[child - 1]; // adjacent entries, one round trip
+        if (r.dist > l.dist)
+        {
+            child--;
+            h[hole] = l;
+        }
+        else
+            h[hole] = r;
         hole = child;
     }
     if ((len & 1) == 0 && child == (len - 2) / 2)
@@ -389,65 +466,52 @@ __device__ __forceinline__ uint32_t heap_pop(HeapEnt *h, int &size)
         h[hole] = h[child - 1];
         hole = child - 1;
     }
-    heap_sift_up(h, hole, 0, value);
+    // __push_heap(first, hole, 0, value): the ancestors of `hole` were all just rewritten by this
+    // thread; walk them directly (short chain, usually stops at once because value came from a leaf)
+    int parent = (hole - 1) / 2;
+    while (hole > 0 && h[parent].dist > value.dist)
+    {
+        h[hole] = h[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    h[hole] = value;
     size = len;
     return top_face;
 }
 
-// collision.cpp:273-297
-__device__ __forceinline__ double epa_init_face(EpaSlab &sl, int f, int i, int j, int k, int opposite)
+// collision.cpp:273-297.  Computes normal / distance of face (i, j, k) from vertex positions already
+// in registers; returns whether the orientation test flipped the face.
+__device__ __forceinline__ bool epa_face_plane(d3 pi, d3 pj, d3 pk, bool has_opp, d3 popp, d3 &n, double &dist)
 {
-    d3 pi = sl.vp(i);
-    d3 ab = sl.vp(j) - pi;
-    d3 ac = sl.vp(k) - pi;
-    d3 n = cross(ab, ac);
+    d3 ab = pj - pi;
+    d3 ac = pk - pi;
+    n = cross(ab, ac);
     if (sqnorm(n) < 1e-12)
         n = d3{0.0, 0.0, 0.0};
     else
         n = normalized(n);
-    uint8_t v1 = static_cast<uint8_t>(j), v2 = static_cast<uint8_t>(k);
-    if (opposite >= 0 && dot(n, sl.vp(opposite) - pi) > 0.0)
+    bool flip = false;
+    if (has_opp && dot(n, popp - pi) > 0.0)
     {
-        uint8_t t = v1;
-        v1 = v2;
-        v2 = t;
+        flip = true;
         n = -n;
     }
-    double dist = dot(n, pi);
-    sl.fnd[f] = make_double4(n.x, n.y, n.z, dist);
-    FaceTopo t;
-    t.adj[0] = t.adj[1] = t.adj[2] = EPA_NULL;
-    t._pad0 = 0;
-    t.v[0] = static_cast<uint8_t>(i);
-    t.v[1] = v1;
-    t.v[2] = v2;
-    t.obsolete = 0;
-    t._pad1 = 0;
-    sl.topo[f] = t;
-    return dist;
-}
-
-// collision.cpp:305-313
-__device__ __forceinline__ void epa_link(EpaSlab &sl, int f1, int f2, int va, int vb)
-{
-    FaceTopo a = sl.topo[f1];
-    int e1 = (a.v[0] == va) ? 0 : (a.v[1] == va ? 1 : 2);
-    sl.topo[f1].adj[e1] = static_cast<uint16_t>(f2);
-    FaceTopo b = sl.topo[f2];
-    int e2 = (b.v[0] == vb) ? 0 : (b.v[1] == vb ? 1 : 2);
-    sl.topo[f2].adj[e2] = static_cast<uint16_t>(f1);
+    dist = dot(n, pi);
+    return flip;
 }
 
 // collision.cpp:424-454
-__device__ __forceinline__ void epa_write_result(const EpaSlab &sl, int f, ContactRec *out, uint64_t key)
+__device__ __forceinline__ void epa_write_result(const EpaSlab &sl, double4 nd, const FaceTail &t, ContactRec *out, uint64_t key)
 {
-    double4 nd = sl.fnd[f];
-    FaceTopo t = sl.topo[f];
     d3 n{nd.x, nd.y, nd.z};
-    const double *q0 = sl.verts + 6 * t.v[0], *q1 = sl.verts + 6 * t.v[1], *q2 = sl.verts + 6 * t.v[2];
-    d3 a0{q0[0], q0[1], q0[2]}, b0{q0[3], q0[4], q0[5]};
-    d3 a1{q1[0], q1[1], q1[2]}, b1{q1[3], q1[4], q1[5]};
-    d3 a2{q2[0], q2[1], q2[2]}, b2{q2[3], q2[4], q2[5]};
+    const double2 *q0 = reinterpret_cast<const double2 *>(sl.verts + 6 * t.v[0]);
+    const double2 *q1 = reinterpret_cast<const double2 *>(sl.verts + 6 * t.v[1]);
+    const double2 *q2 = reinterpret_cast<const double2 *>(sl.verts + 6 * t.v[2]);
+    double2 x0 = q0[0], x1 = q0[1], x2 = q0[2], y0 = q1[0], y1 = q1[1], y2 = q1[2], z0 = q2[0], z1 = q2[1], z2 = q2[2];
+    d3 a0{x0.x, x0.y, x1.x}, b0{x1.y, x2.x, x2.y};
+    d3 a1{y0.x, y0.y, y1.x}, b1{y1.y, y2.x, y2.y};
+    d3 a2{z0.x, z0.y, z1.x}, b2{z1.y, z2.x, z2.y};
     d3 p0 = a0 - b0, p1 = a1 - b1, p2 = a2 - b2;
     d3 pm = n * nd.w;
     d3 v0 = p1 - p0, v1 = p2 - p0, v2 = pm - p0;
@@ -458,7 +522,7 @@ __device__ __forceinline__ void epa_write_result(const EpaSlab &sl, int f, Conta
     double u = 1.0 - v - w;
     d3 wa = (u * a0 + v * a1) + w * a2;
     d3 wb = (u * b0 + v * b1) + w * b2;
-    out->key = key;
+    out->key = key; // 88-byte records are only 8-byte aligned: scalar stores
     out->normal[0] = -n.x;
     out->normal[1] = -n.y;
     out->normal[2] = -n.z;
@@ -471,12 +535,66 @@ __device__ __forceinline__ void epa_write_result(const EpaSlab &sl, int f, Conta
     out->depth = nd.w;
 }
 
+// Per-thread copy of the two ShapeViews in shared memory (transposed: conflict-free), so that the
+// long-lived loop state of the persistent kernel fits in 128 registers.
+struct EpaShapeSmem
+{
+    double f[2][10][EPA_THREADS]; // p xyz, h xyz, q xyzw
+    const double *verts[2][EPA_THREADS];
+    int kind[2][EPA_THREADS];
+    uint32_t nverts[2][EPA_THREADS];
+};
+__device__ __forceinline__ void smem_put_shape(EpaShapeSmem &sm, int which, const ShapeView &v)
+{
+    const int t = threadIdx.x;
+    sm.f[which][0][t] = v.p.x; sm.f[which][1][t] = v.p.y; sm.f[which][2][t] = v.p.z;
+    sm.f[which][3][t] = v.h.x; sm.f[which][4][t] = v.h.y; sm.f[which][5][t] = v.h.z;
+    sm.f[which][6][t] = v.q.x; sm.f[which][7][t] = v.q.y; sm.f[which][8][t] = v.q.z; sm.f[which][9][t] = v.q.w;
+    sm.verts[which][t] = v.verts;
+    sm.kind[which][t] = v.kind;
+    sm.nverts[which][t] = v.nverts;
+}
+__device__ __forceinline__ ShapeView smem_get_shape(const EpaShapeSmem &sm, int which)
+{
+    const int t = threadIdx.x;
+    ShapeView v;
+    v.p = {sm.f[which][0][t], sm.f[which][1][t], sm.f[which][2][t]};
+    v.h = {sm.f[which][3][t], sm.f[which][4][t], sm.f[which][5][t]};
+    v.q = {sm.f[which][6][t], sm.f[which][7][t], sm.f[which][8][t], sm.f[which][9][t]};
+    v.verts = sm.verts[which][t];
+    v.kind = sm.kind[which][t];
+    v.nverts = sm.nverts[which][t];
+    return v;
+}
+__device__ __forceinline__ SupportPt minkowski_support_smem(const EpaShapeSmem &sm, d3 d)
+{
+    SupportPt s;
+    {
+        ShapeView A = smem_get_shape(sm, 0);
+        s.pa = support(A, d);
+    }
+    {
+        ShapeView B = smem_get_shape(sm, 1);
+        s.pb = support(B, -d);
+    }
+    return s;
+}
+
+#ifndef PK_EPA_MIN_BLOCKS
+#define PK_EPA_MIN_BLOCKS 8
+#endif
+#ifndef PK_EPA_FETCH_MIN
+#define PK_EPA_FETCH_MIN 6
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // K7b: persistent EPA (collision.cpp:411-504).
 //   out_index[pair] gives the slot of the pair's contact in the key-sorted contact array
 //   (exclusive scan of the GJK hit flags); valid[slot] = 1 when EPA produced a value.
+//   Lanes whose pair has finished wait until PK_EPA_FETCH_MIN lanes of the warp are idle (or nobody
+//   is left running) before the set-up path runs, so that path is never executed for one lane.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EPA_THREADS)
+__global__ void __launch_bounds__(EPA_THREADS, PK_EPA_MIN_BLOCKS)
 epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
            const uint32_t *__restrict__ pair_b, const SimplexRec *__restrict__ simplices,
            const unsigned long long *__restrict__ hit_count_ptr, uint64_t hit_capacity,
@@ -484,98 +602,128 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
            unsigned char *__restrict__ slabs, unsigned long long *__restrict__ cursor,
            unsigned long long *__restrict__ counters /* [0]=valid contacts, [1]=overflow */)
 {
+    __shared__ EpaShapeSmem shp;
     const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     EpaSlab sl(slabs + tid * EPA_SLAB_BYTES);
     unsigned long long nhits = *hit_count_ptr;
     if (nhits > hit_capacity) nhits = hit_capacity;
 
-    bool active = false;
-    ShapeView A, B;
+    bool active = false, done = false;
     int nfaces = 0, nverts = 0, heap_size = 0, iter = 0;
     uint32_t out_slot = 0;
     uint64_t key = 0;
     unsigned long long n_valid = 0, n_over = 0;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
 
     for (;;)
     {
-        if (!active)
+        const unsigned m_active = __ballot_sync(FULL, active);
+        const unsigned m_idle = __ballot_sync(FULL, !active && !done);
+        if (m_active == 0 && m_idle == 0) break;
+        if (!active && !done && (__popc(m_idle) >= PK_EPA_FETCH_MIN || m_active == 0))
         {
             unsigned long long slot = atomicAdd(cursor, 1ull);
-            if (slot >= nhits) break;
-            const SimplexRec *r = simplices + slot;
-            uint32_t pair = r->pair;
-            uint32_t ia, ib;
-            if (keys)
-            {
-                key = keys[pair];
-                ia = static_cast<uint32_t>(key >> 32);
-                ib = static_cast<uint32_t>(key & 0xFFFFFFFFu);
-            }
+            if (slot >= nhits)
+                done = true;
             else
             {
-                ia = pair_a[pair];
-                ib = pair_b[pair];
-                key = (static_cast<uint64_t>(ia) << 32) | ib;
-            }
-            out_slot = out_index[pair];
-            A = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ia);
-            B = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ib);
-            Simplex s;
-            s.n = static_cast<int>(r->n);
-            for (int i = 0; i < 4; ++i)
-            {
-                if (i < s.n)
+                const SimplexRec *r = simplices + slot;
+                uint32_t pair = r->pair;
+                uint32_t ia, ib;
+                if (keys)
                 {
-                    s.pt[i].pa = d3{r->v[i][0], r->v[i][1], r->v[i][2]};
-                    s.pt[i].pb = d3{r->v[i][3], r->v[i][4], r->v[i][5]};
+                    key = keys[pair];
+                    ia = static_cast<uint32_t>(key >> 32);
+                    ib = static_cast<uint32_t>(key & 0xFFFFFFFFu);
                 }
-            }
-            if (s.n < 4 && !pad_simplex(A, B, s))
-            {
-                valid[out_slot] = 0; // degenerate: treated as no collision (collision.cpp:414-415)
-                continue;
-            }
-            for (int i = 0; i < 4; ++i) sl.set_vert(i, s.pt[i]);
-            nverts = 4;
-            nfaces = 4;
-            heap_size = 0;
-            // build_initial_tetrahedron (collision.cpp:355-388)
-            heap_push(sl.heap, heap_size, 0, epa_init_face(sl, 0, 0, 1, 2, 3));
-            heap_push(sl.heap, heap_size, 1, epa_init_face(sl, 1, 0, 2, 3, 1));
-            heap_push(sl.heap, heap_size, 2, epa_init_face(sl, 2, 0, 3, 1, 2));
-            heap_push(sl.heap, heap_size, 3, epa_init_face(sl, 3, 1, 3, 2, 0));
-            for (int i = 0; i < 4; ++i)
-                for (int j = i + 1; j < 4; ++j)
+                else
                 {
-                    FaceTopo fi = sl.topo[i];
-                    FaceTopo fj = sl.topo[j];
-                    for (int e1 = 0; e1 < 3; ++e1)
+                    ia = pair_a[pair];
+                    ib = pair_b[pair];
+                    key = (static_cast<uint64_t>(ia) << 32) | ib;
+                }
+                out_slot = out_index[pair];
+                Simplex s;
+                s.n = static_cast<int>(r->n);
+                for (int i = 0; i < 4; ++i)
+                {
+                    if (i < s.n)
                     {
-                        uint8_t u1 = fi.v[e1], v1 = fi.v[(e1 + 1) % 3];
-                        for (int e2 = 0; e2 < 3; ++e2)
-                        {
-                            uint8_t u2 = fj.v[e2], v2 = fj.v[(e2 + 1) % 3];
-                            if (u1 == v2 && v1 == u2)
-                            {
-                                fi.adj[e1] = static_cast<uint16_t>(j);
-                                fj.adj[e2] = static_cast<uint16_t>(i);
-                            }
-                        }
+                        s.pt[i].pa = d3{r->v[i][0], r->v[i][1], r->v[i][2]};
+                        s.pt[i].pb = d3{r->v[i][3], r->v[i][4], r->v[i][5]};
                     }
-                    sl.topo[i] = fi;
-                    sl.topo[j] = fj;
                 }
-            iter = 0;
-            active = true;
+                bool ok = true;
+                {
+                    ShapeView A = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ia);
+                    ShapeView B = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ib);
+                    smem_put_shape(shp, 0, A);
+                    smem_put_shape(shp, 1, B);
+                    if (s.n < 4) ok = pad_simplex(A, B, s);
+                }
+                if (!ok)
+                    valid[out_slot] = 0; // degenerate: treated as no collision (collision.cpp:414-415)
+                else
+                {
+                    d3 pv[4];
+                    for (int i = 0; i < 4; ++i)
+                    {
+                        sl.set_vert(i, s.pt[i]);
+                        pv[i] = P(s.pt[i]);
+                    }
+                    nverts = 4;
+                    nfaces = 4;
+                    heap_size = 0;
+                    // build_initial_tetrahedron (collision.cpp:355-388): faces (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0)
+                    const int fi[4] = {0, 0, 0, 1}, fj[4] = {1, 2, 3, 3}, fk[4] = {2, 3, 1, 2}, fo[4] = {3, 1, 2, 0};
+                    FaceTail tl[4];
+                    for (int f = 0; f < 4; ++f)
+                    {
+                        d3 n;
+                        double dist;
+                        bool flip = epa_face_plane(pv[fi[f]], pv[fj[f]], pv[fk[f]], true, pv[fo[f]], n, dist);
+                        tl[f].v[0] = static_cast<uint8_t>(fi[f]);
+                        tl[f].v[1] = static_cast<uint8_t>(flip ? fk[f] : fj[f]);
+                        tl[f].v[2] = static_cast<uint8_t>(flip ? fj[f] : fk[f]);
+                        tl[f].adj[0] = tl[f].adj[1] = tl[f].adj[2] = EPA_NULL;
+                        tl[f].obsolete = 0;
+                        sl.store_nd(f, n, dist);
+                        heap_push(sl.heap, heap_size, static_cast<uint32_t>(f), dist);
+                    }
+                    for (int i = 0; i < 4; ++i)
+                        for (int j = i + 1; j < 4; ++j)
+                            for (int e1 = 0; e1 < 3; ++e1)
+                            {
+                                uint8_t u1 = tl[i].v[e1], v1 = tl[i].v[(e1 + 1) % 3];
+                                for (int e2 = 0; e2 < 3; ++e2)
+                                {
+                                    uint8_t u2 = tl[j].v[e2], v2 = tl[j].v[(e2 + 1) % 3];
+                                    if (u1 == v2 && v1 == u2)
+                                    {
+                                        tl[i].adj[e1] = static_cast<uint16_t>(j);
+                                        tl[j].adj[e2] = static_cast<uint16_t>(i);
+                                    }
+                                }
+                            }
+                    for (int f = 0; f < 4; ++f) sl.store_tail(f, tl[f]);
+                    iter = 0;
+                    active = true;
+                }
+            }
         }
+        if (!active) continue;
 
         // ---- one EPA iteration, or the post-loop "best guess" when iter == 64 -----------------
         // pop_face(): skip obsolete entries (collision.cpp:397-408)
         int min_face = -1;
+        double4 mf;
+        FaceTail mt;
         while (heap_size > 0)
         {
             uint32_t f = heap_pop(sl.heap, heap_size);
-            if (!sl.topo[f].obsolete)
+            mf = sl.load_nd(f);
+            mt = sl.load_tail(f);
+            if (!mt.obsolete)
             {
                 min_face = static_cast<int>(f);
                 break;
@@ -589,65 +737,86 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
         }
         if (iter >= 64)
         {
-            epa_write_result(sl, min_face, contacts + out_slot, key); // best guess (collision.cpp:500-503)
+            epa_write_result(sl, mf, mt, contacts + out_slot, key); // best guess (collision.cpp:500-503)
             valid[out_slot] = 1;
             ++n_valid;
             active = false;
             continue;
         }
         ++iter;
-        double4 mf = sl.fnd[min_face];
         d3 mn{mf.x, mf.y, mf.z};
-        SupportPt sp = minkowski_support(A, B, mn);
+        SupportPt sp = minkowski_support_smem(shp, mn);
         d3 p = P(sp);
         if (dot(mn, p) - mf.w < 1e-6)
         {
-            epa_write_result(sl, min_face, contacts + out_slot, key); // converged (collision.cpp:465-466)
+            epa_write_result(sl, mf, mt, contacts + out_slot, key); // converged (collision.cpp:465-466)
             valid[out_slot] = 1;
             ++n_valid;
             active = false;
             continue;
         }
 
-        // find_silhouette (collision.cpp:315-353): DFS, LIFO stack, edge order preserved
+        // find_silhouette (collision.cpp:315-353): DFS, LIFO stack, edge order preserved.
+        // The three neighbours of a face are fetched together before any is examined.
         uint16_t stack[EPA_MAX_STACK];
         uint8_t hz_start[EPA_MAX_HORIZON], hz_end[EPA_MAX_HORIZON];
         uint16_t hz_adj[EPA_MAX_HORIZON];
         int sp_top = 0, nh = 0;
         bool overflow = false;
-        stack[sp_top++] = static_cast<uint16_t>(min_face);
-        sl.topo[min_face].obsolete = 1;
-        while (sp_top > 0)
+        sl.set_obsolete(min_face);
         {
-            int cur = stack[--sp_top];
-            FaceTopo cf = sl.topo[cur];
-            for (int i = 0; i < 3; ++i)
+            FaceTail cf = mt;
+            int cur = min_face;
+            for (;;)
             {
-                uint16_t nidx = cf.adj[i];
-                if (nidx == EPA_NULL) continue;
-                if (sl.topo[nidx].obsolete) continue;
-                double4 nf = sl.fnd[nidx];
-                if (dot(d3{nf.x, nf.y, nf.z}, p) > nf.w + 1e-6)
+                double4 nf[3];
+                uint8_t nobs[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
                 {
-                    sl.topo[nidx].obsolete = 1;
-                    if (sp_top < EPA_MAX_STACK)
-                        stack[sp_top++] = nidx;
-                    else
-                        overflow = true;
-                }
-                else
-                {
-                    if (nh < EPA_MAX_HORIZON)
+                    uint16_t nidx = cf.adj[i];
+                    if (nidx != EPA_NULL)
                     {
-                        hz_start[nh] = cf.v[i];
-                        hz_end[nh] = cf.v[(i + 1) % 3];
-                        hz_adj[nh] = nidx;
-                        ++nh;
+                        nf[i] = sl.load_nd(nidx);
+                        nobs[i] = sl.faces[nidx].obsolete;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                {
+                    uint16_t nidx = cf.adj[i];
+                    if (nidx == EPA_NULL) continue;
+                    // a neighbour reached twice from this face sees the flag set by the first visit
+                    bool obs = nobs[i] != 0;
+                    if (i >= 1 && cf.adj[0] == nidx && dot(d3{nf[0].x, nf[0].y, nf[0].z}, p) > nf[0].w + 1e-6) obs = true;
+                    if (i == 2 && cf.adj[1] == nidx && dot(d3{nf[1].x, nf[1].y, nf[1].z}, p) > nf[1].w + 1e-6) obs = true;
+                    if (obs) continue;
+                    if (dot(d3{nf[i].x, nf[i].y, nf[i].z}, p) > nf[i].w + 1e-6)
+                    {
+                        sl.set_obsolete(nidx);
+                        if (sp_top < EPA_MAX_STACK)
+                            stack[sp_top++] = nidx;
+                        else
+                            overflow = true;
                     }
                     else
-                        overflow = true;
+                    {
+                        if (nh < EPA_MAX_HORIZON)
+                        {
+                            hz_start[nh] = cf.v[i];
+                            hz_end[nh] = cf.v[(i + 1) % 3];
+                            hz_adj[nh] = nidx;
+                            ++nh;
+                        }
+                        else
+                            overflow = true;
+                    }
                 }
+                if (sp_top == 0) break;
+                cur = stack[--sp_top];
+                cf = sl.load_tail(cur);
             }
+            (void)cur;
         }
         if (nh == 0 && !overflow)
         {
@@ -665,21 +834,71 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
         sl.set_vert(nverts, sp);
         const int p_idx = nverts++;
         const int first_new = nfaces;
+        nfaces += nh;
+        // new faces (start, end, p_idx), no orientation flip (collision.cpp:475-482).  Planes first
+        // (independent work), then adjacency, then the heap.
+        double new_dist[EPA_MAX_HORIZON];
         for (int e = 0; e < nh; ++e)
         {
-            int f = nfaces++;
-            double dist = epa_init_face(sl, f, hz_start[e], hz_end[e], p_idx, -1);
-            epa_link(sl, f, hz_adj[e], hz_start[e], hz_end[e]);
-            heap_push(sl.heap, heap_size, static_cast<uint32_t>(f), dist);
+            d3 n;
+            double dist;
+            epa_face_plane(sl.vp(hz_start[e]), sl.vp(hz_end[e]), p, false, d3{0, 0, 0}, n, dist);
+            new_dist[e] = dist;
+            sl.store_nd(first_new + e, n, dist);
+            // link_faces(f, adj_face, start, end): on the old face the edge starts at `end`
+            FaceTail b = sl.load_tail(hz_adj[e]);
+            int e2 = (b.v[0] == hz_end[e]) ? 0 : (b.v[1] == hz_end[e] ? 1 : 2);
+            sl.set_adj(hz_adj[e], e2, static_cast<uint16_t>(first_new + e));
         }
-        for (int i = 0; i < nh; ++i)
-            for (int j = i + 1; j < nh; ++j)
+        // ring links among the new faces (collision.cpp:484-497), same order and overwrite semantics as
+        // the reference's i<j double loop, but on registers: face e = (start_e, end_e, p_idx), so
+        // link_faces(i, j, end_i, p_idx) sets adj[edge of end_i in face i] and adj[edge of p_idx in face j].
+        {
+            uint16_t nadj[EPA_MAX_HORIZON][3];
+            for (int e = 0; e < nh; ++e)
             {
-                if (hz_end[i] == hz_start[j])
-                    epa_link(sl, first_new + i, first_new + j, hz_end[i], p_idx);
-                else if (hz_start[i] == hz_end[j])
-                    epa_link(sl, first_new + j, first_new + i, hz_end[j], p_idx);
+                // link_faces(f, adj, start, end) on the new face: edge index of `start` (= 0)
+                nadj[e][0] = hz_adj[e];
+                nadj[e][1] = EPA_NULL;
+                nadj[e][2] = EPA_NULL;
             }
+            for (int i = 0; i < nh; ++i)
+                for (int j = i + 1; j < nh; ++j)
+                {
+                    int a, b, va;
+                    if (hz_end[i] == hz_start[j])
+                    {
+                        a = i;
+                        b = j;
+                        va = hz_end[i];
+                    }
+                    else if (hz_start[i] == hz_end[j])
+                    {
+                        a = j;
+                        b = i;
+                        va = hz_end[j];
+                    }
+                    else
+                        continue;
+                    int e1 = (hz_start[a] == va) ? 0 : (hz_end[a] == va ? 1 : 2);
+                    int e2 = (hz_start[b] == p_idx) ? 0 : (hz_end[b] == p_idx ? 1 : 2);
+                    nadj[a][e1] = static_cast<uint16_t>(first_new + b);
+                    nadj[b][e2] = static_cast<uint16_t>(first_new + a);
+                }
+            for (int e = 0; e < nh; ++e)
+            {
+                FaceTail t;
+                t.adj[0] = nadj[e][0];
+                t.adj[1] = nadj[e][1];
+                t.adj[2] = nadj[e][2];
+                t.v[0] = hz_start[e];
+                t.v[1] = hz_end[e];
+                t.v[2] = static_cast<uint8_t>(p_idx);
+                t.obsolete = 0;
+                sl.store_tail(first_new + e, t);
+            }
+        }
+        for (int e = 0; e < nh; ++e) heap_push(sl.heap, heap_size, static_cast<uint32_t>(first_new + e), new_dist[e]);
     }
     if (n_valid) atomicAdd(counters + 0, n_valid);
     if (n_over) atomicAdd(counters + 1, n_over);
