@@ -54,7 +54,10 @@ enum Counter
     C_VALID,
     C_EPA_OVERFLOW,
     C_SCAN_TOTAL,
-    C_COUNT = 8
+    C_GJK_CURSOR,
+    C_CLASS_COUNT, // [3]
+    C_CLASS_FILL = C_CLASS_COUNT + 3, // [3]
+    C_COUNT = 16
 };
 
 } // namespace
@@ -108,8 +111,10 @@ struct pk_ctx
     ContactRec *d_contacts_final = nullptr;
     uint8_t *d_valid = nullptr;
     uint32_t *d_valid_index = nullptr;
+    uint32_t *d_epa_order = nullptr;
     unsigned char *d_slabs = nullptr;
     uint32_t epa_blocks = 0;
+    uint32_t gjk_blocks = 0;
 
     // results
     int32_t epoch = 0;
@@ -236,8 +241,9 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
     if (timed) cudaEventRecord(ctx->ev[ST_GJK], ctx->stream);
     if (npairs)
     {
-        gjk_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit,
-                                                                 ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts);
+        gjk_kernel<<<div_up(npairs, PK_GJK_THREADS), PK_GJK_THREADS, 0, ctx->stream>>>(
+            body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
+            ctx->d_counters + C_CLASS_COUNT);
         ctx->launches += 1;
     }
     if (timed) cudaEventRecord(ctx->ev[ST_SCAN], ctx->stream);
@@ -252,11 +258,14 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
     if (timed) cudaEventRecord(ctx->ev[ST_EPA], ctx->stream);
     if (npairs)
     {
+        epa_order_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
+                                                                     ctx->d_counters + C_CLASS_COUNT, ctx->d_counters + C_CLASS_FILL,
+                                                                     ctx->d_epa_order);
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
-            ctx->d_out_index, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs, ctx->d_counters + C_EPA_CURSOR,
+            ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs, ctx->d_counters + C_EPA_CURSOR,
             ctx->d_counters + C_VALID);
-        ctx->launches += 1;
+        ctx->launches += 2;
     }
     if (timed) cudaEventRecord(ctx->ev[ST_COMPACT], ctx->stream);
     PK_CUDA(cudaGetLastError());
@@ -308,7 +317,7 @@ int pk_destroy(pk_ctx *ctx)
                    ctx->d_leaves,      ctx->d_nodes,        ctx->d_right,       ctx->d_range_last,   ctx->d_root,
                    ctx->d_merge_flag,  ctx->d_pkeys[0],     ctx->d_pkeys[1],    ctx->d_hit,          ctx->d_out_index,
                    ctx->d_scan_tiles,  ctx->d_simplices,    ctx->d_contacts[0], ctx->d_contacts[1],  ctx->d_valid,
-                   ctx->d_valid_index, ctx->d_slabs};
+                   ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -398,8 +407,13 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     A(ctx->d_contacts[1], nc);
     A(ctx->d_valid, nc + 16);
     A(ctx->d_valid_index, nc);
+    A(ctx->d_epa_order, nc);
     // persistent EPA grid: enough resident threads to fill the machine, never more than the work
     {
+        int gjk_per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm, gjk_kernel, PK_GJK_THREADS, 0) != cudaSuccess || gjk_per_sm < 1)
+            gjk_per_sm = 2;
+        ctx->gjk_blocks = static_cast<uint32_t>(ctx->sm_count * gjk_per_sm);
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_kernel, EPA_THREADS, 0) != cudaSuccess || per_sm < 1)
             per_sm = 4;

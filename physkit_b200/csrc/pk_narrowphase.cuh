@@ -39,8 +39,8 @@ __device__ __forceinline__ SupportPt minkowski_support(const ShapeView &a, const
     return s;
 }
 
-// Terminating simplex handed from GJK to EPA: 200 bytes.
-struct SimplexRec
+// Terminating simplex handed from GJK to EPA: 208 bytes (16-byte aligned).
+struct alignas(16) SimplexRec
 {
     double v[4][6]; // pa xyz, pb xyz
     uint32_t n;
@@ -62,8 +62,12 @@ __device__ __forceinline__ void sx_erase(Simplex &s, int i)
     --s.n;
 }
 
+// The handlers return the UN-normalised search direction; the caller normalises once.  Every
+// branch of the reference ends in `direction = X.normalized()`, so this is the same arithmetic with
+// one call site instead of eleven (smaller code: the r1 profile showed instruction-fetch stalls).
+
 // collision.cpp:12-41
-__device__ __forceinline__ void handle_line(Simplex &s, d3 &dir)
+__device__ __forceinline__ d3 handle_line(Simplex &s)
 {
     const d3 a = P(s.pt[1]);
     const d3 b = P(s.pt[0]);
@@ -77,20 +81,16 @@ __device__ __forceinline__ void handle_line(Simplex &s, d3 &dir)
             d3 ab_hat = normalized(ab);
             d3 perp = cross(ab_hat, d3{0.0, 1.0, 0.0});
             if (sqnorm(perp) < 1e-12) perp = cross(ab_hat, d3{0.0, 0.0, 1.0});
-            dir = normalized(perp);
+            return perp;
         }
-        else
-            dir = normalized(triple);
+        return triple;
     }
-    else
-    {
-        sx_erase(s, 0);
-        dir = normalized(ao);
-    }
+    sx_erase(s, 0);
+    return ao;
 }
 
 // collision.cpp:43-88
-__device__ __forceinline__ void handle_triangle(Simplex &s, d3 &dir)
+__device__ __forceinline__ d3 handle_triangle(Simplex &s)
 {
     const d3 a = P(s.pt[2]);
     const d3 b = P(s.pt[1]);
@@ -104,30 +104,31 @@ __device__ __forceinline__ void handle_triangle(Simplex &s, d3 &dir)
     {
         sx_erase(s, 0);
         d3 triple = cross(cross(ab, ao), ab);
-        dir = (sqnorm(triple) < 1e-12) ? normalized(ao) : normalized(triple);
-        return;
+        return (sqnorm(triple) < 1e-12) ? ao : triple;
     }
     const d3 ac_perp = cross(abc, ac);
     if (dot(ac_perp, ao) > 0.0)
     {
         sx_erase(s, 1);
         d3 triple = cross(cross(ac, ao), ac);
-        dir = (sqnorm(triple) < 1e-12) ? normalized(ao) : normalized(triple);
-        return;
+        return (sqnorm(triple) < 1e-12) ? ao : triple;
     }
     if (dot(abc, ao) <= 0.0)
     {
         SupportPt t = s.pt[0];
         s.pt[0] = s.pt[1];
         s.pt[1] = t;
-        dir = normalized(-abc);
+        return -abc;
     }
-    else
-        dir = normalized(abc);
+    return abc;
 }
 
-// collision.cpp:90-147; returns true when the tetrahedron encloses the origin
-__device__ __forceinline__ bool handle_tetrahedron(Simplex &s, d3 &dir)
+// collision.cpp:90-147.  Returns true when the tetrahedron encloses the origin; otherwise the simplex
+// has been rebuilt as the selected triangle ({c,b,a} / {d,c,a} / {b,d,a}) and the caller continues
+// with handle_triangle, exactly as the reference's `return handle_triangle(simplex, direction)`.
+// (The reference's `direction = abc.normalized()` before that call is dead: handle_triangle always
+// overwrites the direction.)
+__device__ __forceinline__ bool handle_tetrahedron(Simplex &s)
 {
     const SupportPt sa = s.pt[3], sb = s.pt[2], sc = s.pt[1], sd = s.pt[0];
     const d3 a = P(sa), b = P(sb), c = P(sc), d = P(sd);
@@ -138,56 +139,52 @@ __device__ __forceinline__ bool handle_tetrahedron(Simplex &s, d3 &dir)
     if (dot(abc, d - a) > 0.0) abc = -abc;
     if (dot(acd, b - a) > 0.0) acd = -acd;
     if (dot(adb, c - a) > 0.0) adb = -adb;
+    int sel = -1;
     if (dot(abc, ao) > 0.0)
-    {
-        s.pt[0] = sc;
-        s.pt[1] = sb;
-        s.pt[2] = sa;
-        s.n = 3;
-        handle_triangle(s, dir);
-        return false;
-    }
-    if (dot(acd, ao) > 0.0)
-    {
-        s.pt[0] = sd;
-        s.pt[1] = sc;
-        s.pt[2] = sa;
-        s.n = 3;
-        handle_triangle(s, dir);
-        return false;
-    }
-    if (dot(adb, ao) > 0.0)
-    {
-        s.pt[0] = sb;
-        s.pt[1] = sd;
-        s.pt[2] = sa;
-        s.n = 3;
-        handle_triangle(s, dir);
-        return false;
-    }
-    return true;
+        sel = 0;
+    else if (dot(acd, ao) > 0.0)
+        sel = 1;
+    else if (dot(adb, ao) > 0.0)
+        sel = 2;
+    if (sel < 0) return true;
+    s.pt[0] = (sel == 0) ? sc : (sel == 1 ? sd : sb);
+    s.pt[1] = (sel == 0) ? sb : (sel == 1 ? sc : sd);
+    s.pt[2] = sa;
+    s.n = 3;
+    return false;
+}
+
+// One GJK iteration after the support point has been pushed (collision.cpp:149-162, 185).
+// Returns true when the origin is enclosed.
+__device__ __forceinline__ bool handle_simplex(Simplex &s, d3 &dir)
+{
+    if (s.n == 4 && handle_tetrahedron(s)) return true;
+    d3 raw = (s.n == 3) ? handle_triangle(s) : handle_line(s);
+    dir = normalized(raw);
+    return false;
 }
 
 // collision.cpp:165-189.  Returns true with the terminating simplex when the shapes intersect.
+// The first support (direction (1,0,0)) and the loop's supports share one call site.
 __device__ __forceinline__ bool gjk_collision(const ShapeView &A, const ShapeView &B, Simplex &s)
 {
     d3 dir{1.0, 0.0, 0.0};
-    s.pt[0] = minkowski_support(A, B, dir);
-    s.n = 1;
-    d3 p0 = P(s.pt[0]);
-    if (sqnorm(p0) < 1e-12) return true;
-    dir = -normalized(p0);
-    for (int iter = 0; iter < 100; ++iter)
+    s.n = 0;
+    for (int iter = -1; iter < 100; ++iter)
     {
         SupportPt np = minkowski_support(A, B, dir);
-        if (dot(P(np), dir) <= 0.0) return false;
+        d3 p = P(np);
+        if (iter < 0)
+        {
+            s.pt[0] = np;
+            s.n = 1;
+            if (sqnorm(p) < 1e-12) return true;
+            dir = -normalized(p);
+            continue;
+        }
+        if (dot(p, dir) <= 0.0) return false;
         s.pt[s.n++] = np;
-        if (s.n == 2)
-            handle_line(s, dir);
-        else if (s.n == 3)
-            handle_triangle(s, dir);
-        else if (handle_tetrahedron(s, dir))
-            return true;
+        if (handle_simplex(s, dir)) return true;
     }
     return false;
 }
@@ -242,10 +239,21 @@ struct BodyArrays
     const uint32_t *shape_id;
 };
 
-__global__ void __launch_bounds__(128)
+#ifndef PK_GJK_THREADS
+#define PK_GJK_THREADS 128
+#endif
+#ifndef PK_GJK_MIN_BLOCKS
+#define PK_GJK_MIN_BLOCKS 3
+#endif
+
+// One thread per candidate pair.  (A persistent-lane variant with per-lane refill was measured in r1
+// and lost: with a mean of 1.9 iterations per pair half the lanes refill every round and the set-up
+// path — two gathered body loads — then sits on the critical path of every round.)
+__global__ void __launch_bounds__(PK_GJK_THREADS, PK_GJK_MIN_BLOCKS)
 gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
            const uint32_t *__restrict__ pair_b, uint64_t npairs, uint8_t *__restrict__ hit,
-           SimplexRec *__restrict__ simplices, unsigned long long *__restrict__ hit_count, uint64_t hit_capacity)
+           SimplexRec *__restrict__ simplices, unsigned long long *__restrict__ hit_count, uint64_t hit_capacity,
+           unsigned long long *__restrict__ class_count /*[3]*/)
 {
     uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (k >= npairs) return;
@@ -276,15 +284,16 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
             {
                 if (i < s.n)
                 {
-                    r->v[i][0] = s.pt[i].pa.x;
-                    r->v[i][1] = s.pt[i].pa.y;
-                    r->v[i][2] = s.pt[i].pa.z;
-                    r->v[i][3] = s.pt[i].pb.x;
-                    r->v[i][4] = s.pt[i].pb.y;
-                    r->v[i][5] = s.pt[i].pb.z;
+                    double2 *d = reinterpret_cast<double2 *>(&r->v[i][0]);
+                    d[0] = make_double2(s.pt[i].pa.x, s.pt[i].pa.y);
+                    d[1] = make_double2(s.pt[i].pa.z, s.pt[i].pb.x);
+                    d[2] = make_double2(s.pt[i].pb.y, s.pt[i].pb.z);
                 }
             }
-            r->n = static_cast<uint32_t>(s.n);
+            // EPA cost class: smooth (sphere) supports need many more EPA iterations than polyhedra
+            const uint32_t cls = (A.kind == KIND_SPHERE ? 1u : 0u) + (B.kind == KIND_SPHERE ? 1u : 0u);
+            atomicAdd(class_count + cls, 1ull);
+            r->n = static_cast<uint32_t>(s.n) | (cls << 8);
             r->pair = static_cast<uint32_t>(k);
         }
     }
@@ -580,8 +589,28 @@ __device__ __forceinline__ SupportPt minkowski_support_smem(const EpaShapeSmem &
     return s;
 }
 
+// Hit slots grouped by EPA cost class (heaviest first) so that the lanes of a warp work on pairs of
+// similar shape: similar trip counts, same support code path.  order[rank] = slot.
+__global__ void __launch_bounds__(256)
+epa_order_kernel(const SimplexRec *__restrict__ simplices, const unsigned long long *__restrict__ hit_count_ptr,
+                 uint64_t hit_capacity, const unsigned long long *__restrict__ class_count,
+                 unsigned long long *__restrict__ class_fill, uint32_t *__restrict__ order)
+{
+    unsigned long long nhits = *hit_count_ptr;
+    if (nhits > hit_capacity) nhits = hit_capacity;
+    const unsigned long long c2 = class_count[2], c1 = class_count[1];
+    for (unsigned long long s = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; s < nhits;
+         s += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+    {
+        const uint32_t cls = (simplices[s].n >> 8) & 3u;
+        const unsigned long long base = (cls == 2) ? 0ull : (cls == 1 ? c2 : c2 + c1);
+        const unsigned long long pos = base + atomicAdd(class_fill + cls, 1ull);
+        if (pos < hit_capacity) order[pos] = static_cast<uint32_t>(s);
+    }
+}
+
 #ifndef PK_EPA_MIN_BLOCKS
-#define PK_EPA_MIN_BLOCKS 8
+#define PK_EPA_MIN_BLOCKS 6
 #endif
 #ifndef PK_EPA_FETCH_MIN
 #define PK_EPA_FETCH_MIN 6
@@ -598,8 +627,8 @@ __global__ void __launch_bounds__(EPA_THREADS, PK_EPA_MIN_BLOCKS)
 epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
            const uint32_t *__restrict__ pair_b, const SimplexRec *__restrict__ simplices,
            const unsigned long long *__restrict__ hit_count_ptr, uint64_t hit_capacity,
-           const uint32_t *__restrict__ out_index, ContactRec *__restrict__ contacts, uint8_t *__restrict__ valid,
-           unsigned char *__restrict__ slabs, unsigned long long *__restrict__ cursor,
+           const uint32_t *__restrict__ out_index, const uint32_t *__restrict__ order, ContactRec *__restrict__ contacts,
+           uint8_t *__restrict__ valid, unsigned char *__restrict__ slabs, unsigned long long *__restrict__ cursor,
            unsigned long long *__restrict__ counters /* [0]=valid contacts, [1]=overflow */)
 {
     __shared__ EpaShapeSmem shp;
@@ -627,7 +656,7 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                 done = true;
             else
             {
-                const SimplexRec *r = simplices + slot;
+                const SimplexRec *r = simplices + order[slot];
                 uint32_t pair = r->pair;
                 uint32_t ia, ib;
                 if (keys)
@@ -644,7 +673,7 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                 }
                 out_slot = out_index[pair];
                 Simplex s;
-                s.n = static_cast<int>(r->n);
+                s.n = static_cast<int>(r->n & 0xFFu);
                 for (int i = 0; i < 4; ++i)
                 {
                     if (i < s.n)
