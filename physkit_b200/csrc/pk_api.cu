@@ -417,6 +417,9 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_kernel, EPA_THREADS, 0) != cudaSuccess || per_sm < 1)
             per_sm = 4;
+#ifdef PK_EPA_BLOCKS_PER_SM
+        per_sm = std::min(per_sm, PK_EPA_BLOCKS_PER_SM);
+#endif
         uint64_t want_threads = static_cast<uint64_t>(ctx->sm_count) * per_sm * EPA_THREADS;
         uint64_t need_threads = ((nc + EPA_THREADS - 1) / EPA_THREADS) * EPA_THREADS;
         uint64_t threads = std::min(want_threads, std::max<uint64_t>(need_threads, EPA_THREADS));

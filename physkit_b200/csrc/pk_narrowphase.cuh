@@ -243,7 +243,7 @@ struct BodyArrays
 #define PK_GJK_THREADS 128
 #endif
 #ifndef PK_GJK_MIN_BLOCKS
-#define PK_GJK_MIN_BLOCKS 3
+#define PK_GJK_MIN_BLOCKS 4
 #endif
 
 // One thread per candidate pair.  (A persistent-lane variant with per-lane refill was measured in r1
