@@ -648,7 +648,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         uint32_t p_begin = static_cast<uint32_t>(static_cast<uint64_t>(m) * ctx->cfg.shard_rank / ctx->cfg.shard_count);
         uint32_t p_end = static_cast<uint32_t>(static_cast<uint64_t>(m) * (ctx->cfg.shard_rank + 1) / ctx->cfg.shard_count);
         if (p_end > p_begin)
-            overlap_kernel<<<div_up(p_end - p_begin, 128), 128, 0, s>>>(ctx->d_nodes, ctx->d_leaves, m, p_begin, p_end, mode_query,
+            overlap_kernel<<<div_up(p_end - p_begin, OVERLAP_THREADS), OVERLAP_THREADS, 0, s>>>(ctx->d_nodes, ctx->d_leaves, m, p_begin, p_end, mode_query,
                                                                        ctx->d_pkeys[0], ctx->cfg.max_pairs,
                                                                        ctx->d_counters + C_PAIRS);
         ctx->launches += 4;
