@@ -20,7 +20,10 @@ namespace pk
 
 constexpr int EPA_MAX_FACES = 768; // reference: unbounded (InlinedVector spills); overflow is flagged
 constexpr int EPA_MAX_VERTS = 68;  // 4 + 64 iterations
-constexpr int EPA_MAX_HORIZON = 32; // reference InlinedVector<…,32> inline capacity; observed max 10
+#ifndef PK_EPA_MAX_HORIZON
+#define PK_EPA_MAX_HORIZON 32
+#endif
+constexpr int EPA_MAX_HORIZON = PK_EPA_MAX_HORIZON; // reference InlinedVector<…,32> inline capacity; observed max 10
 constexpr int EPA_MAX_STACK = 32;   // observed max 4
 constexpr int EPA_THREADS = 64;
 
@@ -300,26 +303,31 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// EPA polytope in a per-thread HBM slab.
+// EPA polytope: per-thread slab in HBM + the hot top of the face heap in shared memory.
 //
-// The kernel is bound by the latency of dependent loads into the slab, not by bandwidth or FP64
-// issue (ncu r1: 72 % of stall samples long_scoreboard, FP64 pipe 4.5 %).  The layout and the code
-// below are therefore organised so that every step issues all the loads it will need at once:
-//   * a face is ONE 48-byte record (normal, distance, vertices, adjacency, obsolete flag)
-//   * heap entries carry a copy of the face distance, so sifting never touches the face array;
-//     sift-up prefetches the whole ancestor chain (its indices do not depend on loaded data)
-//   * linking new faces never re-reads what was just written: the adjacency of the new faces is
-//     built in registers and each record is stored once
+// The kernel is bound by the latency of dependent accesses to the polytope, not by bandwidth or FP64
+// issue (ncu r1, 1 M bodies: 76 % of stall samples long_scoreboard, FP64 pipe 5 %, 41 GB of DRAM
+// traffic for 0.4 GB of algorithmic bytes).  Layout and code are organised around that:
+//   * the first EPA_HEAP_SMEM heap entries (levels 0-4 and part of 5: where every sift starts) live in
+//     shared memory, transposed per thread; deeper entries spill to the slab
+//   * heap entries carry a copy of the face distance, so sifting never touches the face array
+//   * "obsolete" is a 768-bit per-thread bitset, so lazy heap deletion and the flood fill test it
+//     without a memory round trip to the face
+//   * face plane (normal, distance) is one 32-byte sector; topology (vertices, adjacency) 16 bytes
+//   * the flood fill fetches the three neighbour planes of a face together
+//   * new faces are linked in registers and stored once; ring links are found through a vertex→edge
+//     table in O(h), with the reference's O(h²) loop kept for degenerate horizons
+//   * vertex positions p = pa − pb are kept in their own 32-byte records (hot), pa / pb (only needed
+//     for the final barycentric witness points) in cold ones
 // ---------------------------------------------------------------------------------------------
-struct alignas(16) FaceRec
+struct alignas(16) FaceTopo
 {
-    double nx, ny, nz, dist;
     uint16_t adj[3];
     uint8_t v[3];
-    uint8_t obsolete;
-    uint8_t _pad[6];
+    uint8_t _pad0;
+    uint16_t _pad1[3];
 };
-static_assert(sizeof(FaceRec) == 48, "FaceRec is three 16-byte words");
+static_assert(sizeof(FaceTopo) == 16, "FaceTopo is one 16-byte word");
 
 struct alignas(16) HeapEnt
 {
@@ -329,112 +337,141 @@ struct alignas(16) HeapEnt
 };
 
 constexpr uint16_t EPA_NULL = 0xFFFFu;
-constexpr int EPA_HEAP_LEVELS = 10; // 2^10 > EPA_MAX_FACES
-constexpr size_t EPA_SLAB_BYTES = static_cast<size_t>(EPA_MAX_FACES) * (sizeof(FaceRec) + sizeof(HeapEnt)) +
-                                  static_cast<size_t>(EPA_MAX_VERTS) * 48;
-
-// second 16-byte word group of a FaceRec as loaded/stored in one transaction
-struct FaceTail
-{
-    uint16_t adj[3];
-    uint8_t v[3];
-    uint8_t obsolete;
-};
+#ifndef PK_EPA_HEAP_SMEM
+#define PK_EPA_HEAP_SMEM 20
+#endif
+constexpr int EPA_HEAP_SMEM = PK_EPA_HEAP_SMEM;
+constexpr int EPA_OBS_WORDS = EPA_MAX_FACES / 32;
+constexpr size_t EPA_SLAB_BYTES = static_cast<size_t>(EPA_MAX_FACES) * (32 + sizeof(FaceTopo) + sizeof(HeapEnt)) +
+                                  static_cast<size_t>(EPA_MAX_VERTS) * (32 + 48);
 
 struct EpaSlab
 {
-    FaceRec *faces;
-    HeapEnt *heap; // binary heap, min distance at the root
-    double *verts; // pa xyz, pb xyz per polytope vertex
+    double4 *plane;   // normal xyz, distance (one sector per face)
+    FaceTopo *topo;   // vertices, adjacency
+    HeapEnt *heap;    // heap entries with index >= EPA_HEAP_SMEM
+    double4 *vpos;    // p = pa - pb per polytope vertex (w unused)
+    double *vab;      // pa xyz, pb xyz per polytope vertex
     __device__ __forceinline__ explicit EpaSlab(unsigned char *base)
     {
-        faces = reinterpret_cast<FaceRec *>(base);
-        heap = reinterpret_cast<HeapEnt *>(base + static_cast<size_t>(EPA_MAX_FACES) * sizeof(FaceRec));
-        verts = reinterpret_cast<double *>(base + static_cast<size_t>(EPA_MAX_FACES) * (sizeof(FaceRec) + sizeof(HeapEnt)));
+        plane = reinterpret_cast<double4 *>(base);
+        base += static_cast<size_t>(EPA_MAX_FACES) * 32;
+        topo = reinterpret_cast<FaceTopo *>(base);
+        base += static_cast<size_t>(EPA_MAX_FACES) * sizeof(FaceTopo);
+        heap = reinterpret_cast<HeapEnt *>(base);
+        base += static_cast<size_t>(EPA_MAX_FACES) * sizeof(HeapEnt);
+        vpos = reinterpret_cast<double4 *>(base);
+        base += static_cast<size_t>(EPA_MAX_VERTS) * 32;
+        vab = reinterpret_cast<double *>(base);
     }
     __device__ __forceinline__ d3 vp(int i) const
     {
-        const double2 *v = reinterpret_cast<const double2 *>(verts + 6 * i);
-        double2 a = v[0], b = v[1], c = v[2];
-        return {a.x - b.y, a.y - c.x, b.x - c.y}; // pa - pb
+        const double2 *v = reinterpret_cast<const double2 *>(vpos + i);
+        double2 a = v[0], b = v[1];
+        return {a.x, a.y, b.x};
     }
-    __device__ __forceinline__ void set_vert(int i, const SupportPt &s)
+    __device__ __forceinline__ void set_vert(int i, const SupportPt &s, d3 p)
     {
-        double2 *v = reinterpret_cast<double2 *>(verts + 6 * i);
+        double2 *q = reinterpret_cast<double2 *>(vpos + i);
+        q[0] = make_double2(p.x, p.y);
+        q[1] = make_double2(p.z, 0.0);
+        double2 *v = reinterpret_cast<double2 *>(vab + 6 * i);
         v[0] = make_double2(s.pa.x, s.pa.y);
         v[1] = make_double2(s.pa.z, s.pb.x);
         v[2] = make_double2(s.pb.y, s.pb.z);
     }
-    __device__ __forceinline__ double4 load_nd(int f) const
+    __device__ __forceinline__ double4 load_plane(int f) const
     {
-        const double2 *q = reinterpret_cast<const double2 *>(faces + f);
+        const double2 *q = reinterpret_cast<const double2 *>(plane + f);
         double2 a = q[0], b = q[1];
         return make_double4(a.x, a.y, b.x, b.y);
     }
-    __device__ __forceinline__ FaceTail load_tail(int f) const
+    __device__ __forceinline__ void store_plane(int f, d3 n, double dist)
     {
-        uint4 w = *reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(faces + f) + 32);
-        FaceTail t;
+        double2 *q = reinterpret_cast<double2 *>(plane + f);
+        q[0] = make_double2(n.x, n.y);
+        q[1] = make_double2(n.z, dist);
+    }
+    __device__ __forceinline__ FaceTopo load_topo(int f) const
+    {
+        uint4 w = *reinterpret_cast<const uint4 *>(topo + f);
+        FaceTopo t;
         t.adj[0] = static_cast<uint16_t>(w.x & 0xFFFFu);
         t.adj[1] = static_cast<uint16_t>(w.x >> 16);
         t.adj[2] = static_cast<uint16_t>(w.y & 0xFFFFu);
         t.v[0] = static_cast<uint8_t>((w.y >> 16) & 0xFFu);
         t.v[1] = static_cast<uint8_t>(w.y >> 24);
         t.v[2] = static_cast<uint8_t>(w.z & 0xFFu);
-        t.obsolete = static_cast<uint8_t>((w.z >> 8) & 0xFFu);
         return t;
     }
-    __device__ __forceinline__ void store_tail(int f, const FaceTail &t)
+    __device__ __forceinline__ void store_topo(int f, const FaceTopo &t)
     {
         uint4 w;
         w.x = static_cast<uint32_t>(t.adj[0]) | (static_cast<uint32_t>(t.adj[1]) << 16);
         w.y = static_cast<uint32_t>(t.adj[2]) | (static_cast<uint32_t>(t.v[0]) << 16) | (static_cast<uint32_t>(t.v[1]) << 24);
-        w.z = static_cast<uint32_t>(t.v[2]) | (static_cast<uint32_t>(t.obsolete) << 8);
+        w.z = static_cast<uint32_t>(t.v[2]);
         w.w = 0;
-        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(faces + f) + 32) = w;
+        *reinterpret_cast<uint4 *>(topo + f) = w;
     }
-    __device__ __forceinline__ void store_nd(int f, d3 n, double dist)
-    {
-        double2 *q = reinterpret_cast<double2 *>(faces + f);
-        q[0] = make_double2(n.x, n.y);
-        q[1] = make_double2(n.z, dist);
-    }
-    __device__ __forceinline__ void set_adj(int f, int e, uint16_t to) { faces[f].adj[e] = to; }
-    __device__ __forceinline__ void set_obsolete(int f) { faces[f].obsolete = 1; }
+    __device__ __forceinline__ void set_adj(int f, int e, uint16_t to) { topo[f].adj[e] = to; }
 };
 
-// libstdc++ std::__push_heap with comp(a,b) = dist[a] > dist[b]  (collision.cpp:390-395).
-// The ancestor chain of `hole` is hole→(hole-1)/2→…→0; its indices are known up front, so all
-// ancestors are loaded together and the comparisons run on registers.
-__device__ __forceinline__ void heap_sift_up(HeapEnt *h, int hole, HeapEnt value)
+// Shared-memory part of the kernel state, transposed so that lane t owns column t.
+struct EpaSmem
 {
-    HeapEnt anc[EPA_HEAP_LEVELS];
+    double f[2][10][EPA_THREADS]; // shape views: p xyz, h xyz, q xyzw
+    const double *verts[2][EPA_THREADS];
+    int kind[2][EPA_THREADS];
+    uint32_t nverts[2][EPA_THREADS];
+    double hdist[EPA_HEAP_SMEM][EPA_THREADS];
+    uint16_t hface[EPA_HEAP_SMEM][EPA_THREADS];
+};
+
+struct EpaHeap
+{
+    EpaSmem *sm;
+    HeapEnt *g;
+    __device__ __forceinline__ HeapEnt get(int k) const
     {
-        int p = hole;
-#pragma unroll
-        for (int l = 0; l < EPA_HEAP_LEVELS; ++l)
+        HeapEnt e;
+        if (k < EPA_HEAP_SMEM)
         {
-            if (p > 0)
-            {
-                p = (p - 1) / 2;
-                anc[l] = h[p];
-            }
-        }
-    }
-#pragma unroll
-    for (int l = 0; l < EPA_HEAP_LEVELS; ++l)
-    {
-        if (hole > 0 && anc[l].dist > value.dist)
-        {
-            h[hole] = anc[l];
-            hole = (hole - 1) / 2;
+            e.dist = sm->hdist[k][threadIdx.x];
+            e.face = sm->hface[k][threadIdx.x];
+            e._pad = 0;
         }
         else
-            break;
+            e = g[k];
+        return e;
     }
-    h[hole] = value;
+    __device__ __forceinline__ double dist(int k) const { return (k < EPA_HEAP_SMEM) ? sm->hdist[k][threadIdx.x] : g[k].dist; }
+    __device__ __forceinline__ void set(int k, const HeapEnt &e) const
+    {
+        if (k < EPA_HEAP_SMEM)
+        {
+            sm->hdist[k][threadIdx.x] = e.dist;
+            sm->hface[k][threadIdx.x] = static_cast<uint16_t>(e.face);
+        }
+        else
+            g[k] = e;
+    }
+};
+
+// libstdc++ std::__push_heap with comp(a,b) = dist[a] > dist[b]  (collision.cpp:390-395)
+__device__ __forceinline__ void heap_sift_up(const EpaHeap &h, int hole, const HeapEnt &value)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > 0)
+    {
+        HeapEnt pe = h.get(parent);
+        if (!(pe.dist > value.dist)) break;
+        h.set(hole, pe);
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    h.set(hole, value);
 }
-__device__ __forceinline__ void heap_push(HeapEnt *h, int &size, uint32_t face, double dist)
+__device__ __forceinline__ void heap_push(const EpaHeap &h, int &size, uint32_t face, double dist)
 {
     HeapEnt e;
     e.dist = dist;
@@ -444,47 +481,38 @@ __device__ __forceinline__ void heap_push(HeapEnt *h, int &size, uint32_t face, 
     ++size;
 }
 // libstdc++ std::pop_heap (→ __pop_heap → __adjust_heap) followed by back()/pop_back()
-__device__ __forceinline__ uint32_t heap_pop(HeapEnt *h, int &size)
+__device__ __forceinline__ uint32_t heap_pop(const EpaHeap &h, int &size)
 {
     if (size == 1)
     {
         size = 0;
-        return h[0].face;
+        return h.get(0).face;
     }
     const int len = size - 1;
-    HeapEnt value = h[len];
-    uint32_t top_face = h[0].face;
+    const HeapEnt value = h.get(len);
+    const uint32_t top_face = h.get(0).face;
     int hole = 0;
     int child = 0;
     while (child < (len - 1) / 2)
     {
         child = 2 * (child + 1);
-        HeapEnt r = h[child], l = h[child - 1]; // adjacent entries, one round trip
+        HeapEnt r = h.get(child), l = h.get(child - 1);
         if (r.dist > l.dist)
         {
             child--;
-            h[hole] = l;
+            h.set(hole, l);
         }
         else
-            h[hole] = r;
+            h.set(hole, r);
         hole = child;
     }
     if ((len & 1) == 0 && child == (len - 2) / 2)
     {
         child = 2 * (child + 1);
-        h[hole] = h[child - 1];
+        h.set(hole, h.get(child - 1));
         hole = child - 1;
     }
-    // __push_heap(first, hole, 0, value): the ancestors of `hole` were all just rewritten by this
-    // thread; walk them directly (short chain, usually stops at once because value came from a leaf)
-    int parent = (hole - 1) / 2;
-    while (hole > 0 && h[parent].dist > value.dist)
-    {
-        h[hole] = h[parent];
-        hole = parent;
-        parent = (hole - 1) / 2;
-    }
-    h[hole] = value;
+    heap_sift_up(h, hole, value); // __push_heap(first, hole, 0, value)
     size = len;
     return top_face;
 }
@@ -511,12 +539,12 @@ __device__ __forceinline__ bool epa_face_plane(d3 pi, d3 pj, d3 pk, bool has_opp
 }
 
 // collision.cpp:424-454
-__device__ __forceinline__ void epa_write_result(const EpaSlab &sl, double4 nd, const FaceTail &t, ContactRec *out, uint64_t key)
+__device__ __forceinline__ void epa_write_result(const EpaSlab &sl, double4 nd, const FaceTopo &t, ContactRec *out, uint64_t key)
 {
     d3 n{nd.x, nd.y, nd.z};
-    const double2 *q0 = reinterpret_cast<const double2 *>(sl.verts + 6 * t.v[0]);
-    const double2 *q1 = reinterpret_cast<const double2 *>(sl.verts + 6 * t.v[1]);
-    const double2 *q2 = reinterpret_cast<const double2 *>(sl.verts + 6 * t.v[2]);
+    const double2 *q0 = reinterpret_cast<const double2 *>(sl.vab + 6 * t.v[0]);
+    const double2 *q1 = reinterpret_cast<const double2 *>(sl.vab + 6 * t.v[1]);
+    const double2 *q2 = reinterpret_cast<const double2 *>(sl.vab + 6 * t.v[2]);
     double2 x0 = q0[0], x1 = q0[1], x2 = q0[2], y0 = q1[0], y1 = q1[1], y2 = q1[2], z0 = q2[0], z1 = q2[1], z2 = q2[2];
     d3 a0{x0.x, x0.y, x1.x}, b0{x1.y, x2.x, x2.y};
     d3 a1{y0.x, y0.y, y1.x}, b1{y1.y, y2.x, y2.y};
@@ -544,16 +572,7 @@ __device__ __forceinline__ void epa_write_result(const EpaSlab &sl, double4 nd, 
     out->depth = nd.w;
 }
 
-// Per-thread copy of the two ShapeViews in shared memory (transposed: conflict-free), so that the
-// long-lived loop state of the persistent kernel fits in 128 registers.
-struct EpaShapeSmem
-{
-    double f[2][10][EPA_THREADS]; // p xyz, h xyz, q xyzw
-    const double *verts[2][EPA_THREADS];
-    int kind[2][EPA_THREADS];
-    uint32_t nverts[2][EPA_THREADS];
-};
-__device__ __forceinline__ void smem_put_shape(EpaShapeSmem &sm, int which, const ShapeView &v)
+__device__ __forceinline__ void smem_put_shape(EpaSmem &sm, int which, const ShapeView &v)
 {
     const int t = threadIdx.x;
     sm.f[which][0][t] = v.p.x; sm.f[which][1][t] = v.p.y; sm.f[which][2][t] = v.p.z;
@@ -563,7 +582,7 @@ __device__ __forceinline__ void smem_put_shape(EpaShapeSmem &sm, int which, cons
     sm.kind[which][t] = v.kind;
     sm.nverts[which][t] = v.nverts;
 }
-__device__ __forceinline__ ShapeView smem_get_shape(const EpaShapeSmem &sm, int which)
+__device__ __forceinline__ ShapeView smem_get_shape(const EpaSmem &sm, int which)
 {
     const int t = threadIdx.x;
     ShapeView v;
@@ -575,7 +594,7 @@ __device__ __forceinline__ ShapeView smem_get_shape(const EpaShapeSmem &sm, int 
     v.nverts = sm.nverts[which][t];
     return v;
 }
-__device__ __forceinline__ SupportPt minkowski_support_smem(const EpaShapeSmem &sm, d3 d)
+__device__ __forceinline__ SupportPt minkowski_support_smem(const EpaSmem &sm, d3 d)
 {
     SupportPt s;
     {
@@ -631,9 +650,10 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
            uint8_t *__restrict__ valid, unsigned char *__restrict__ slabs, unsigned long long *__restrict__ cursor,
            unsigned long long *__restrict__ counters /* [0]=valid contacts, [1]=overflow */)
 {
-    __shared__ EpaShapeSmem shp;
+    __shared__ EpaSmem shm;
     const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     EpaSlab sl(slabs + tid * EPA_SLAB_BYTES);
+    EpaHeap heap{&shm, sl.heap};
     unsigned long long nhits = *hit_count_ptr;
     if (nhits > hit_capacity) nhits = hit_capacity;
 
@@ -642,6 +662,10 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
     uint32_t out_slot = 0;
     uint64_t key = 0;
     unsigned long long n_valid = 0, n_over = 0;
+    uint32_t obs[EPA_OBS_WORDS];           // obsolete flags of the current polytope
+    uint8_t edge_of_start[EPA_MAX_VERTS];  // vertex → horizon edge starting there (0xFF = none)
+    uint8_t edge_of_end[EPA_MAX_VERTS];
+    for (int i = 0; i < EPA_MAX_VERTS; ++i) edge_of_start[i] = edge_of_end[i] = 0xFF;
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
     for (;;)
@@ -686,8 +710,8 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                 {
                     ShapeView A = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ia);
                     ShapeView B = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ib);
-                    smem_put_shape(shp, 0, A);
-                    smem_put_shape(shp, 1, B);
+                    smem_put_shape(shm, 0, A);
+                    smem_put_shape(shm, 1, B);
                     if (s.n < 4) ok = pad_simplex(A, B, s);
                 }
                 if (!ok)
@@ -697,15 +721,16 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                     d3 pv[4];
                     for (int i = 0; i < 4; ++i)
                     {
-                        sl.set_vert(i, s.pt[i]);
                         pv[i] = P(s.pt[i]);
+                        sl.set_vert(i, s.pt[i], pv[i]);
                     }
                     nverts = 4;
                     nfaces = 4;
                     heap_size = 0;
+                    for (int w = 0; w < EPA_OBS_WORDS; ++w) obs[w] = 0u;
                     // build_initial_tetrahedron (collision.cpp:355-388): faces (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0)
                     const int fi[4] = {0, 0, 0, 1}, fj[4] = {1, 2, 3, 3}, fk[4] = {2, 3, 1, 2}, fo[4] = {3, 1, 2, 0};
-                    FaceTail tl[4];
+                    FaceTopo tl[4];
                     for (int f = 0; f < 4; ++f)
                     {
                         d3 n;
@@ -715,9 +740,8 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                         tl[f].v[1] = static_cast<uint8_t>(flip ? fk[f] : fj[f]);
                         tl[f].v[2] = static_cast<uint8_t>(flip ? fj[f] : fk[f]);
                         tl[f].adj[0] = tl[f].adj[1] = tl[f].adj[2] = EPA_NULL;
-                        tl[f].obsolete = 0;
-                        sl.store_nd(f, n, dist);
-                        heap_push(sl.heap, heap_size, static_cast<uint32_t>(f), dist);
+                        sl.store_plane(f, n, dist);
+                        heap_push(heap, heap_size, static_cast<uint32_t>(f), dist);
                     }
                     for (int i = 0; i < 4; ++i)
                         for (int j = i + 1; j < 4; ++j)
@@ -734,7 +758,7 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                                     }
                                 }
                             }
-                    for (int f = 0; f < 4; ++f) sl.store_tail(f, tl[f]);
+                    for (int f = 0; f < 4; ++f) sl.store_topo(f, tl[f]);
                     iter = 0;
                     active = true;
                 }
@@ -745,14 +769,10 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
         // ---- one EPA iteration, or the post-loop "best guess" when iter == 64 -----------------
         // pop_face(): skip obsolete entries (collision.cpp:397-408)
         int min_face = -1;
-        double4 mf;
-        FaceTail mt;
         while (heap_size > 0)
         {
-            uint32_t f = heap_pop(sl.heap, heap_size);
-            mf = sl.load_nd(f);
-            mt = sl.load_tail(f);
-            if (!mt.obsolete)
+            uint32_t f = heap_pop(heap, heap_size);
+            if (!((obs[f >> 5] >> (f & 31u)) & 1u))
             {
                 min_face = static_cast<int>(f);
                 break;
@@ -764,6 +784,8 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
             active = false;
             continue;
         }
+        const double4 mf = sl.load_plane(min_face);
+        const FaceTopo mt = sl.load_topo(min_face);
         if (iter >= 64)
         {
             epa_write_result(sl, mf, mt, contacts + out_slot, key); // best guess (collision.cpp:500-503)
@@ -774,7 +796,7 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
         }
         ++iter;
         d3 mn{mf.x, mf.y, mf.z};
-        SupportPt sp = minkowski_support_smem(shp, mn);
+        SupportPt sp = minkowski_support_smem(shm, mn);
         d3 p = P(sp);
         if (dot(mn, p) - mf.w < 1e-6)
         {
@@ -786,43 +808,36 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
         }
 
         // find_silhouette (collision.cpp:315-353): DFS, LIFO stack, edge order preserved.
-        // The three neighbours of a face are fetched together before any is examined.
         uint16_t stack[EPA_MAX_STACK];
         uint8_t hz_start[EPA_MAX_HORIZON], hz_end[EPA_MAX_HORIZON];
         uint16_t hz_adj[EPA_MAX_HORIZON];
         int sp_top = 0, nh = 0;
         bool overflow = false;
-        sl.set_obsolete(min_face);
+        obs[min_face >> 5] |= 1u << (min_face & 31);
         {
-            FaceTail cf = mt;
-            int cur = min_face;
+            FaceTopo cf = mt;
             for (;;)
             {
                 double4 nf[3];
-                uint8_t nobs[3];
+                bool live[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
                 {
                     uint16_t nidx = cf.adj[i];
-                    if (nidx != EPA_NULL)
-                    {
-                        nf[i] = sl.load_nd(nidx);
-                        nobs[i] = sl.faces[nidx].obsolete;
-                    }
+                    live[i] = nidx != EPA_NULL && !((obs[nidx >> 5] >> (nidx & 31u)) & 1u);
+                    if (live[i]) nf[i] = sl.load_plane(nidx);
                 }
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
                 {
+                    if (!live[i]) continue;
                     uint16_t nidx = cf.adj[i];
-                    if (nidx == EPA_NULL) continue;
-                    // a neighbour reached twice from this face sees the flag set by the first visit
-                    bool obs = nobs[i] != 0;
-                    if (i >= 1 && cf.adj[0] == nidx && dot(d3{nf[0].x, nf[0].y, nf[0].z}, p) > nf[0].w + 1e-6) obs = true;
-                    if (i == 2 && cf.adj[1] == nidx && dot(d3{nf[1].x, nf[1].y, nf[1].z}, p) > nf[1].w + 1e-6) obs = true;
-                    if (obs) continue;
+                    // a neighbour reached through two edges of this face: the second visit must see the
+                    // flag set by the first one
+                    if ((obs[nidx >> 5] >> (nidx & 31u)) & 1u) continue;
                     if (dot(d3{nf[i].x, nf[i].y, nf[i].z}, p) > nf[i].w + 1e-6)
                     {
-                        sl.set_obsolete(nidx);
+                        obs[nidx >> 5] |= 1u << (nidx & 31);
                         if (sp_top < EPA_MAX_STACK)
                             stack[sp_top++] = nidx;
                         else
@@ -842,10 +857,8 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                     }
                 }
                 if (sp_top == 0) break;
-                cur = stack[--sp_top];
-                cf = sl.load_tail(cur);
+                cf = sl.load_topo(stack[--sp_top]);
             }
-            (void)cur;
         }
         if (nh == 0 && !overflow)
         {
@@ -860,12 +873,11 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
             active = false;
             continue;
         }
-        sl.set_vert(nverts, sp);
+        sl.set_vert(nverts, sp, p);
         const int p_idx = nverts++;
         const int first_new = nfaces;
         nfaces += nh;
-        // new faces (start, end, p_idx), no orientation flip (collision.cpp:475-482).  Planes first
-        // (independent work), then adjacency, then the heap.
+        // new faces (start, end, p_idx), no orientation flip (collision.cpp:475-482)
         double new_dist[EPA_MAX_HORIZON];
         for (int e = 0; e < nh; ++e)
         {
@@ -873,61 +885,90 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
             double dist;
             epa_face_plane(sl.vp(hz_start[e]), sl.vp(hz_end[e]), p, false, d3{0, 0, 0}, n, dist);
             new_dist[e] = dist;
-            sl.store_nd(first_new + e, n, dist);
-            // link_faces(f, adj_face, start, end): on the old face the edge starts at `end`
-            FaceTail b = sl.load_tail(hz_adj[e]);
+            sl.store_plane(first_new + e, n, dist);
+            // link_faces(f, adj_face, start, end): on the old face the shared edge starts at `end`
+            FaceTopo b = sl.load_topo(hz_adj[e]);
             int e2 = (b.v[0] == hz_end[e]) ? 0 : (b.v[1] == hz_end[e] ? 1 : 2);
             sl.set_adj(hz_adj[e], e2, static_cast<uint16_t>(first_new + e));
         }
-        // ring links among the new faces (collision.cpp:484-497), same order and overwrite semantics as
-        // the reference's i<j double loop, but on registers: face e = (start_e, end_e, p_idx), so
-        // link_faces(i, j, end_i, p_idx) sets adj[edge of end_i in face i] and adj[edge of p_idx in face j].
+        // ring links among the new faces (collision.cpp:484-497).  Face e = (start_e, end_e, p_idx);
+        // link_faces(i, j, end_i, p_idx) sets adj[edge of end_i in face i] = j and adj[edge of p_idx in
+        // face j] = i.  For a proper horizon (every vertex starts exactly one edge and ends exactly one,
+        // no self loop, no 2-cycle) every successor link is made exactly once whatever the visiting
+        // order, so a vertex→edge table gives the same result in O(h).  Anything else takes the
+        // reference's i<j double loop with its overwrite order.
         {
             uint16_t nadj[EPA_MAX_HORIZON][3];
+            bool proper = nh >= 3;
             for (int e = 0; e < nh; ++e)
             {
-                // link_faces(f, adj, start, end) on the new face: edge index of `start` (= 0)
-                nadj[e][0] = hz_adj[e];
+                nadj[e][0] = hz_adj[e]; // link_faces(f, adj, start, end) on the new face: edge of `start` (= 0)
                 nadj[e][1] = EPA_NULL;
                 nadj[e][2] = EPA_NULL;
+                if (edge_of_start[hz_start[e]] != 0xFF || edge_of_end[hz_end[e]] != 0xFF || hz_start[e] == hz_end[e]) proper = false;
+                edge_of_start[hz_start[e]] = static_cast<uint8_t>(e);
+                edge_of_end[hz_end[e]] = static_cast<uint8_t>(e);
             }
-            for (int i = 0; i < nh; ++i)
-                for (int j = i + 1; j < nh; ++j)
+            if (proper)
+            {
+                for (int e = 0; e < nh; ++e)
                 {
-                    int a, b, va;
-                    if (hz_end[i] == hz_start[j])
-                    {
-                        a = i;
-                        b = j;
-                        va = hz_end[i];
-                    }
-                    else if (hz_start[i] == hz_end[j])
-                    {
-                        a = j;
-                        b = i;
-                        va = hz_end[j];
-                    }
-                    else
-                        continue;
-                    int e1 = (hz_start[a] == va) ? 0 : (hz_end[a] == va ? 1 : 2);
-                    int e2 = (hz_start[b] == p_idx) ? 0 : (hz_end[b] == p_idx ? 1 : 2);
-                    nadj[a][e1] = static_cast<uint16_t>(first_new + b);
-                    nadj[b][e2] = static_cast<uint16_t>(first_new + a);
+                    const uint8_t j = edge_of_start[hz_end[e]];
+                    if (j == 0xFF) continue;
+                    if (edge_of_start[hz_end[j]] == e) proper = false; // 2-cycle: reference links only one way
                 }
+            }
+            if (proper)
+            {
+                for (int e = 0; e < nh; ++e)
+                {
+                    const uint8_t j = edge_of_start[hz_end[e]];
+                    if (j == 0xFF) continue;
+                    nadj[e][1] = static_cast<uint16_t>(first_new + j);
+                    nadj[j][2] = static_cast<uint16_t>(first_new + e);
+                }
+            }
+            else
+            {
+                for (int i = 0; i < nh; ++i)
+                    for (int j = i + 1; j < nh; ++j)
+                    {
+                        int a, b, va;
+                        if (hz_end[i] == hz_start[j])
+                        {
+                            a = i;
+                            b = j;
+                            va = hz_end[i];
+                        }
+                        else if (hz_start[i] == hz_end[j])
+                        {
+                            a = j;
+                            b = i;
+                            va = hz_end[j];
+                        }
+                        else
+                            continue;
+                        int e1 = (hz_start[a] == va) ? 0 : (hz_end[a] == va ? 1 : 2);
+                        int e2 = (hz_start[b] == p_idx) ? 0 : (hz_end[b] == p_idx ? 1 : 2);
+                        nadj[a][e1] = static_cast<uint16_t>(first_new + b);
+                        nadj[b][e2] = static_cast<uint16_t>(first_new + a);
+                    }
+            }
             for (int e = 0; e < nh; ++e)
             {
-                FaceTail t;
+                edge_of_start[hz_start[e]] = 0xFF;
+                edge_of_end[hz_end[e]] = 0xFF;
+                FaceTopo t;
                 t.adj[0] = nadj[e][0];
                 t.adj[1] = nadj[e][1];
                 t.adj[2] = nadj[e][2];
                 t.v[0] = hz_start[e];
                 t.v[1] = hz_end[e];
                 t.v[2] = static_cast<uint8_t>(p_idx);
-                t.obsolete = 0;
-                sl.store_tail(first_new + e, t);
+                sl.store_topo(first_new + e, t);
             }
         }
-        for (int e = 0; e < nh; ++e) heap_push(sl.heap, heap_size, static_cast<uint32_t>(first_new + e), new_dist[e]);
+        for (int e = 0; e < nh; ++e) heap_push(heap, heap_size, static_cast<uint32_t>(first_new + e), new_dist[e]);
     }
     if (n_valid) atomicAdd(counters + 0, n_valid);
     if (n_over) atomicAdd(counters + 1, n_over);
