@@ -112,6 +112,7 @@ struct pk_ctx
     uint8_t *d_valid = nullptr;
     uint32_t *d_valid_index = nullptr;
     uint32_t *d_epa_order = nullptr;
+    uint32_t *d_gjk_work = nullptr;
     unsigned char *d_slabs = nullptr;
     uint32_t epa_blocks = 0;
     uint32_t gjk_blocks = 0;
@@ -241,10 +242,12 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
     if (timed) cudaEventRecord(ctx->ev[ST_GJK], ctx->stream);
     if (npairs)
     {
+        gjk_prefilter_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit,
+                                                                          ctx->d_gjk_work, ctx->d_counters + C_GJK_CURSOR);
         gjk_kernel<<<div_up(npairs, PK_GJK_THREADS), PK_GJK_THREADS, 0, ctx->stream>>>(
-            body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
-            ctx->d_counters + C_CLASS_COUNT);
-        ctx->launches += 1;
+            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_gjk_work, ctx->d_counters + C_GJK_CURSOR, ctx->d_hit, ctx->d_simplices,
+            ctx->d_counters + C_HITS, ctx->max_contacts, ctx->d_counters + C_CLASS_COUNT);
+        ctx->launches += 2;
     }
     if (timed) cudaEventRecord(ctx->ev[ST_SCAN], ctx->stream);
     if (npairs)
@@ -317,7 +320,7 @@ int pk_destroy(pk_ctx *ctx)
                    ctx->d_leaves,      ctx->d_nodes,        ctx->d_right,       ctx->d_range_last,   ctx->d_root,
                    ctx->d_merge_flag,  ctx->d_pkeys[0],     ctx->d_pkeys[1],    ctx->d_hit,          ctx->d_out_index,
                    ctx->d_scan_tiles,  ctx->d_simplices,    ctx->d_contacts[0], ctx->d_contacts[1],  ctx->d_valid,
-                   ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order};
+                   ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order,    ctx->d_gjk_work};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -408,6 +411,7 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     A(ctx->d_valid, nc + 16);
     A(ctx->d_valid_index, nc);
     A(ctx->d_epa_order, nc);
+    A(ctx->d_gjk_work, np);
     // persistent EPA grid: enough resident threads to fill the machine, never more than the work
     {
         int gjk_per_sm = 0;

@@ -249,18 +249,9 @@ struct BodyArrays
 #define PK_GJK_MIN_BLOCKS 4
 #endif
 
-// One thread per candidate pair.  (A persistent-lane variant with per-lane refill was measured in r1
-// and lost: with a mean of 1.9 iterations per pair half the lanes refill every round and the set-up
-// path — two gathered body loads — then sits on the critical path of every round.)
-__global__ void __launch_bounds__(PK_GJK_THREADS, PK_GJK_MIN_BLOCKS)
-gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
-           const uint32_t *__restrict__ pair_b, uint64_t npairs, uint8_t *__restrict__ hit,
-           SimplexRec *__restrict__ simplices, unsigned long long *__restrict__ hit_count, uint64_t hit_capacity,
-           unsigned long long *__restrict__ class_count /*[3]*/)
+__device__ __forceinline__ void load_pair(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
+                                          const uint32_t *__restrict__ pair_b, uint64_t k, uint32_t &ia, uint32_t &ib)
 {
-    uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (k >= npairs) return;
-    uint32_t ia, ib;
     if (keys)
     {
         uint64_t key = keys[k];
@@ -272,6 +263,63 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
         ia = pair_a[k];
         ib = pair_b[k];
     }
+}
+
+// K7a-0: the first two support evaluations of gjk_collision for every pair (collision.cpp:170-182).
+// 59 % of C3's candidate pairs end right there (second support makes no progress ⇒ separated); they get
+// hit = 0 and never reach the divergent part.  All lanes do identical work, so this kernel runs at full
+// lane efficiency; survivors are appended to a work list and redone from scratch by gjk_kernel (the
+// two redundant supports cost less than carrying 120 bytes of state per survivor through HBM).
+__global__ void __launch_bounds__(128)
+gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
+                     const uint32_t *__restrict__ pair_b, uint64_t npairs, uint8_t *__restrict__ hit,
+                     uint32_t *__restrict__ work, unsigned long long *__restrict__ work_count)
+{
+    const uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    bool survive = false;
+    if (k < npairs)
+    {
+        uint32_t ia, ib;
+        load_pair(keys, pair_a, pair_b, k, ia, ib);
+        ShapeView A = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ia);
+        ShapeView B = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ib);
+        d3 p0 = P(minkowski_support(A, B, d3{1.0, 0.0, 0.0}));
+        if (sqnorm(p0) < 1e-12)
+            survive = true; // origin hit on the first point: full path decides (collision.cpp:174)
+        else
+        {
+            d3 dir = -normalized(p0);
+            d3 p1 = P(minkowski_support(A, B, dir));
+            survive = !(dot(p1, dir) <= 0.0); // collision.cpp:181-182
+        }
+        if (!survive) hit[k] = 0;
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, survive);
+    if (m)
+    {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(work_count, static_cast<unsigned long long>(__popc(m)));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+        if (survive) work[base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint32_t>(k);
+    }
+}
+
+// One thread per surviving pair.  (A persistent-lane variant with per-lane refill was measured in r1
+// and lost: with a mean of 1.9 iterations per pair half the lanes refill every round and the set-up
+// path — two gathered body loads — then sits on the critical path of every round.)
+__global__ void __launch_bounds__(PK_GJK_THREADS, PK_GJK_MIN_BLOCKS)
+gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
+           const uint32_t *__restrict__ pair_b, const uint32_t *__restrict__ work,
+           const unsigned long long *__restrict__ work_count, uint8_t *__restrict__ hit,
+           SimplexRec *__restrict__ simplices, unsigned long long *__restrict__ hit_count, uint64_t hit_capacity,
+           unsigned long long *__restrict__ class_count /*[3]*/)
+{
+    const uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (w >= *work_count) return;
+    const uint64_t k = work[w];
+    uint32_t ia, ib;
+    load_pair(keys, pair_a, pair_b, k, ia, ib);
     ShapeView A = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ia);
     ShapeView B = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ib);
     Simplex s;
@@ -295,7 +343,10 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
             }
             // EPA cost class: smooth (sphere) supports need many more EPA iterations than polyhedra
             const uint32_t cls = (A.kind == KIND_SPHERE ? 1u : 0u) + (B.kind == KIND_SPHERE ? 1u : 0u);
-            atomicAdd(class_count + cls, 1ull);
+            {
+                const unsigned peers = __match_any_sync(__activemask(), cls);
+                if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(class_count + cls, static_cast<unsigned long long>(__popc(peers)));
+            }
             r->n = static_cast<uint32_t>(s.n) | (cls << 8);
             r->pair = static_cast<uint32_t>(k);
         }
@@ -623,7 +674,14 @@ epa_order_kernel(const SimplexRec *__restrict__ simplices, const unsigned long l
     {
         const uint32_t cls = (simplices[s].n >> 8) & 3u;
         const unsigned long long base = (cls == 2) ? 0ull : (cls == 1 ? c2 : c2 + c1);
-        const unsigned long long pos = base + atomicAdd(class_fill + cls, 1ull);
+        // one atomic per (warp, class) instead of one per hit: three hot addresses would serialise
+        const unsigned peers = __match_any_sync(__activemask(), cls);
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(peers) - 1;
+        unsigned long long first = 0;
+        if (lane == leader) first = atomicAdd(class_fill + cls, static_cast<unsigned long long>(__popc(peers)));
+        first = __shfl_sync(peers, first, leader);
+        const unsigned long long pos = base + first + __popc(peers & ((1u << lane) - 1u));
         if (pos < hit_capacity) order[pos] = static_cast<uint32_t>(s);
     }
 }
