@@ -175,6 +175,11 @@ STAGE_BYTES_DOC = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+# `ncu --set full` capture of this workload at side 100 (profiles/r1_epa_c3_1M.md); null otherwise
+NCU_TRAFFIC_BYTES = {"epa": 29_770_394_000}
+
+
 def stage_bytes(name, n, pairs, hits):
     unit, b = STAGE_BYTES_DOC[name]
     if unit == "body":
@@ -315,7 +320,7 @@ def run_ours(args, rank, world, local_rank):
         dev_step_ms = dev_ms / args.steps
         roofline = {
             "bound": "hbm", "kernel": dom[0], "achieved": dom[3], "peak": peak, "unit": "GB/s", "frac": dom[3] / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": NCU_TRAFFIC_BYTES.get(dom[0]) if n == 1_000_000 else None, "peak_source": peak_src,
             "kernel_ms": dom[1], "kernel_share_of_step": dom[1] / max(dev_step_ms, 1e-9),
             "whole_step": {"alg_bytes": total_bytes, "device_ms": dev_step_ms,
                            "achieved": total_bytes / (dev_step_ms * 1e-3) / 1e9, "frac": total_bytes / (dev_step_ms * 1e-3) / 1e9 / peak},
@@ -356,6 +361,116 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_c4(args, rank, world, local_rank):
+    """BASELINE C4: narrowphase only, random hull pairs from a 1024-hull library (V in 32..256)."""
+    import torch
+
+    import physkit_b200 as pk
+    from scenes import scene_c4
+
+    torch.cuda.set_device(local_rank)
+    npairs = args.pairs // world
+    sc, pa, pb = scene_c4(n_pairs=npairs, n_hulls=1024, seed=0x5EED0004 + rank)
+    nh = sum(len(s[1]) for s in sc.shapes)
+    ctx = pk.Context(sc.n, npairs, mode=pk.MODE_QUERY, device=local_rank, max_shapes=len(sc.shapes), max_contacts=npairs,
+                     max_hull_vertices=nh + 8)
+    ctx.add_shapes(sc.shapes)
+    ctx.resize(sc.n)
+    ctx.upload(sc.pos, sc.quat, None, sc.shape_id, sc.flags)
+    d_a, d_b = ctx.device_alloc(4 * npairs), ctx.device_alloc(4 * npairs)
+    d_out, d_hit = ctx.device_alloc(88 * npairs), ctx.device_alloc(npairs)
+    ctx.h2d(d_a, pa)
+    ctx.h2d(d_b, pb)
+    for _ in range(args.warmup):
+        ctx.gjk_epa_batch_device(d_a, d_b, npairs, d_out, d_hit)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev = 0.0
+    for _ in range(args.steps):
+        dev += ctx.gjk_epa_batch_device(d_a, d_b, npairs, d_out, d_hit)
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    st, launches = ctx.stage_times()
+    hit = np.empty(npairs, np.uint8)
+    ctx.d2h(hit, d_hit)
+    mean_v = float(np.mean([len(s[1]) for s in sc.shapes]))
+    staged = npairs * (24.0 * 2 * mean_v + 153) + int(hit.sum()) * 88
+    peak, peak_src = measured_peak()
+    if rank == 0:
+        line = {"metric": "colliding-pair tests/sec (GJK/EPA batch, convex hulls 32-256 verts)", "value": npairs * world / (ms * 1e-3),
+                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C4: {npairs * world} random hull pairs, 1024-hull library", "hit_rate": float(hit.mean())},
+                "device_ms_per_step": dev / args.steps, "gpu_launches": launches * args.steps,
+                "roofline": {"bound": "hbm", "kernel": "gjk+epa (staged hull bytes)", "achieved": staged / (ms * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": staged / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "stages_ms": {k: round(v, 4) for k, v in st.items() if v > 0}}}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def run_c5(args, rank, world, local_rank):
+    """BASELINE C5: independent 513-body worlds batched in one context per rank (no collective)."""
+    import torch
+
+    import physkit_b200 as pk
+    from scenes import SplitMix64, scene_c1
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nw = args.worlds // world
+    base = scene_c1(side=8, spacing=0.97)
+    per = base.n
+    pos = np.concatenate([base.pos + SplitMix64(0x5EED0005 + rank * nw + k).uniform(-0.03, 0.03, per, 3) for k in range(nw)])
+    quat = np.tile(base.quat, (nw, 1))
+    sid = np.tile(base.shape_id, nw)
+    flags = np.tile(base.flags, nw)
+    wid = np.repeat(np.arange(nw, dtype=np.uint32), per)
+    n = len(pos)
+    ctx = pk.Context(n, int(14 * n), mode=pk.MODE_WORLD, device=local_rank, max_shapes=8, max_contacts=int(7 * n),
+                     max_hull_vertices=64, num_worlds=nw)
+    ctx.add_shapes(base.shapes)
+    ctx.resize(n)
+    ctx.upload(pos, quat, None, sid, flags, wid)
+    ctx.collide_resident()
+    p1 = pos.copy()
+    p1[:, 1] -= 0.04
+    ctx.update_pose(p1)
+    r = ctx.collide_resident()
+    for _ in range(args.warmup):
+        ctx.collide_resident()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = ctx.collide_resident()
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    pairs = int(r.num_pairs)
+    if world > 1:
+        t = torch.tensor([float(pairs), ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        tp = t.clone()
+        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pairs, ms = int(tp[0].item()), float(t[1].item())
+    st, launches = ctx.stage_times()
+    if rank == 0:
+        line = {"metric": "colliding-pair tests/sec (batched independent worlds)", "value": pairs / (ms * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C5: {nw * world} worlds x {per} bodies (8-vertex box hulls + ground), worlds split across ranks",
+                           "pairs_per_step": pairs, "worlds_per_s": nw * world / (ms * 1e-3)},
+                "gpu_launches": launches * args.steps, "stages_ms": {k: round(v, 4) for k, v in st.items() if v > 0}}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,6 +481,9 @@ def main():
     ap.add_argument("--cpu-side", type=int, default=50, help="lattice side of the cpu_baseline sample")
     ap.add_argument("--ref-side", type=int, default=40, help="lattice side of the --impl reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"], help="c3 is the headline; c4/c5 are extra configs")
+    ap.add_argument("--pairs", type=int, default=2_000_000, help="c4: number of hull pairs")
+    ap.add_argument("--worlds", type=int, default=4096, help="c5: number of independent worlds")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -376,6 +494,10 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         log(f"bench.py: --gpus {args.gpus} without torchrun: running rank 0 of 1 (launch with torch.distributed.run for N>1)")
+    if args.workload == "c4":
+        return run_c4(args, rank, world, local_rank)
+    if args.workload == "c5":
+        return run_c5(args, rank, world, local_rank)
     run_ours(args, rank, world, local_rank)
 
 

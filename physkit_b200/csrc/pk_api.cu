@@ -75,6 +75,7 @@ struct pk_ctx
     bool shapes_dirty = false;
     ShapeRec *d_shapes = nullptr;
     double *d_verts = nullptr;
+    float4 *d_verts_f = nullptr;
 
     // bodies
     uint32_t n_bodies = 0;
@@ -201,9 +202,18 @@ int upload_shapes(pk_ctx *ctx)
     if (!ctx->h_shapes.empty())
         PK_CUDA(cudaMemcpyAsync(ctx->d_shapes, ctx->h_shapes.data(), ctx->h_shapes.size() * sizeof(ShapeRec),
                                 cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<float4> vf;
     if (!ctx->h_verts.empty())
+    {
         PK_CUDA(cudaMemcpyAsync(ctx->d_verts, ctx->h_verts.data(), ctx->h_verts.size() * sizeof(double),
                                 cudaMemcpyHostToDevice, ctx->stream));
+        // float copy for the hull-support prefilter (round to nearest; the error bound covers it)
+        vf.resize(ctx->h_verts.size() / 3);
+        for (size_t i = 0; i < vf.size(); ++i)
+            vf[i] = make_float4(static_cast<float>(ctx->h_verts[3 * i]), static_cast<float>(ctx->h_verts[3 * i + 1]),
+                                static_cast<float>(ctx->h_verts[3 * i + 2]), 0.f);
+        PK_CUDA(cudaMemcpyAsync(ctx->d_verts_f, vf.data(), vf.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    }
     PK_CUDA(cudaStreamSynchronize(ctx->stream)); // host vectors may be reallocated by the next pk_shape_*
     ctx->shapes_dirty = false;
     return PK_OK;
@@ -228,6 +238,7 @@ BodyArrays body_arrays(pk_ctx *ctx)
     BodyArrays b;
     b.shapes = ctx->d_shapes;
     b.verts = ctx->d_verts;
+    b.verts_f = ctx->d_verts_f;
     b.pos = ctx->d_pos;
     b.quat = ctx->d_quat;
     b.shape_id = ctx->d_shape_id;
@@ -313,7 +324,7 @@ int pk_destroy(pk_ctx *ctx)
     if (!ctx) return PK_E_INVALID;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void *dev[] = {ctx->d_shapes,      ctx->d_verts,        ctx->d_pos,         ctx->d_quat,         ctx->d_disp,
+    void *dev[] = {ctx->d_verts_f, ctx->d_shapes,      ctx->d_verts,        ctx->d_pos,         ctx->d_quat,         ctx->d_disp,
                    ctx->d_shape_id,    ctx->d_world,        ctx->d_flags,       ctx->st.stored,      ctx->st.last_move,
                    ctx->st.create,     ctx->st.alive,       ctx->d_scene,       ctx->d_counters,     ctx->d_bkeys[0],
                    ctx->d_bkeys[1],    ctx->d_bvals[0],     ctx->d_bvals[1],    ctx->d_tile_hist,    ctx->d_digit_total,
@@ -375,6 +386,7 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     return fail(s)
     A(ctx->d_shapes, cfg->max_shapes);
     A(ctx->d_verts, cfg->max_hull_vertices * 3 + 2);
+    A(ctx->d_verts_f, cfg->max_hull_vertices + 1);
     A(ctx->d_pos, nb * 3);
     A(ctx->d_quat, nb * 4);
     A(ctx->d_disp, nb * 3);

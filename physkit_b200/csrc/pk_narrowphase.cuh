@@ -233,14 +233,6 @@ __device__ __forceinline__ bool pad_simplex(const ShapeView &A, const ShapeView 
 //   pair source: either sorted u64 keys (a = key>>32, b = key&0xffffffff) or explicit a[]/b[] arrays.
 //   Outputs: hit flag per pair, dense hit list with simplices.
 // ---------------------------------------------------------------------------------------------
-struct BodyArrays
-{
-    const ShapeRec *shapes;
-    const double *verts;
-    const double *pos;
-    const double *quat;
-    const uint32_t *shape_id;
-};
 
 #ifndef PK_GJK_THREADS
 #define PK_GJK_THREADS 128
@@ -281,8 +273,8 @@ gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const
     {
         uint32_t ia, ib;
         load_pair(keys, pair_a, pair_b, k, ia, ib);
-        ShapeView A = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ia);
-        ShapeView B = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ib);
+        ShapeView A = load_shape(bodies, ia);
+        ShapeView B = load_shape(bodies, ib);
         d3 p0 = P(minkowski_support(A, B, d3{1.0, 0.0, 0.0}));
         if (sqnorm(p0) < 1e-12)
             survive = true; // origin hit on the first point: full path decides (collision.cpp:174)
@@ -320,8 +312,8 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
     const uint64_t k = work[w];
     uint32_t ia, ib;
     load_pair(keys, pair_a, pair_b, k, ia, ib);
-    ShapeView A = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ia);
-    ShapeView B = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ib);
+    ShapeView A = load_shape(bodies, ia);
+    ShapeView B = load_shape(bodies, ib);
     Simplex s;
     bool h = gjk_collision(A, B, s);
     hit[k] = h ? 1 : 0;
@@ -472,6 +464,8 @@ struct EpaSmem
 {
     double f[2][10][EPA_THREADS]; // shape views: p xyz, h xyz, q xyzw
     const double *verts[2][EPA_THREADS];
+    const float4 *vf[2][EPA_THREADS];
+    float hull_r[2][EPA_THREADS];
     int kind[2][EPA_THREADS];
     uint32_t nverts[2][EPA_THREADS];
     double hdist[EPA_HEAP_SMEM][EPA_THREADS];
@@ -630,6 +624,8 @@ __device__ __forceinline__ void smem_put_shape(EpaSmem &sm, int which, const Sha
     sm.f[which][3][t] = v.h.x; sm.f[which][4][t] = v.h.y; sm.f[which][5][t] = v.h.z;
     sm.f[which][6][t] = v.q.x; sm.f[which][7][t] = v.q.y; sm.f[which][8][t] = v.q.z; sm.f[which][9][t] = v.q.w;
     sm.verts[which][t] = v.verts;
+    sm.vf[which][t] = v.vf;
+    sm.hull_r[which][t] = v.hull_r;
     sm.kind[which][t] = v.kind;
     sm.nverts[which][t] = v.nverts;
 }
@@ -641,6 +637,8 @@ __device__ __forceinline__ ShapeView smem_get_shape(const EpaSmem &sm, int which
     v.h = {sm.f[which][3][t], sm.f[which][4][t], sm.f[which][5][t]};
     v.q = {sm.f[which][6][t], sm.f[which][7][t], sm.f[which][8][t], sm.f[which][9][t]};
     v.verts = sm.verts[which][t];
+    v.vf = sm.vf[which][t];
+    v.hull_r = sm.hull_r[which][t];
     v.kind = sm.kind[which][t];
     v.nverts = sm.nverts[which][t];
     return v;
@@ -766,8 +764,8 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                 }
                 bool ok = true;
                 {
-                    ShapeView A = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ia);
-                    ShapeView B = load_shape(bodies.shapes, bodies.verts, bodies.pos, bodies.quat, bodies.shape_id, ib);
+                    ShapeView A = load_shape(bodies, ia);
+                    ShapeView B = load_shape(bodies, ib);
                     smem_put_shape(shm, 0, A);
                     smem_put_shape(shm, 1, B);
                     if (s.n < 4) ok = pad_simplex(A, B, s);

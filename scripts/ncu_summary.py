@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""Summarise ncu artefacts brought back in gpurun_out/ into profiles/ (tracked).
+
+  python scripts/ncu_summary.py launches <launches.csv> <out.md>
+  python scripts/ncu_summary.py kernel <report.ncu-rep> <kernel-substr> <out.md> [lib.so]
+
+`kernel` needs ncu, cuobjdump and nvdisasm (all in the CUDA toolkit; no GPU).  Per-line stall
+attribution joins ncu's SASS-level source page with nvdisasm's line table of the library."""
+import collections
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+]
+
+
+def launches(path, out):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        name = r[ik].split("(")[0].replace("void ", "")
+        v = float(r[iv].replace(",", ""))
+        v *= {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}.get(r[iu], 1.0)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(v[1] for v in agg.values())
+    with open(out, "w") as f:
+        f.write(f"# ncu launch list: {os.path.basename(path)}\n\n")
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare SHARES).\n\n")
+        f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {v[0]} | {v[1]:.3f} | {100 * v[1] / tot:.1f} % |\n")
+        f.write(f"| total | {sum(v[0] for v in agg.values())} | {tot:.3f} | |\n")
+    print(open(out).read())
+
+
+def kernel(rep, kern, out, lib):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    hdr, units, vals = rr[0], rr[1], rr[2]
+    lines = [f"# ncu --set full: `{vals[4].split('(')[0]}`  ({os.path.basename(rep)})\n", f"grid {vals[8]} block {vals[7]}\n", "| metric | value | unit |\n|---|---:|---|\n"]
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            lines.append(f"| `{k}` | {vals[i]} | {units[i]} |\n")
+    stalls = []
+    for i, h in enumerate(hdr):
+        if h.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in h:
+            try:
+                stalls.append((float(vals[i]), h.replace("smsp__pcsamp_warps_issue_stalled_", "")))
+            except ValueError:
+                pass
+    tot = sum(s[0] for s in stalls) or 1.0
+    lines.append("\nStall reasons (PC samples): " + ", ".join(f"{n} {100 * v / tot:.1f} %" for v, n in sorted(stalls, reverse=True)[:6]) + "\n")
+    # per-line attribution
+    with tempfile.TemporaryDirectory() as td:
+        subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=td, capture_output=True)
+        cub = [os.path.join(td, f) for f in os.listdir(td) if f.endswith(".cubin")]
+        dis = subprocess.run(["nvdisasm", "-g", "-c"] + cub, capture_output=True, text=True).stdout.split("\n")
+    start = next((i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l and l.endswith(":")), None)
+    off2line, cur = {}, None
+    if start is not None:
+        for l in dis[start + 1:]:
+            if l.startswith("//-----"):
+                break
+            m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+            if m:
+                cur = (os.path.basename(m.group(1)), int(m.group(2)))
+                continue
+            m = re.search(r"/\*([0-9a-f]{4,})\*/\s+\S", l)
+            if m and cur:
+                off2line[int(m.group(1), 16)] = cur
+    sr = list(csv.reader(io.StringIO(src)))
+    sh = sr[1]
+    ia, isamp, iinst, ithr, ilsb = sh.index("Address"), sh.index("# Samples"), sh.index("Instructions Executed"), sh.index("Thread Instructions Executed"), sh.index("stall_long_sb")
+    base = int(sr[2][ia], 16)
+    agg = collections.defaultdict(lambda: [0, 0, 0, 0])
+    t = [0, 0, 0, 0]
+    for r in sr[2:]:
+        key = off2line.get(int(r[ia], 16) - base, ("?", 0))
+        v = [int(r[isamp]), int(r[iinst]), int(r[ithr]), int(r[ilsb])]
+        for k in range(4):
+            agg[key][k] += v[k]
+            t[k] += v[k]
+    cache = {}
+
+    def text(f, n):
+        p = os.path.join(ROOT, "physkit_b200", "csrc", f)
+        if not os.path.exists(p):
+            return ""
+        if p not in cache:
+            cache[p] = open(p).read().split("\n")
+        return cache[p][n - 1].strip()[:100] if 0 < n <= len(cache[p]) else ""
+
+    lines.append(f"\nWarp instructions {t[1]:,}; thread instructions {t[2]:,}; average active lanes {t[2] / max(t[1], 1):.2f} / 32.\n")
+    lines.append("\n| samples | instr | lanes | long_sb | source |\n|---:|---:|---:|---:|---|\n")
+    for key, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:28]:
+        lines.append(f"| {100 * v[0] / t[0]:.1f} % | {100 * v[1] / t[1]:.1f} % | {v[2] / max(v[1], 1):.1f} | {100 * v[3] / max(v[0], 1):.0f} % | `{key[0]}:{key[1]}` `{text(*key)}` |\n")
+    open(out, "w").write("".join(lines))
+    print("".join(lines))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3])
+    else:
+        kernel(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else os.path.join(ROOT, "physkit_b200", "libpk_collide.so"))
