@@ -342,6 +342,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C3: {n}-body jittered lattice (side {args.side}), analytic spheres + OBBs, world-mode fat-AABB pairs",
                        "bodies": n, "pairs_per_step": tot_pairs, "contacts_per_step": tot_contacts,
+                       "epa_fallback_pairs": getattr(ctx, "epa_fallback", None),
                        "sharding": "pairs by sorted-leaf range, tree rebuilt per rank, one all-gather of contacts" if world > 1 else "none",
                        "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush",
                        "timing": "wall clock around K synchronous steps bracketed by barrier+synchronize, max over ranks; "

@@ -108,6 +108,7 @@ typedef struct pk_stage_times
     float ms[PK_NUM_STAGES];
     const char *name[PK_NUM_STAGES];
     uint32_t launches; /* kernels launched by the last pk_collide */
+    uint32_t epa_fallback; /* GJK hits the group EPA kernel handed to the thread-per-pair EPA kernel */
 } pk_stage_times;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

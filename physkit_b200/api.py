@@ -67,7 +67,7 @@ class StepResult(C.Structure):
 
 
 class _StageTimes(C.Structure):
-    _fields_ = [("ms", C.c_float * NUM_STAGES), ("name", C.c_char_p * NUM_STAGES), ("launches", C.c_uint32)]
+    _fields_ = [("ms", C.c_float * NUM_STAGES), ("name", C.c_char_p * NUM_STAGES), ("launches", C.c_uint32), ("epa_fallback", C.c_uint32)]
 
 
 _lib = None
@@ -307,6 +307,7 @@ class Context:
         st = _StageTimes()
         self._check(self.L.pk_stage_times_get(self.h, C.byref(st)))
         d = {st.name[k].decode(): float(st.ms[k]) for k in range(NUM_STAGES)}
+        self.epa_fallback = int(st.epa_fallback)
         return d, int(st.launches)
 
     def stream(self):

@@ -9,6 +9,8 @@
 #include "pk_broadphase.cuh"
 #include "pk_common.cuh"
 #include "pk_narrowphase.cuh"
+#include "pk_epa_group.cuh"
+#include "pk_epa_scan.cuh"
 #include "pk_sort.cuh"
 
 #include <algorithm>
@@ -20,6 +22,33 @@
 #include <vector>
 
 using namespace pk;
+
+// EPA implementation: 2 = scan kernel (pk_epa_scan.cuh) + epa_kernel for its fallback list (default),
+// 1 = group kernel (pk_epa_group.cuh, measured slower: kept as an experiment), 0 = epa_kernel only
+#ifndef PK_EPA_IMPL
+#ifdef PK_EPA_LEGACY_ONLY
+#define PK_EPA_IMPL 0
+#else
+#define PK_EPA_IMPL 2
+#endif
+#endif
+// group EPA configuration: lanes per pair, shared-memory capacities (faces, heap entries, vertices)
+#ifndef PK_EPA_G
+#define PK_EPA_G 4
+#endif
+#ifndef PK_EPA_FS
+#define PK_EPA_FS 64
+#endif
+#ifndef PK_EPA_HS
+#define PK_EPA_HS 126
+#endif
+#ifndef PK_EPA_VS
+#define PK_EPA_VS 36
+#endif
+using EpaGroupSpill = EgSpillLayout<PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>;
+constexpr int EG_GROUPS_PER_BLOCK = eg_groups_per_block<PK_EPA_G, PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>();
+constexpr size_t EpaGroupSmemBytes = sizeof(EgSmem<PK_EPA_G, PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>) * EG_GROUPS_PER_BLOCK;
+static_assert(EpaGroupSmemBytes <= 232448, "group EPA shared memory exceeds the 227 KB per-block limit");
 
 namespace
 {
@@ -57,7 +86,9 @@ enum Counter
     C_GJK_CURSOR,
     C_CLASS_COUNT, // [3]
     C_CLASS_FILL = C_CLASS_COUNT + 3, // [3]
-    C_COUNT = 16
+    C_EPA_FALLBACK = C_CLASS_FILL + 3, // pairs the group EPA kernel handed to the thread-per-pair kernel
+    C_EPA_CURSOR2,
+    C_COUNT = 24
 };
 
 } // namespace
@@ -115,6 +146,10 @@ struct pk_ctx
     uint32_t *d_epa_order = nullptr;
     uint32_t *d_gjk_work = nullptr;
     unsigned char *d_slabs = nullptr;
+    unsigned char *d_epa_spill = nullptr;
+    uint32_t *d_epa_fallback = nullptr;
+    uint32_t epa_group_blocks = 0;
+    uint32_t epa_scan_blocks = 0;
     uint32_t epa_blocks = 0;
     uint32_t gjk_blocks = 0;
 
@@ -275,11 +310,35 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
         epa_order_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
                                                                      ctx->d_counters + C_CLASS_COUNT, ctx->d_counters + C_CLASS_FILL,
                                                                      ctx->d_epa_order);
+#if PK_EPA_IMPL == 0
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs, ctx->d_counters + C_EPA_CURSOR,
             ctx->d_counters + C_VALID);
         ctx->launches += 2;
+#else
+        // fast kernel first; what it cannot take (exact distance ties, padded simplices, improper horizons,
+        // capacity) lands in d_epa_fallback and is done by epa_kernel, which restates the reference's heap
+#if PK_EPA_IMPL == 1
+        epa_group_kernel<PK_EPA_G, PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>
+            <<<ctx->epa_group_blocks, EG_GROUPS_PER_BLOCK * PK_EPA_G, EpaGroupSmemBytes, ctx->stream>>>(
+                body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
+                ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
+                ctx->d_counters + C_EPA_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
+                ctx->d_counters + C_EPA_FALLBACK);
+#else
+        epa_scan_kernel<<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
+            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
+            ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
+            ctx->d_counters + C_EPA_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
+            ctx->d_counters + C_EPA_FALLBACK);
+#endif
+        epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
+            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK, ctx->max_contacts,
+            ctx->d_out_index, ctx->d_epa_fallback, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
+            ctx->d_counters + C_EPA_CURSOR2, ctx->d_counters + C_VALID);
+        ctx->launches += 3;
+#endif
     }
     if (timed) cudaEventRecord(ctx->ev[ST_COMPACT], ctx->stream);
     PK_CUDA(cudaGetLastError());
@@ -331,7 +390,8 @@ int pk_destroy(pk_ctx *ctx)
                    ctx->d_leaves,      ctx->d_nodes,        ctx->d_right,       ctx->d_range_last,   ctx->d_root,
                    ctx->d_merge_flag,  ctx->d_pkeys[0],     ctx->d_pkeys[1],    ctx->d_hit,          ctx->d_out_index,
                    ctx->d_scan_tiles,  ctx->d_simplices,    ctx->d_contacts[0], ctx->d_contacts[1],  ctx->d_valid,
-                   ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order,    ctx->d_gjk_work};
+                   ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order,    ctx->d_gjk_work,
+                   ctx->d_epa_spill,   ctx->d_epa_fallback};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -441,6 +501,33 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
         uint64_t threads = std::min(want_threads, std::max<uint64_t>(need_threads, EPA_THREADS));
         ctx->epa_blocks = static_cast<uint32_t>(threads / EPA_THREADS);
         A(ctx->d_slabs, threads * EPA_SLAB_BYTES);
+#if PK_EPA_IMPL == 1
+        // group EPA: one persistent block per SM (its shared memory holds EG_GROUPS_PER_BLOCK polytopes)
+        if (cudaFuncSetAttribute(epa_group_kernel<PK_EPA_G, PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EpaGroupSmemBytes)) != cudaSuccess)
+        {
+            ctx->last_error = "epa_group_kernel: shared-memory carve-out refused";
+            return fail(PK_E_CUDA);
+        }
+        uint64_t want_blocks = static_cast<uint64_t>(ctx->sm_count);
+        uint64_t need_blocks = (nc + EG_GROUPS_PER_BLOCK - 1) / EG_GROUPS_PER_BLOCK;
+        ctx->epa_group_blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min(want_blocks, need_blocks)));
+        A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_group_blocks) * EG_GROUPS_PER_BLOCK * EpaGroupSpill::BYTES);
+#elif PK_EPA_IMPL == 2
+        // scan EPA: 48 KB of shared memory per 64-thread block, as many blocks per SM as the carve-out allows
+        cudaFuncSetAttribute(epa_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int es_per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_scan_kernel, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
+            es_per_sm = 1;
+#ifdef PK_ES_BLOCKS_PER_SM
+        es_per_sm = std::min(es_per_sm, PK_ES_BLOCKS_PER_SM);
+#endif
+        uint64_t es_want = static_cast<uint64_t>(ctx->sm_count) * es_per_sm;
+        uint64_t es_need = (nc + ES_THREADS - 1) / ES_THREADS;
+        ctx->epa_scan_blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min(es_want, es_need)));
+        A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_scan_blocks) * ES_THREADS * ES_SLAB_BYTES);
+#endif
+        A(ctx->d_epa_fallback, nc);
     }
 #undef A
     if (cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_counters), C_COUNT * sizeof(unsigned long long),
@@ -863,6 +950,7 @@ int pk_stage_times_get(pk_ctx *ctx, pk_stage_times *out)
         out->name[k] = kStageNames[k];
     }
     out->launches = ctx->launches;
+    out->epa_fallback = static_cast<uint32_t>(ctx->h_counters ? ctx->h_counters[C_EPA_FALLBACK] : 0);
     return PK_OK;
 }
 
