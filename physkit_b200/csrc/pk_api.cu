@@ -951,6 +951,12 @@ int pk_stage_times_get(pk_ctx *ctx, pk_stage_times *out)
     }
     out->launches = ctx->launches;
     out->epa_fallback = static_cast<uint32_t>(ctx->h_counters ? ctx->h_counters[C_EPA_FALLBACK] : 0);
+#ifdef PK_ES_REASONS
+    if (ctx->h_counters)
+        fprintf(stderr, "[epa fallback] total %llu: pad %llu tie %llu capacity %llu improper %llu; iterations thrown away %llu\n",
+                ctx->h_counters[C_EPA_FALLBACK], ctx->h_counters[C_EPA_FALLBACK + 2], ctx->h_counters[C_EPA_FALLBACK + 3],
+                ctx->h_counters[C_EPA_FALLBACK + 4], ctx->h_counters[C_EPA_FALLBACK + 5], ctx->h_counters[C_EPA_FALLBACK + 6]);
+#endif
     return PK_OK;
 }
 

@@ -19,8 +19,9 @@
 //     neighbourhood of every face it pushes; the face loop prefetches all its operands first
 //   * horizon and ring-link scratch live in shared memory, not in local memory
 //
-// Capacity is cut to what shared memory holds (96 face slots ⇒ 46 iterations, 16 horizon edges); pairs
-// beyond it, padded simplices and improper horizons also go to epa_kernel through the fallback list.
+// Shared memory holds keys for the first 96 face slots (46 iterations); the few polytopes that grow past
+// that scan the remaining distances from their slab.  Padded simplices, improper horizons and horizons
+// longer than 16 edges also go to epa_kernel through the fallback list.
 // Results are bit-identical to epa_kernel.
 #pragma once
 
@@ -30,22 +31,23 @@ namespace pk
 {
 
 constexpr int ES_THREADS = 64;
-constexpr int ES_SLOTS = 96;   // live faces = 2V − 4
-constexpr int ES_VERTS = 50;   // 2·50 − 4 = 96
+constexpr int ES_SLOTS = 136;  // live faces = 2V − 4 ≤ 132
+constexpr int ES_KEYS = 96;    // slots with a float key in shared memory (the rest is scanned from the slab)
+constexpr int ES_VERTS = 68;   // 4 + 64 iterations
 constexpr int ES_HORIZON = 16; // observed max 10
 constexpr int ES_STACK = 8;    // observed max 4
 constexpr size_t ES_SLAB_BYTES = static_cast<size_t>(ES_SLOTS) * (32 + 8) + static_cast<size_t>(ES_VERTS) * (32 + 48);
 
 struct EsSmem
 {
-    float key[ES_SLOTS][ES_THREADS]; // float(distance) rounded down; +inf = free slot
+    float key[ES_KEYS][ES_THREADS];  // float(distance) rounded down; +inf = free slot
     double f[2][10][ES_THREADS];     // shape views: p xyz, h xyz, q xyzw
     const double *verts[2][ES_THREADS];
     const float4 *vf[2][ES_THREADS];
     float hull_r[2][ES_THREADS];
     int kind[2][ES_THREADS];
     uint32_t nverts[2][ES_THREADS];
-    uint32_t hz[ES_HORIZON][ES_THREADS];   // start | end << 8 | adjacent slot << 16 | new slot << 24
+    uint32_t hz[ES_HORIZON][ES_THREADS];   // start:7 | end:7 | adjacent slot:8 | its edge:2 | new slot:8
     uint16_t ring[ES_HORIZON][ES_THREADS]; // successor slot | predecessor slot << 8 (0xFF = none)
     uint8_t edge_of_start[ES_VERTS][ES_THREADS];
 };
@@ -103,6 +105,16 @@ struct EsSlab
 
 __device__ __forceinline__ int es_v(unsigned long long t, int i) { return static_cast<int>((t >> (8 * i)) & 0xFFull); }
 __device__ __forceinline__ int es_adj(unsigned long long t, int i) { return static_cast<int>((t >> (24 + 8 * i)) & 0xFFull); }
+__device__ __forceinline__ int hz_start(uint32_t h) { return static_cast<int>(h & 0x7Fu); }
+__device__ __forceinline__ int hz_end(uint32_t h) { return static_cast<int>((h >> 7) & 0x7Fu); }
+__device__ __forceinline__ int hz_adj(uint32_t h) { return static_cast<int>((h >> 14) & 0xFFu); }
+__device__ __forceinline__ int hz_e2(uint32_t h) { return static_cast<int>((h >> 22) & 0x3u); }
+__device__ __forceinline__ int hz_slot(uint32_t h) { return static_cast<int>(h >> 24); }
+// initial tetrahedron: faces (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0)  (collision.cpp:361-364)
+__device__ __forceinline__ int fi4(int f) { return f == 3 ? 1 : 0; }
+__device__ __forceinline__ int fj4(int f) { return (0x3321 >> (4 * f)) & 0xF; }
+__device__ __forceinline__ int fk4(int f) { return (0x2132 >> (4 * f)) & 0xF; }
+__device__ __forceinline__ int fo4(int f) { return (0x0213 >> (4 * f)) & 0xF; }
 __device__ __forceinline__ void es_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float es_inf() { return __int_as_float(0x7F800000); }
 
@@ -133,8 +145,18 @@ __device__ __forceinline__ ShapeView es_get_shape(const EsSmem &sm, int which)
     return v;
 }
 
+// One copy of the face-plane arithmetic (collision.cpp:273-297) instead of one per call site: with eight
+// warps per SM at unrelated program counters, instruction-cache misses were 22 % of the issue stalls.
+__device__ __forceinline__ double4 es_face_plane(d3 pi, d3 pj, d3 pk, bool has_opp, d3 popp, bool &flip)
+{
+    d3 n;
+    double dist;
+    flip = epa_face_plane(pi, pj, pk, has_opp, popp, n, dist);
+    return make_double4(n.x, n.y, n.z, dist);
+}
+
 // collision.cpp:424-454
-__device__ __forceinline__ void es_write_result(const EsSlab &sl, double4 nd, unsigned long long t, ContactRec *out, uint64_t key)
+__device__ __noinline__ void es_write_result(const EsSlab &sl, double4 nd, unsigned long long t, ContactRec *out, uint64_t key)
 {
     d3 n{nd.x, nd.y, nd.z};
     const double2 *q0 = reinterpret_cast<const double2 *>(sl.vab + 6 * es_v(t, 0));
@@ -192,36 +214,57 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
     const float INF = es_inf();
 
     bool active = false, done = false;
-    int nverts = 0, iter = 0, hi = 0; // hi: slots [0, hi) have been used by the current polytope
-    unsigned long long fm0 = 0;       // free slots 0-63
-    uint32_t fm1 = 0;                 // free slots 64-95
+    int nverts = 0, iter = 0, hi = 0;      // hi: slots [0, hi) have been used by the current polytope
+    unsigned long long fm0 = 0, fm1 = 0;   // free slots 0-63, 64-127
+    uint32_t fm2 = 0;                      // free slots 128-135
     uint32_t out_slot = 0, cur_sidx = 0;
     uint64_t key = 0;
     // zero-distance ties (see pop): all faces created before the last batch were strictly farther than 0
     bool older_positive = true, batch_positive = true;
-    int batch_first = 0, batch_n = 0; // hz[] entries of the last batch are still valid when batch_n > 0
+    int batch_n = 0; // hz[0, batch_n) still describes the last batch of faces
     unsigned long long n_valid = 0;
-    for (int s = 0; s < ES_SLOTS; ++s) shm.key[s][t] = INF;
+#pragma unroll 1
+    for (int s = 0; s < ES_KEYS; ++s) shm.key[s][t] = INF;
+#pragma unroll 1
     for (int v = 0; v < ES_VERTS; ++v) shm.edge_of_start[v][t] = 0xFF;
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
-    auto to_fallback = [&]()
+    int fb = 0; // reason + 1 when the current pair has to go to epa_kernel (one atomic site for all of them)
+    auto is_free = [&](int f) -> bool
     {
-        unsigned long long i = atomicAdd(fallback_count, 1ull);
-        if (i < hit_capacity) fallback_list[i] = cur_sidx;
-        active = false;
+        const unsigned long long w = (f < 64) ? fm0 : (f < 128 ? fm1 : static_cast<unsigned long long>(fm2));
+        return (w >> (f & 63)) & 1ull;
     };
     auto kill_slot = [&](int f)
     {
-        shm.key[f][t] = INF;
+        if (f < ES_KEYS) shm.key[f][t] = INF;
         if (f < 64)
             fm0 |= 1ull << f;
+        else if (f < 128)
+            fm1 |= 1ull << (f - 64);
         else
-            fm1 |= 1u << (f - 64);
+            fm2 |= 1u << (f - 128);
+    };
+    // float key of slot s: shared memory for the first ES_KEYS slots, derived from the slab beyond
+    auto key_of = [&](int s) -> float
+    {
+        if (s < ES_KEYS) return shm.key[s][t];
+        return is_free(s) ? INF : __double2float_rd(sl.plane[4 * s + 3]);
     };
 
     for (;;)
     {
+        if (fb)
+        {
+            unsigned long long i = atomicAdd(fallback_count, 1ull);
+            if (i < hit_capacity) fallback_list[i] = cur_sidx;
+#ifdef PK_ES_REASONS
+            atomicAdd(fallback_count + 1 + fb, 1ull); // debug build only: C_EPA_FALLBACK + 2 + reason
+            atomicAdd(fallback_count + 6, static_cast<unsigned long long>(iter));
+#endif
+            fb = 0;
+            active = false;
+        }
         const unsigned m_active = __ballot_sync(FULL, active);
         const unsigned m_idle = __ballot_sync(FULL, !active && !done);
         if (m_active == 0 && m_idle == 0) break;
@@ -235,8 +278,9 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 cur_sidx = order[slot];
                 const SimplexRec *r = simplices + cur_sidx;
                 const uint32_t pair = r->pair;
+                iter = 0;
                 if ((r->n & 0xFFu) != 4u)
-                    to_fallback(); // pad_simplex path (collision.cpp:191-248): rare, left to epa_kernel
+                    fb = 1; // pad_simplex path (collision.cpp:191-248): rare, left to epa_kernel
                 else
                 {
                     uint32_t ia, ib;
@@ -260,6 +304,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                         es_put_shape(shm, 1, B);
                     }
                     d3 pv[4];
+#pragma unroll
                     for (int i = 0; i < 4; ++i)
                     {
                         SupportPt s;
@@ -268,73 +313,86 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                         pv[i] = P(s);
                         sl.set_vert(i, s, pv[i]);
                     }
-                    for (int s = 4; s < hi; ++s) shm.key[s][t] = INF; // leftovers of the previous polytope
+                    for (int s = 4; s < hi && s < ES_KEYS; ++s) shm.key[s][t] = INF; // leftovers of the previous polytope
                     // build_initial_tetrahedron (collision.cpp:355-388): faces (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0)
-                    const int fi[4] = {0, 0, 0, 1}, fj[4] = {1, 2, 3, 3}, fk[4] = {2, 3, 1, 2}, fo[4] = {3, 1, 2, 0};
-                    uint8_t tv[4][3], ta[4][3];
+                    uint32_t tv[4]; // vertex triples, one byte each
                     bool bad = false;
                     batch_positive = true;
+#pragma unroll
                     for (int f = 0; f < 4; ++f)
                     {
-                        d3 n;
-                        double dist;
-                        bool flip = epa_face_plane(pv[fi[f]], pv[fj[f]], pv[fk[f]], true, pv[fo[f]], n, dist);
-                        tv[f][0] = static_cast<uint8_t>(fi[f]);
-                        tv[f][1] = static_cast<uint8_t>(flip ? fk[f] : fj[f]);
-                        tv[f][2] = static_cast<uint8_t>(flip ? fj[f] : fk[f]);
-                        ta[f][0] = ta[f][1] = ta[f][2] = 0xFF;
+                        bool flip;
+                        const double4 pl = es_face_plane(pv[fi4(f)], pv[fj4(f)], pv[fk4(f)], true, pv[fo4(f)], flip);
+                        const d3 n{pl.x, pl.y, pl.z};
+                        const double dist = pl.w;
+                        tv[f] = static_cast<uint32_t>(fi4(f)) | (static_cast<uint32_t>(flip ? fk4(f) : fj4(f)) << 8) |
+                                (static_cast<uint32_t>(flip ? fj4(f) : fk4(f)) << 16);
                         sl.store_plane(f, n, dist);
                         if (!(fabs(dist) < 1e30)) bad = true; // NaN / inf: the key order would not be the heap's
                         if (!(dist > 0.0)) batch_positive = false;
                         shm.key[f][t] = __double2float_rd(dist);
-                        // horizon-order record of this batch (used only to resolve zero-distance ties)
-                        shm.hz[f][t] = static_cast<uint32_t>(f) << 24;
+                        shm.hz[f][t] = static_cast<uint32_t>(f) << 24; // push order of this batch (zero-distance ties)
                     }
-                    for (int i = 0; i < 4; ++i)
-                        for (int j = i + 1; j < 4; ++j)
-                            for (int e1 = 0; e1 < 3; ++e1)
-                            {
-                                uint8_t u1 = tv[i][e1], v1 = tv[i][(e1 + 1) % 3];
-                                for (int e2 = 0; e2 < 3; ++e2)
-                                {
-                                    uint8_t u2 = tv[j][e2], v2 = tv[j][(e2 + 1) % 3];
-                                    if (u1 == v2 && v1 == u2)
-                                    {
-                                        ta[i][e1] = static_cast<uint8_t>(j);
-                                        ta[j][e2] = static_cast<uint8_t>(i);
-                                    }
-                                }
-                            }
+                    // brute-force adjacency (collision.cpp:373-388).  An undirected tetrahedron edge belongs to
+                    // exactly two faces, so a directed edge has at most one reversed partner and the reference's
+                    // i<j visiting order cannot matter: each face looks its three partners up independently.
+#pragma unroll
                     for (int f = 0; f < 4; ++f)
                     {
-                        unsigned long long w = 0;
-                        for (int k = 0; k < 3; ++k)
-                            w |= (static_cast<unsigned long long>(tv[f][k]) << (8 * k)) | (static_cast<unsigned long long>(ta[f][k]) << (24 + 8 * k));
+                        unsigned long long w = tv[f];
+#pragma unroll
+                        for (int e1 = 0; e1 < 3; ++e1)
+                        {
+                            const uint32_t u1 = (tv[f] >> (8 * e1)) & 0xFFu, v1 = (tv[f] >> (8 * ((e1 + 1) % 3))) & 0xFFu;
+                            unsigned long long adj = 0xFFull;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                            {
+                                const uint32_t o = tv[j];
+                                const bool m = (j != f) && (((o & 0xFFu) == v1 && ((o >> 8) & 0xFFu) == u1) ||
+                                                            (((o >> 8) & 0xFFu) == v1 && ((o >> 16) & 0xFFu) == u1) ||
+                                                            (((o >> 16) & 0xFFu) == v1 && (o & 0xFFu) == u1));
+                                if (m) adj = static_cast<unsigned long long>(j);
+                            }
+                            w |= adj << (24 + 8 * e1);
+                        }
                         sl.topo[f] = w;
                     }
                     fm0 = ~0xFull;
-                    fm1 = 0xFFFFFFFFu;
+                    fm1 = ~0ull;
+                    fm2 = (1u << (ES_SLOTS - 128)) - 1u;
                     hi = 4;
                     nverts = 4;
-                    iter = 0;
                     older_positive = true;
-                    batch_first = 0;
                     batch_n = 4;
                     active = true;
-                    if (bad) to_fallback();
+                    if (bad) fb = 4;
                 }
             }
         }
-        if (!active) continue;
+        if (!active || fb) continue;
 
         // ---- pop_face (collision.cpp:397-408) without a heap: the live face with the smallest distance ----
         int min_face = -1;
         {
             float m = INF;
             int cnt = 0;
-            for (int s = 0; s < hi; ++s)
+            const int hs = hi < ES_KEYS ? hi : ES_KEYS;
+            for (int s = 0; s < hs; ++s)
             {
                 const float k = shm.key[s][t];
+                if (k < m)
+                {
+                    m = k;
+                    min_face = s;
+                    cnt = 1;
+                }
+                else if (k == m)
+                    ++cnt;
+            }
+            for (int s = ES_KEYS; s < hi; ++s) // only polytopes past 46 iterations
+            {
+                const float k = key_of(s);
                 if (k < m)
                 {
                     m = k;
@@ -351,7 +409,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 bool tie = false;
                 for (int s = min_face + 1; s < hi; ++s)
                 {
-                    if (shm.key[s][t] != m) continue;
+                    if (key_of(s) != m) continue;
                     const double d = sl.plane[4 * s + 3];
                     if (d < best)
                     {
@@ -375,8 +433,8 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                     {
                         for (int e = 0; e < batch_n && !resolved; ++e)
                         {
-                            const int s = static_cast<int>(shm.hz[batch_first + e][t] >> 24);
-                            if (shm.key[s][t] != INF && sl.plane[4 * s + 3] == 0.0)
+                            const int s = hz_slot(shm.hz[e][t]);
+                            if (!is_free(s) && sl.plane[4 * s + 3] == 0.0)
                             {
                                 min_face = s;
                                 resolved = true;
@@ -385,7 +443,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                     }
                     if (!resolved)
                     {
-                        to_fallback();
+                        fb = 2;
                         continue;
                     }
                 }
@@ -399,29 +457,37 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         }
         const double4 mf = sl.load_plane(min_face);
         const unsigned long long mt = sl.topo[min_face];
-        if (iter >= 64)
+        bool finished = iter >= 64; // best guess after the loop (collision.cpp:500-503)
+        if (!finished) ++iter;
+        // the flood fill starts with the three neighbours of this face: have them on their way during the
+        // support evaluation
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
         {
-            es_write_result(sl, mf, mt, contacts + out_slot, key); // best guess (collision.cpp:500-503)
-            valid[out_slot] = 1;
-            ++n_valid;
-            active = false;
-            continue;
+            const int b = es_adj(mt, k);
+            if (b != 0xFF)
+            {
+                es_prefetch(sl.plane + 4 * b);
+                es_prefetch(sl.topo + b);
+            }
         }
-        ++iter;
         const d3 mn{mf.x, mf.y, mf.z};
-        SupportPt sp;
+        SupportPt sp{}; // minkowski_support (collision.h:41-49); one copy of the support code for both shapes
+        if (!finished)
         {
-            ShapeView A = es_get_shape(shm, 0);
-            sp.pa = support(A, mn);
-        }
-        {
-            ShapeView B = es_get_shape(shm, 1);
-            sp.pb = support(B, -mn);
+            {
+                const ShapeView A = es_get_shape(shm, 0);
+                sp.pa = support(A, mn);
+            }
+            {
+                const ShapeView B = es_get_shape(shm, 1);
+                sp.pb = support(B, -mn);
+            }
         }
         const d3 p = P(sp);
-        if (dot(mn, p) - mf.w < 1e-6)
+        if (finished || dot(mn, p) - mf.w < 1e-6) // converged (collision.cpp:465-466)
         {
-            es_write_result(sl, mf, mt, contacts + out_slot, key); // converged (collision.cpp:465-466)
+            es_write_result(sl, mf, mt, contacts + out_slot, key);
             valid[out_slot] = 1;
             ++n_valid;
             active = false;
@@ -445,7 +511,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 for (int i = 0; i < 3; ++i)
                 {
                     const int a = es_adj(cur, i);
-                    live[i] = a != 0xFF && shm.key[a][t] != INF;
+                    live[i] = a != 0xFF && !is_free(a);
                     if (live[i])
                     {
                         nf[i] = sl.load_plane(a);
@@ -457,7 +523,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 {
                     if (!live[i]) continue;
                     const int a = es_adj(cur, i);
-                    if (shm.key[a][t] == INF) continue; // reached through two edges of this face: first visit killed it
+                    if (is_free(a)) continue; // reached through two edges of this face: the first visit killed it
                     if (dot(d3{nf[i].x, nf[i].y, nf[i].z}, p) > nf[i].w + 1e-6)
                     {
                         kill_slot(a);
@@ -482,14 +548,21 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                     }
                     else
                     {
+                        // horizon edge (cur.v[i], cur.v[i+1], a).  link_faces(f, a, start, end) will need the
+                        // edge of `a` that starts at `end` (collision.cpp:305-313): `a` is in registers now
+                        const int st = es_v(cur, i), en = es_v(cur, (i + 1) % 3);
+                        const int e2 = (es_v(nt[i], 0) == en) ? 0 : (es_v(nt[i], 1) == en ? 1 : 2);
+                        if (es_v(nt[i], e2) != en) bad = true; // unmatched link: slot recycling is no longer safe
                         if (nh < ES_HORIZON)
                         {
-                            shm.hz[nh][t] = static_cast<uint32_t>(es_v(cur, i)) | (static_cast<uint32_t>(es_v(cur, (i + 1) % 3)) << 8) |
-                                            (static_cast<uint32_t>(a) << 16);
+                            shm.hz[nh][t] = static_cast<uint32_t>(st) | (static_cast<uint32_t>(en) << 7) | (static_cast<uint32_t>(a) << 14) |
+                                            (static_cast<uint32_t>(e2) << 22);
                             ++nh;
                         }
                         else
                             bad = true;
+                        es_prefetch(sl.vpos + 4 * st); // operands of the face loop
+                        es_prefetch(sl.vpos + 4 * en);
                     }
                 }
                 if (depth == 0) break;
@@ -504,87 +577,96 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
             iter = 64; // empty horizon → best remaining face (collision.cpp:469,500-503)
             continue;
         }
-        const int nfree = __popcll(fm0) + __popc(fm1);
+        const int nfree = __popcll(fm0) + __popcll(fm1) + __popc(fm2);
         if (bad || nh < 3 || nfree < nh || nverts >= ES_VERTS)
         {
-            to_fallback();
+            fb = (nfree < nh || nverts >= ES_VERTS) ? 3 : 4;
             continue;
-        }
-        // operands of the face loop: horizon vertices and the topology of the faces across the horizon
-        for (int e = 0; e < nh; ++e)
-        {
-            const uint32_t h = shm.hz[e][t];
-            es_prefetch(sl.vpos + 4 * (h & 0xFFu));
-            es_prefetch(sl.topo + ((h >> 16) & 0xFFu));
         }
         sl.set_vert(nverts, sp, p);
         const int p_idx = nverts++;
         older_positive = older_positive && batch_positive;
         batch_positive = true;
-        // new faces (start, end, p_idx), no orientation flip (collision.cpp:475-482), slots lowest free first
-        unsigned long long end_seen = 0;
+        // new faces (start, end, p_idx), no orientation flip (collision.cpp:475-482), slots lowest free first;
+        // the vertex loads of edge e+1 are issued before the arithmetic of edge e
+        unsigned long long end_seen0 = 0;
+        uint32_t end_seen1 = 0;
+        uint32_t h = shm.hz[0][t];
+        d3 ps = sl.vp(hz_start(h)), pe = sl.vp(hz_end(h));
         for (int e = 0; e < nh; ++e)
         {
-            const uint32_t h = shm.hz[e][t];
-            const int st = static_cast<int>(h & 0xFFu), en = static_cast<int>((h >> 8) & 0xFFu), ad = static_cast<int>((h >> 16) & 0xFFu);
+            const uint32_t hc = h;
+            const d3 cs = ps, ce = pe;
+            if (e + 1 < nh)
+            {
+                h = shm.hz[e + 1][t];
+                ps = sl.vp(hz_start(h));
+                pe = sl.vp(hz_end(h));
+            }
+            const int st = hz_start(hc), en = hz_end(hc);
             int slot;
             if (fm0)
             {
                 slot = __ffsll(static_cast<long long>(fm0)) - 1;
                 fm0 &= fm0 - 1;
             }
-            else
+            else if (fm1)
             {
-                slot = 64 + __ffs(static_cast<int>(fm1)) - 1;
+                slot = 64 + __ffsll(static_cast<long long>(fm1)) - 1;
                 fm1 &= fm1 - 1;
             }
+            else
+            {
+                slot = 128 + __ffs(static_cast<int>(fm2)) - 1;
+                fm2 &= fm2 - 1;
+            }
             if (slot >= hi) hi = slot + 1;
-            d3 n;
-            double dist;
-            epa_face_plane(sl.vp(st), sl.vp(en), p, false, d3{0, 0, 0}, n, dist);
+            bool flip_unused;
+            const double4 pl = es_face_plane(cs, ce, p, false, d3{0, 0, 0}, flip_unused);
+            const d3 n{pl.x, pl.y, pl.z};
+            const double dist = pl.w;
             sl.store_plane(slot, n, dist);
             if (!(fabs(dist) < 1e30)) bad = true;
             if (!(dist > 0.0)) batch_positive = false;
-            shm.key[slot][t] = __double2float_rd(dist);
-            shm.hz[e][t] = h | (static_cast<uint32_t>(slot) << 24);
+            if (slot < ES_KEYS) shm.key[slot][t] = __double2float_rd(dist);
+            shm.hz[e][t] = hc | (static_cast<uint32_t>(slot) << 24);
             shm.ring[e][t] = 0xFFFFu;
-            // link_faces(f, adj_face, start, end): on the old face the shared edge starts at `end`
-            const unsigned long long tb = sl.topo[ad];
-            const int e2 = (es_v(tb, 0) == en) ? 0 : (es_v(tb, 1) == en ? 1 : 2);
-            if (es_v(tb, e2) != en) bad = true; // unmatched link: slot recycling is no longer safe
-            sl.set_adj(ad, e2, slot);
+            sl.set_adj(hz_adj(hc), hz_e2(hc), slot); // link_faces(f, adj_face, start, end), the old face's side
             // proper horizon: every vertex starts at most one edge and ends at most one, no self loop
-            if (st == en || shm.edge_of_start[st][t] != 0xFF || ((end_seen >> en) & 1ull)) bad = true;
+            const bool ends_twice = (en < 64) ? ((end_seen0 >> en) & 1ull) : ((end_seen1 >> (en - 64)) & 1u);
+            if (st == en || shm.edge_of_start[st][t] != 0xFF || ends_twice) bad = true;
             shm.edge_of_start[st][t] = static_cast<uint8_t>(e);
-            end_seen |= 1ull << en;
+            if (en < 64)
+                end_seen0 |= 1ull << en;
+            else
+                end_seen1 |= 1u << (en - 64);
         }
         // ring links among the new faces (collision.cpp:484-497): face e = (start, end, p_idx) gets its
         // successor (the edge starting at `end`) on edge 1 and is that face's neighbour on edge 2
         for (int e = 0; e < nh; ++e)
         {
-            const uint32_t h = shm.hz[e][t];
-            const int j = shm.edge_of_start[(h >> 8) & 0xFFu][t];
+            const uint32_t he = shm.hz[e][t];
+            const int j = shm.edge_of_start[hz_end(he)][t];
             if (j == 0xFF) continue;
             const uint32_t hj = shm.hz[j][t];
-            if (shm.edge_of_start[(hj >> 8) & 0xFFu][t] == e) bad = true; // 2-cycle: the reference links it one way only
+            if (shm.edge_of_start[hz_end(hj)][t] == e) bad = true; // 2-cycle: the reference links it one way only
             shm.ring[e][t] = static_cast<uint16_t>((shm.ring[e][t] & 0xFF00u) | (hj >> 24));
-            shm.ring[j][t] = static_cast<uint16_t>((shm.ring[j][t] & 0x00FFu) | ((h >> 24) << 8));
+            shm.ring[j][t] = static_cast<uint16_t>((shm.ring[j][t] & 0x00FFu) | ((he >> 24) << 8));
         }
         for (int e = 0; e < nh; ++e)
         {
-            const uint32_t h = shm.hz[e][t];
+            const uint32_t he = shm.hz[e][t];
             const uint32_t rg = shm.ring[e][t];
-            shm.edge_of_start[h & 0xFFu][t] = 0xFF;
-            sl.topo[h >> 24] = static_cast<unsigned long long>(h & 0xFFFFu) | (static_cast<unsigned long long>(p_idx) << 16) |
-                               (static_cast<unsigned long long>((h >> 16) & 0xFFu) << 24) |
-                               (static_cast<unsigned long long>(rg & 0xFFu) << 32) | (static_cast<unsigned long long>(rg >> 8) << 40);
+            shm.edge_of_start[hz_start(he)][t] = 0xFF;
+            sl.topo[hz_slot(he)] = static_cast<unsigned long long>(hz_start(he)) | (static_cast<unsigned long long>(hz_end(he)) << 8) |
+                                   (static_cast<unsigned long long>(p_idx) << 16) | (static_cast<unsigned long long>(hz_adj(he)) << 24) |
+                                   (static_cast<unsigned long long>(rg & 0xFFu) << 32) | (static_cast<unsigned long long>(rg >> 8) << 40);
         }
         if (bad)
         {
-            to_fallback();
+            fb = 4;
             continue;
         }
-        batch_first = 0;
         batch_n = nh;
     }
     if (n_valid) atomicAdd(counters + 0, n_valid);
