@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -86,9 +87,11 @@ enum Counter
     C_GJK_CURSOR,
     C_CLASS_COUNT, // [3]
     C_CLASS_FILL = C_CLASS_COUNT + 3, // [3]
-    C_EPA_FALLBACK = C_CLASS_FILL + 3, // pairs the group EPA kernel handed to the thread-per-pair kernel
-    C_EPA_CURSOR2,
-    C_COUNT = 24
+    C_EPA_FALLBACK = C_CLASS_FILL + 3, // [2] pairs handed back by the SCAN / by the HEAP instance of epa_scan_kernel
+    C_EPA_SCAN_CURSOR = C_EPA_FALLBACK + 3, // [2] work cursors of those two launches
+    C_EPA_FB_CURSOR = C_EPA_SCAN_CURSOR + 3, // work cursor of epa_kernel on the second fallback list
+    C_EPA_REASONS = C_EPA_FALLBACK + 10, // [6] debug builds (PK_ES_REASONS)
+    C_COUNT = 32
 };
 
 } // namespace
@@ -147,7 +150,7 @@ struct pk_ctx
     uint32_t *d_gjk_work = nullptr;
     unsigned char *d_slabs = nullptr;
     unsigned char *d_epa_spill = nullptr;
-    uint32_t *d_epa_fallback = nullptr;
+    uint32_t *d_epa_fallback = nullptr, *d_epa_fallback2 = nullptr;
     uint32_t epa_group_blocks = 0;
     uint32_t epa_scan_blocks = 0;
     uint32_t epa_blocks = 0;
@@ -326,18 +329,33 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
                 ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
                 ctx->d_counters + C_EPA_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
                 ctx->d_counters + C_EPA_FALLBACK);
-#else
-        epa_scan_kernel<<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
-            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
-            ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
-            ctx->d_counters + C_EPA_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK);
-#endif
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_fallback, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
-            ctx->d_counters + C_EPA_CURSOR2, ctx->d_counters + C_VALID);
+            ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID);
         ctx->launches += 3;
+#else
+        // Pairs with a sphere: heap-free pop (SCAN instance).  What it hands back (exact distance ties that
+        // only the heap's history can break) goes first into the HEAP instance, which restates the heap and
+        // then does the polyhedron pairs; what that one hands back (padded simplices, improper horizons,
+        // polytopes past 255 faces: a handful) is left to epa_kernel.
+        epa_scan_kernel<false><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
+            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
+            ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
+            ctx->d_counters + C_EPA_SCAN_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
+            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr);
+        epa_scan_kernel<true><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
+            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
+            ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
+            ctx->d_counters + C_EPA_SCAN_CURSOR + 1, ctx->d_counters + C_VALID, ctx->d_epa_fallback2,
+            ctx->d_counters + C_EPA_FALLBACK + 1, ctx->d_counters + C_CLASS_COUNT, ctx->d_epa_fallback,
+            ctx->d_counters + C_EPA_FALLBACK);
+        epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
+            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK + 1, ctx->max_contacts,
+            ctx->d_out_index, ctx->d_epa_fallback2, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
+            ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID);
+        ctx->launches += 4;
+#endif
 #endif
     }
     if (timed) cudaEventRecord(ctx->ev[ST_COMPACT], ctx->stream);
@@ -391,7 +409,7 @@ int pk_destroy(pk_ctx *ctx)
                    ctx->d_merge_flag,  ctx->d_pkeys[0],     ctx->d_pkeys[1],    ctx->d_hit,          ctx->d_out_index,
                    ctx->d_scan_tiles,  ctx->d_simplices,    ctx->d_contacts[0], ctx->d_contacts[1],  ctx->d_valid,
                    ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order,    ctx->d_gjk_work,
-                   ctx->d_epa_spill,   ctx->d_epa_fallback};
+                   ctx->d_epa_spill,   ctx->d_epa_fallback, ctx->d_epa_fallback2};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -515,17 +533,23 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
         A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_group_blocks) * EG_GROUPS_PER_BLOCK * EpaGroupSpill::BYTES);
 #elif PK_EPA_IMPL == 2
         // scan EPA: 48 KB of shared memory per 64-thread block, as many blocks per SM as the carve-out allows
-        cudaFuncSetAttribute(epa_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_scan_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_scan_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int es_per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_scan_kernel, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_scan_kernel<false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
             es_per_sm = 1;
 #ifdef PK_ES_BLOCKS_PER_SM
         es_per_sm = std::min(es_per_sm, PK_ES_BLOCKS_PER_SM);
 #endif
-        uint64_t es_want = static_cast<uint64_t>(ctx->sm_count) * es_per_sm;
-        uint64_t es_need = (nc + ES_THREADS - 1) / ES_THREADS;
-        ctx->epa_scan_blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min(es_want, es_need)));
-        A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_scan_blocks) * ES_THREADS * ES_SLAB_BYTES);
+#ifdef PK_ES_FORCE_BLOCKS
+        es_per_sm = PK_ES_FORCE_BLOCKS;
+#endif
+        if (getenv("PK_DEBUG")) fprintf(stderr, "[pk] epa_scan_kernel: %d blocks per SM\n", es_per_sm);
+        const uint64_t es_need = (nc + ES_THREADS - 1) / ES_THREADS;
+        ctx->epa_scan_blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(ctx->sm_count) * es_per_sm, es_need)));
+        // the two instances run one after the other and share the slab area
+        A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_scan_blocks) * ES_THREADS * std::max(es_slab_bytes(false), es_slab_bytes(true)));
+        A(ctx->d_epa_fallback2, nc);
 #endif
         A(ctx->d_epa_fallback, nc);
     }
@@ -950,12 +974,16 @@ int pk_stage_times_get(pk_ctx *ctx, pk_stage_times *out)
         out->name[k] = kStageNames[k];
     }
     out->launches = ctx->launches;
-    out->epa_fallback = static_cast<uint32_t>(ctx->h_counters ? ctx->h_counters[C_EPA_FALLBACK] : 0);
+    out->epa_fallback = static_cast<uint32_t>(ctx->h_counters ? ctx->h_counters[C_EPA_FALLBACK + 1] : 0);
 #ifdef PK_ES_REASONS
     if (ctx->h_counters)
         fprintf(stderr, "[epa fallback] total %llu: pad %llu tie %llu capacity %llu improper %llu; iterations thrown away %llu\n",
-                ctx->h_counters[C_EPA_FALLBACK], ctx->h_counters[C_EPA_FALLBACK + 2], ctx->h_counters[C_EPA_FALLBACK + 3],
-                ctx->h_counters[C_EPA_FALLBACK + 4], ctx->h_counters[C_EPA_FALLBACK + 5], ctx->h_counters[C_EPA_FALLBACK + 6]);
+                static_cast<unsigned long long>(out->epa_fallback), ctx->h_counters[C_EPA_REASONS], ctx->h_counters[C_EPA_REASONS + 1],
+                ctx->h_counters[C_EPA_REASONS + 2], ctx->h_counters[C_EPA_REASONS + 3], ctx->h_counters[C_EPA_REASONS + 4]);
+    if (ctx->h_counters)
+        fprintf(stderr, "[epa fallback] SCAN handed back %llu; HEAP handed back: pad %llu capacity %llu improper %llu\n",
+                ctx->h_counters[C_EPA_FALLBACK], ctx->h_counters[C_EPA_REASONS + 6], ctx->h_counters[C_EPA_REASONS + 8],
+                ctx->h_counters[C_EPA_REASONS + 9]);
 #endif
     return PK_OK;
 }

@@ -32,15 +32,49 @@ namespace pk
 
 constexpr int ES_THREADS = 64;
 constexpr int ES_SLOTS = 136;  // live faces = 2V − 4 ≤ 132
-constexpr int ES_KEYS = 96;    // slots with a float key in shared memory (the rest is scanned from the slab)
+constexpr int ES_KEYS = 92;    // slots with a float key in shared memory (the rest is scanned from the slab);
+                               // 92/4 is odd: a thread's keys are contiguous and 128-bit loads are conflict-free
 constexpr int ES_VERTS = 68;   // 4 + 64 iterations
 constexpr int ES_HORIZON = 16; // observed max 10
 constexpr int ES_STACK = 8;    // observed max 4
-constexpr size_t ES_SLAB_BYTES = static_cast<size_t>(ES_SLOTS) * (32 + 8) + static_cast<size_t>(ES_VERTS) * (32 + 48);
+constexpr int ES_HEAP_MAX = EPA_MAX_FACES; // HEAP mode: heap entries (= faces ever created), as epa_kernel
+// per-thread slab: planes, topology, vertices (+ in HEAP mode the heap entries beyond the shared-memory top)
+__host__ __device__ constexpr size_t es_slab_bytes(bool heap)
+{
+    return static_cast<size_t>(ES_SLOTS) * (32 + 8) + static_cast<size_t>(ES_VERTS) * (32 + 48) +
+           (heap ? static_cast<size_t>(ES_HEAP_MAX) * (8 + 4) : 0);
+}
+
+constexpr int ES_HCAP = 30; // heap entries of the exact-heap mode kept in shared memory (polyhedron pairs: observed max 34)
+
+// How pop_face finds the closest live face, chosen per pair.  SCAN (pairs with a sphere): float keys, no
+// heap — distances of distinct faces practically never tie.  HEAP (polyhedron pairs): the reference's
+// binary heap restated in shared memory — coplanar faces tie all the time, but these polytopes stay small
+// enough for the whole heap to fit.  Both share one area of shared memory.
+// per-thread area: ES_KEYS floats (SCAN) or ES_HCAP × (double distance, uint8 face) (HEAP).  Threads of one
+// block are in different modes at the same time, so both layouts keep a thread inside its own bytes.
+struct alignas(16) EsPopThread
+{
+    union
+    {
+        float key[ES_KEYS]; // float(distance) rounded down; +inf = free slot; scanned four at a time
+        struct
+        {
+            double hd[ES_HCAP];   // heap: copy of the face distance
+            uint32_t hf[ES_HCAP]; // heap: slot | creation serial << 8 (slots are recycled: the serial tells a
+                                  // lazily deleted entry from the face that lives in its slot now)
+        } heap;
+    };
+};
+static_assert(sizeof(EsPopThread) == ES_KEYS * 4, "the heap must fit the key area");
+struct EsPop
+{
+    EsPopThread th[ES_THREADS];
+};
 
 struct EsSmem
 {
-    float key[ES_KEYS][ES_THREADS];  // float(distance) rounded down; +inf = free slot
+    EsPop pop;
     double f[2][10][ES_THREADS];     // shape views: p xyz, h xyz, q xyzw
     const double *verts[2][ES_THREADS];
     const float4 *vf[2][ES_THREADS];
@@ -49,7 +83,6 @@ struct EsSmem
     uint32_t nverts[2][ES_THREADS];
     uint32_t hz[ES_HORIZON][ES_THREADS];   // start:7 | end:7 | adjacent slot:8 | its edge:2 | new slot:8
     uint16_t ring[ES_HORIZON][ES_THREADS]; // successor slot | predecessor slot << 8 (0xFF = none)
-    uint8_t edge_of_start[ES_VERTS][ES_THREADS];
 };
 static_assert(sizeof(EsSmem) <= 48 * 1024, "EsSmem must fit static shared memory");
 
@@ -59,15 +92,22 @@ struct EsSlab
     unsigned long long *topo; // bytes 0-2 vertices, 3-5 adjacent slots (0xFF = none)
     double *vpos;             // p = pa − pb, padded to 32 bytes
     double *vab;              // pa xyz, pb xyz
-    __device__ __forceinline__ explicit EsSlab(unsigned char *base)
+    double *hd;               // HEAP mode: heap entries ≥ ES_HCAP (distance)
+    uint32_t *hf;             // HEAP mode: heap entries ≥ ES_HCAP (slot | creation serial << 8)
+    __device__ __forceinline__ EsSlab(unsigned char *base, bool heap)
     {
+        const size_t slots = ES_SLOTS;
         plane = reinterpret_cast<double *>(base);
-        base += static_cast<size_t>(ES_SLOTS) * 32;
+        base += slots * 32;
         topo = reinterpret_cast<unsigned long long *>(base);
-        base += static_cast<size_t>(ES_SLOTS) * 8;
+        base += slots * 8;
         vpos = reinterpret_cast<double *>(base);
         base += static_cast<size_t>(ES_VERTS) * 32;
         vab = reinterpret_cast<double *>(base);
+        base += static_cast<size_t>(ES_VERTS) * 48;
+        hd = reinterpret_cast<double *>(base);
+        base += static_cast<size_t>(ES_HEAP_MAX) * 8;
+        hf = reinterpret_cast<uint32_t *>(base);
     }
     __device__ __forceinline__ double4 load_plane(int f) const
     {
@@ -118,7 +158,7 @@ __device__ __forceinline__ int fo4(int f) { return (0x0213 >> (4 * f)) & 0xF; }
 __device__ __forceinline__ void es_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float es_inf() { return __int_as_float(0x7F800000); }
 
-__device__ __forceinline__ void es_put_shape(EsSmem &sm, int which, const ShapeView &v)
+template <class SM> __device__ __forceinline__ void es_put_shape(SM &sm, int which, const ShapeView &v)
 {
     const int t = threadIdx.x;
     sm.f[which][0][t] = v.p.x; sm.f[which][1][t] = v.p.y; sm.f[which][2][t] = v.p.z;
@@ -130,7 +170,7 @@ __device__ __forceinline__ void es_put_shape(EsSmem &sm, int which, const ShapeV
     sm.kind[which][t] = v.kind;
     sm.nverts[which][t] = v.nverts;
 }
-__device__ __forceinline__ ShapeView es_get_shape(const EsSmem &sm, int which)
+template <class SM> __device__ __forceinline__ ShapeView es_get_shape(const SM &sm, int which)
 {
     const int t = threadIdx.x;
     ShapeView v;
@@ -189,6 +229,80 @@ __device__ __noinline__ void es_write_result(const EsSlab &sl, double4 nd, unsig
     out->depth = nd.w;
 }
 
+// HEAP mode: the first ES_HCAP heap entries live in the thread's shared-memory area (every sift starts
+// there; polyhedron pairs never leave it), deeper ones in its slab.
+struct EsHeapRef
+{
+    EsPopThread *pt;
+    double *gd;
+    uint32_t *gf;
+    __device__ __forceinline__ double d(int k) const { return k < ES_HCAP ? pt->heap.hd[k] : gd[k]; }
+    __device__ __forceinline__ uint32_t f(int k) const { return k < ES_HCAP ? pt->heap.hf[k] : gf[k]; }
+    __device__ __forceinline__ void set(int k, double dist, uint32_t face) const
+    {
+        if (k < ES_HCAP)
+        {
+            pt->heap.hd[k] = dist;
+            pt->heap.hf[k] = face;
+        }
+        else
+        {
+            gd[k] = dist;
+            gf[k] = face;
+        }
+    }
+};
+// libstdc++ std::__push_heap with comp(a,b) = dist[a] > dist[b]  (collision.cpp:390-395)
+__device__ __forceinline__ void es_sift_up(const EsHeapRef &h, int hole, double vd, uint32_t vf)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > 0)
+    {
+        const double pd = h.d(parent);
+        if (!(pd > vd)) break;
+        h.set(hole, pd, h.f(parent));
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    h.set(hole, vd, vf);
+}
+// libstdc++ std::pop_heap (→ __pop_heap → __adjust_heap) followed by back()/pop_back()
+__device__ __forceinline__ uint32_t es_heap_pop(const EsHeapRef &h, int &size)
+{
+    const uint32_t top = h.f(0);
+    if (size == 1)
+    {
+        size = 0;
+        return top;
+    }
+    const int len = size - 1;
+    const double vd = h.d(len);
+    const uint32_t vf = h.f(len);
+    int hole = 0, child = 0;
+    while (child < (len - 1) / 2)
+    {
+        child = 2 * (child + 1);
+        const double rd = h.d(child), ld = h.d(child - 1);
+        if (rd > ld)
+        {
+            child--;
+            h.set(hole, ld, h.f(child));
+        }
+        else
+            h.set(hole, rd, h.f(child));
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2)
+    {
+        child = 2 * (child + 1);
+        h.set(hole, h.d(child - 1), h.f(child - 1));
+        hole = child - 1;
+    }
+    es_sift_up(h, hole, vd, vf);
+    size = len;
+    return top;
+}
+
 #ifndef PK_ES_MIN_BLOCKS
 #define PK_ES_MIN_BLOCKS 4
 #endif
@@ -196,6 +310,13 @@ __device__ __noinline__ void es_write_result(const EsSlab &sl, double4 nd, unsig
 #define PK_ES_FETCH_MIN 6
 #endif
 
+// The hit list is grouped by cost class (order[]: sphere–sphere, sphere–polyhedron, polyhedron–polyhedron);
+// class_count[] = sizes of the groups with 0, 1, 2 spheres.  The SCAN instance takes the two groups with a
+// sphere in one persistent launch, the HEAP instance the polyhedron pairs (a single kernel choosing the
+// mode per pair was measured slower: more registers, and both pop paths in every warp's instruction
+// stream).  Pairs handed back are published in fallback_list[] (entries start as EPA_LIST_EMPTY), where a
+// small epa_kernel launch running next to these kernels picks them up (pk_api.cu).
+template <bool HEAP>
 __global__ void __launch_bounds__(ES_THREADS, PK_ES_MIN_BLOCKS)
 epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
                 const uint32_t *__restrict__ pair_b, const SimplexRec *__restrict__ simplices,
@@ -203,53 +324,99 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 const uint32_t *__restrict__ out_index, const uint32_t *__restrict__ order, ContactRec *__restrict__ contacts,
                 uint8_t *__restrict__ valid, unsigned char *__restrict__ slabs, unsigned long long *__restrict__ cursor,
                 unsigned long long *__restrict__ counters /* [0]=valid contacts */, uint32_t *__restrict__ fallback_list,
-                unsigned long long *__restrict__ fallback_count)
+                unsigned long long *__restrict__ fallback_count, const unsigned long long *__restrict__ class_count,
+                const uint32_t *__restrict__ leftovers, const unsigned long long *__restrict__ leftover_count)
 {
+    // Work of the HEAP instance: first the pairs the SCAN instance handed back (leftovers[], complete at
+    // launch: mostly sphere–sphere pairs with an exact distance tie, long ones — started first so that
+    // they overlap the rest), then the polyhedron pairs of order[].
     __shared__ EsSmem shm;
     const int t = threadIdx.x;
     const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    const EsSlab sl(slabs + tid * ES_SLAB_BYTES);
+    const EsSlab sl(slabs + tid * es_slab_bytes(HEAP), HEAP);
+    const EsHeapRef hp{&shm.pop.th[t], sl.hd, sl.hf};
     unsigned long long nhits = *hit_count_ptr;
     if (nhits > hit_capacity) nhits = hit_capacity;
+    const unsigned long long fb_capacity = nhits;
+    unsigned long long first_hit = class_count[2] + class_count[1]; // where the polyhedron pairs start
+    if (first_hit > nhits) first_hit = nhits;
+    unsigned long long nleft = 0;
+    if (HEAP)
+    {
+        nhits -= first_hit;
+        nleft = *leftover_count < fb_capacity ? *leftover_count : fb_capacity;
+    }
+    else
+    {
+        nhits = first_hit;
+        first_hit = 0;
+    }
     const float INF = es_inf();
 
     bool active = false, done = false;
-    int nverts = 0, iter = 0, hi = 0;      // hi: slots [0, hi) have been used by the current polytope
-    unsigned long long fm0 = 0, fm1 = 0;   // free slots 0-63, 64-127
-    uint32_t fm2 = 0;                      // free slots 128-135
+    int nverts = 0, iter = 0, hi = 0; // hi: slots [0, hi) have been used by the current polytope
+    bool keys_dirty = true;           // the key area does not hold +inf beyond the current polytope
+    unsigned long long fm0 = 0, fm1 = 0, fm2 = 0; // free slots, 64 per word
     uint32_t out_slot = 0, cur_sidx = 0;
     uint64_t key = 0;
-    // zero-distance ties (see pop): all faces created before the last batch were strictly farther than 0
-    bool older_positive = true, batch_positive = true;
-    int batch_n = 0; // hz[0, batch_n) still describes the last batch of faces
+    // tie breaking (see pop): lower bound of the distances of the lazily deleted heap entries the reference's
+    // heap would still hold (faces killed by the flood fill; a pop removes every entry below the popped one)
+    double stale_lb = 1e300;
+    int batch_n = 0; // hz[0, batch_n) still describes the last batch of faces, in push order
     unsigned long long n_valid = 0;
-#pragma unroll 1
-    for (int s = 0; s < ES_KEYS; ++s) shm.key[s][t] = INF;
-#pragma unroll 1
-    for (int v = 0; v < ES_VERTS; ++v) shm.edge_of_start[v][t] = 0xFF;
+    int heap_size = 0, nfaces = 0; // HEAP: number of faces created so far = serial of the next one
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
     int fb = 0; // reason + 1 when the current pair has to go to epa_kernel (one atomic site for all of them)
     auto is_free = [&](int f) -> bool
     {
-        const unsigned long long w = (f < 64) ? fm0 : (f < 128 ? fm1 : static_cast<unsigned long long>(fm2));
+        const unsigned long long w = (f < 64) ? fm0 : (f < 128 ? fm1 : fm2);
         return (w >> (f & 63)) & 1ull;
     };
     auto kill_slot = [&](int f)
     {
-        if (f < ES_KEYS) shm.key[f][t] = INF;
+        if constexpr (!HEAP)
+        {
+            if (f < ES_KEYS) shm.pop.th[t].key[f] = INF;
+        }
         if (f < 64)
             fm0 |= 1ull << f;
         else if (f < 128)
             fm1 |= 1ull << (f - 64);
         else
-            fm2 |= 1u << (f - 128);
+            fm2 |= 1ull << (f - 128);
     };
     // float key of slot s: shared memory for the first ES_KEYS slots, derived from the slab beyond
     auto key_of = [&](int s) -> float
     {
-        if (s < ES_KEYS) return shm.key[s][t];
+        if constexpr (!HEAP)
+        {
+            if (s < ES_KEYS) return shm.pop.th[t].key[s];
+        }
         return is_free(s) ? INF : __double2float_rd(sl.plane[4 * s + 3]);
+    };
+    // slot of a new face.  SCAN: lowest free first (keeps the live polytope dense at the start of the slab
+    // and inside the keyed slots).  HEAP: never-used slots first, so that as long as the polytope has
+    // created at most ES_SLOTS faces a heap entry's slot equals its serial and "slot free" is the whole
+    // obsolete test; only bigger polytopes recycle and have to compare serials.
+    auto take_slot = [&]() -> int
+    {
+        int slot;
+        if (HEAP && nfaces < ES_SLOTS)
+            slot = nfaces;
+        else if (fm0)
+            slot = __ffsll(static_cast<long long>(fm0)) - 1;
+        else if (fm1)
+            slot = 64 + __ffsll(static_cast<long long>(fm1)) - 1;
+        else
+            slot = 128 + __ffsll(static_cast<long long>(fm2)) - 1;
+        if (slot < 64)
+            fm0 &= ~(1ull << slot);
+        else if (slot < 128)
+            fm1 &= ~(1ull << (slot - 64));
+        else
+            fm2 &= ~(1ull << (slot - 128));
+        return slot;
     };
 
     for (;;)
@@ -257,10 +424,10 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         if (fb)
         {
             unsigned long long i = atomicAdd(fallback_count, 1ull);
-            if (i < hit_capacity) fallback_list[i] = cur_sidx;
+            if (i < fb_capacity) fallback_list[i] = cur_sidx; // one word: publication needs no fence
 #ifdef PK_ES_REASONS
-            atomicAdd(fallback_count + 1 + fb, 1ull); // debug build only: C_EPA_FALLBACK + 2 + reason
-            atomicAdd(fallback_count + 6, static_cast<unsigned long long>(iter));
+            atomicAdd(fallback_count - (HEAP ? 1 : 0) + 9 + fb + (HEAP ? 6 : 0), 1ull); // debug build only
+            if (!HEAP) atomicAdd(fallback_count + 14, static_cast<unsigned long long>(iter));
 #endif
             fb = 0;
             active = false;
@@ -271,11 +438,11 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         if (!active && !done && (__popc(m_idle) >= PK_ES_FETCH_MIN || m_active == 0))
         {
             unsigned long long slot = atomicAdd(cursor, 1ull);
-            if (slot >= nhits)
+            if (slot >= nleft + nhits)
                 done = true;
             else
             {
-                cur_sidx = order[slot];
+                cur_sidx = (slot < nleft) ? leftovers[slot] : order[first_hit + (slot - nleft)];
                 const SimplexRec *r = simplices + cur_sidx;
                 const uint32_t pair = r->pair;
                 iter = 0;
@@ -313,11 +480,20 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                         pv[i] = P(s);
                         sl.set_vert(i, s, pv[i]);
                     }
-                    for (int s = 4; s < hi && s < ES_KEYS; ++s) shm.key[s][t] = INF; // leftovers of the previous polytope
+                    if constexpr (!HEAP)
+                    {
+                        // leftovers of the previous polytope; everything at start and after a HEAP pair,
+                        // whose heap occupied the same shared memory
+                        const int dirty = keys_dirty ? ES_KEYS : (hi < ES_KEYS ? hi : ES_KEYS);
+                        for (int s = 4; s < dirty; ++s) shm.pop.th[t].key[s] = INF;
+                        keys_dirty = false;
+                    }
+                    else
+                        keys_dirty = true;
+                    heap_size = 0;
                     // build_initial_tetrahedron (collision.cpp:355-388): faces (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0)
                     uint32_t tv[4]; // vertex triples, one byte each
                     bool bad = false;
-                    batch_positive = true;
 #pragma unroll
                     for (int f = 0; f < 4; ++f)
                     {
@@ -329,9 +505,16 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                                 (static_cast<uint32_t>(flip ? fj4(f) : fk4(f)) << 16);
                         sl.store_plane(f, n, dist);
                         if (!(fabs(dist) < 1e30)) bad = true; // NaN / inf: the key order would not be the heap's
-                        if (!(dist > 0.0)) batch_positive = false;
-                        shm.key[f][t] = __double2float_rd(dist);
-                        shm.hz[f][t] = static_cast<uint32_t>(f) << 24; // push order of this batch (zero-distance ties)
+                        if constexpr (HEAP)
+                        {
+                            es_sift_up(hp, heap_size, dist, static_cast<uint32_t>(f) | (static_cast<uint32_t>(f) << 8)); // push_face
+                            ++heap_size;
+                        }
+                        else
+                        {
+                            shm.pop.th[t].key[f] = __double2float_rd(dist);
+                            shm.hz[f][t] = static_cast<uint32_t>(f) << 24; // push order of this batch (zero-distance ties)
+                        }
                     }
                     // brute-force adjacency (collision.cpp:373-388).  An undirected tetrahedron edge belongs to
                     // exactly two faces, so a directed edge has at most one reversed partner and the reference's
@@ -356,14 +539,15 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                             }
                             w |= adj << (24 + 8 * e1);
                         }
-                        sl.topo[f] = w;
+                        sl.topo[f] = w | (static_cast<unsigned long long>(f) << 48); // creation serial
                     }
                     fm0 = ~0xFull;
                     fm1 = ~0ull;
-                    fm2 = (1u << (ES_SLOTS - 128)) - 1u;
+                    fm2 = (1ull << (ES_SLOTS - 128)) - 1ull;
                     hi = 4;
+                    nfaces = 4;
                     nverts = 4;
-                    older_positive = true;
+                    stale_lb = 1e300;
                     batch_n = 4;
                     active = true;
                     if (bad) fb = 4;
@@ -374,21 +558,40 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
 
         // ---- pop_face (collision.cpp:397-408) without a heap: the live face with the smallest distance ----
         int min_face = -1;
+        if constexpr (HEAP)
+        {
+            while (heap_size > 0) // skip obsolete entries: slot free, or re-used by a younger face
+            {
+                const uint32_t id = es_heap_pop(hp, heap_size);
+                const int f = static_cast<int>(id & 0xFFu);
+                if (is_free(f)) continue;
+                if (nfaces > ES_SLOTS && static_cast<uint32_t>(sl.topo[f] >> 48) != (id >> 8)) continue;
+                min_face = f;
+                break;
+            }
+        }
+        else
         {
             float m = INF;
             int cnt = 0;
             const int hs = hi < ES_KEYS ? hi : ES_KEYS;
-            for (int s = 0; s < hs; ++s)
+            const float4 *kq = reinterpret_cast<const float4 *>(shm.pop.th[t].key);
+            for (int s = 0; s < hs; s += 4) // slots in [hs, s+4) hold +inf: they never win and never count
             {
-                const float k = shm.key[s][t];
-                if (k < m)
+                const float4 k4 = kq[s >> 2];
+                const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
                 {
-                    m = k;
-                    min_face = s;
-                    cnt = 1;
+                    if (kk[u] < m)
+                    {
+                        m = kk[u];
+                        min_face = s + u;
+                        cnt = 1;
+                    }
+                    else if (kk[u] == m)
+                        ++cnt;
                 }
-                else if (k == m)
-                    ++cnt;
             }
             for (int s = ES_KEYS; s < hi; ++s) // only polytopes past 46 iterations
             {
@@ -422,23 +625,45 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 }
                 if (tie)
                 {
-                    // Which of two equidistant faces std::pop_heap delivers depends on the heap's history,
-                    // with one provable exception: if every entry ever pushed before the last batch was
-                    // strictly positive and the minimum is ±0, the first zero pushed by that batch sifted
-                    // up to the root (all ancestors > 0) and no later zero passes it (__push_heap moves a
-                    // parent down only if parent > value).  That is the degenerate-face case (normal 0,
-                    // distance 0, collision.cpp:282-287) which ends EPA at this pop.
+                    // Which of several equidistant faces std::pop_heap delivers depends on the heap's history.
+                    // Two cases can be decided without it.  Let d be the tied minimum and suppose every
+                    // lazily deleted entry still in the heap is farther than d (stale_lb, below).
+                    //  (1) exactly one tied face is older than the last batch of pushes: before that batch it
+                    //      was the strict minimum of the whole heap, hence the root; __push_heap moves a parent
+                    //      down only if parent > value, so no new entry with the same distance passed it.
+                    //  (2) all tied faces belong to the last batch: every older entry is farther than d, so the
+                    //      first of them to be pushed sifted up to the root and, as in (1), stayed there.
+                    // (2) covers the degenerate faces (normal 0, distance 0, collision.cpp:282-287) that one
+                    // iteration creates in pairs; (1) the mirror-image faces of sphere–sphere polytopes.
                     bool resolved = false;
-                    if (best == 0.0 && older_positive && batch_n > 0)
+                    if (best < stale_lb)
                     {
-                        for (int e = 0; e < batch_n && !resolved; ++e)
+                        int n_old = 0, old_face = -1, first_new = -1;
+                        for (int e = batch_n - 1; e >= 0; --e)
                         {
                             const int s = hz_slot(shm.hz[e][t]);
-                            if (!is_free(s) && sl.plane[4 * s + 3] == 0.0)
+                            if (!is_free(s) && sl.plane[4 * s + 3] == best) first_new = s;
+                        }
+                        for (int s = 0; s < hi; ++s)
+                        {
+                            if (key_of(s) != m || sl.plane[4 * s + 3] != best) continue; // (free slots have key +inf)
+                            bool in_batch = false;
+                            for (int e = 0; e < batch_n; ++e) in_batch = in_batch || hz_slot(shm.hz[e][t]) == s;
+                            if (!in_batch)
                             {
-                                min_face = s;
-                                resolved = true;
+                                ++n_old;
+                                old_face = s;
                             }
+                        }
+                        if (n_old == 1)
+                        {
+                            min_face = old_face;
+                            resolved = true;
+                        }
+                        else if (n_old == 0 && first_new >= 0)
+                        {
+                            min_face = first_new;
+                            resolved = true;
                         }
                     }
                     if (!resolved)
@@ -457,6 +682,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         }
         const double4 mf = sl.load_plane(min_face);
         const unsigned long long mt = sl.topo[min_face];
+        if (mf.w > stale_lb) stale_lb = mf.w; // entries closer than the popped face have left the heap
         bool finished = iter >= 64; // best guess after the loop (collision.cpp:500-503)
         if (!finished) ++iter;
         // the flood fill starts with the three neighbours of this face: have them on their way during the
@@ -527,6 +753,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                     if (dot(d3{nf[i].x, nf[i].y, nf[i].z}, p) > nf[i].w + 1e-6)
                     {
                         kill_slot(a);
+                        if (nf[i].w < stale_lb) stale_lb = nf[i].w; // its heap entry stays behind
                         if (depth < ES_STACK)
                         {
                             stack = (stack << 8) | static_cast<unsigned long long>(a);
@@ -577,20 +804,19 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
             iter = 64; // empty horizon → best remaining face (collision.cpp:469,500-503)
             continue;
         }
-        const int nfree = __popcll(fm0) + __popcll(fm1) + __popc(fm2);
-        if (bad || nh < 3 || nfree < nh || nverts >= ES_VERTS)
+        const int nfree = __popcll(fm0) + __popcll(fm1) + __popcll(fm2);
+        const bool full = nfree < nh || nverts >= ES_VERTS || (HEAP && heap_size + nh > ES_HEAP_MAX);
+        if (bad || nh < 3 || full)
         {
-            fb = (nfree < nh || nverts >= ES_VERTS) ? 3 : 4;
+            fb = full ? 3 : 4;
             continue;
         }
         sl.set_vert(nverts, sp, p);
         const int p_idx = nverts++;
-        older_positive = older_positive && batch_positive;
-        batch_positive = true;
         // new faces (start, end, p_idx), no orientation flip (collision.cpp:475-482), slots lowest free first;
         // the vertex loads of edge e+1 are issued before the arithmetic of edge e
-        unsigned long long end_seen0 = 0;
-        uint32_t end_seen1 = 0;
+        unsigned long long end_seen0 = 0, start_seen0 = 0;
+        uint32_t end_seen1 = 0, start_seen1 = 0;
         uint32_t h = shm.hz[0][t];
         d3 ps = sl.vp(hz_start(h)), pe = sl.vp(hz_end(h));
         for (int e = 0; e < nh; ++e)
@@ -604,22 +830,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 pe = sl.vp(hz_end(h));
             }
             const int st = hz_start(hc), en = hz_end(hc);
-            int slot;
-            if (fm0)
-            {
-                slot = __ffsll(static_cast<long long>(fm0)) - 1;
-                fm0 &= fm0 - 1;
-            }
-            else if (fm1)
-            {
-                slot = 64 + __ffsll(static_cast<long long>(fm1)) - 1;
-                fm1 &= fm1 - 1;
-            }
-            else
-            {
-                slot = 128 + __ffs(static_cast<int>(fm2)) - 1;
-                fm2 &= fm2 - 1;
-            }
+            const int slot = take_slot();
             if (slot >= hi) hi = slot + 1;
             bool flip_unused;
             const double4 pl = es_face_plane(cs, ce, p, false, d3{0, 0, 0}, flip_unused);
@@ -627,29 +838,45 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
             const double dist = pl.w;
             sl.store_plane(slot, n, dist);
             if (!(fabs(dist) < 1e30)) bad = true;
-            if (!(dist > 0.0)) batch_positive = false;
-            if (slot < ES_KEYS) shm.key[slot][t] = __double2float_rd(dist);
+            if constexpr (HEAP)
+            {
+                es_sift_up(hp, heap_size, dist, static_cast<uint32_t>(slot) | (static_cast<uint32_t>(nfaces) << 8)); // push_face, horizon order
+                ++heap_size;
+            }
+            else
+            {
+                if (slot < ES_KEYS) shm.pop.th[t].key[slot] = __double2float_rd(dist);
+            }
+            ++nfaces;
             shm.hz[e][t] = hc | (static_cast<uint32_t>(slot) << 24);
             shm.ring[e][t] = 0xFFFFu;
             sl.set_adj(hz_adj(hc), hz_e2(hc), slot); // link_faces(f, adj_face, start, end), the old face's side
             // proper horizon: every vertex starts at most one edge and ends at most one, no self loop
             const bool ends_twice = (en < 64) ? ((end_seen0 >> en) & 1ull) : ((end_seen1 >> (en - 64)) & 1u);
-            if (st == en || shm.edge_of_start[st][t] != 0xFF || ends_twice) bad = true;
-            shm.edge_of_start[st][t] = static_cast<uint8_t>(e);
+            const bool starts_twice = (st < 64) ? ((start_seen0 >> st) & 1ull) : ((start_seen1 >> (st - 64)) & 1u);
+            if (st == en || starts_twice || ends_twice) bad = true;
             if (en < 64)
                 end_seen0 |= 1ull << en;
             else
                 end_seen1 |= 1u << (en - 64);
+            if (st < 64)
+                start_seen0 |= 1ull << st;
+            else
+                start_seen1 |= 1u << (st - 64);
         }
         // ring links among the new faces (collision.cpp:484-497): face e = (start, end, p_idx) gets its
         // successor (the edge starting at `end`) on edge 1 and is that face's neighbour on edge 2
+        // (starts are unique, so the successor of an edge is found by a search over the ≤16 horizon records)
         for (int e = 0; e < nh; ++e)
         {
             const uint32_t he = shm.hz[e][t];
-            const int j = shm.edge_of_start[hz_end(he)][t];
-            if (j == 0xFF) continue;
-            const uint32_t hj = shm.hz[j][t];
-            if (shm.edge_of_start[hz_end(hj)][t] == e) bad = true; // 2-cycle: the reference links it one way only
+            const int en = hz_end(he);
+            const bool has_succ = (en < 64) ? ((start_seen0 >> en) & 1ull) : ((start_seen1 >> (en - 64)) & 1u);
+            if (!has_succ) continue;
+            int j = 0;
+            uint32_t hj = shm.hz[0][t];
+            while (hz_start(hj) != en) hj = shm.hz[++j][t];
+            if (hz_end(hj) == hz_start(he)) bad = true; // 2-cycle: the reference links it one way only
             shm.ring[e][t] = static_cast<uint16_t>((shm.ring[e][t] & 0xFF00u) | (hj >> 24));
             shm.ring[j][t] = static_cast<uint16_t>((shm.ring[j][t] & 0x00FFu) | ((he >> 24) << 8));
         }
@@ -657,10 +884,10 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         {
             const uint32_t he = shm.hz[e][t];
             const uint32_t rg = shm.ring[e][t];
-            shm.edge_of_start[hz_start(he)][t] = 0xFF;
             sl.topo[hz_slot(he)] = static_cast<unsigned long long>(hz_start(he)) | (static_cast<unsigned long long>(hz_end(he)) << 8) |
                                    (static_cast<unsigned long long>(p_idx) << 16) | (static_cast<unsigned long long>(hz_adj(he)) << 24) |
-                                   (static_cast<unsigned long long>(rg & 0xFFu) << 32) | (static_cast<unsigned long long>(rg >> 8) << 40);
+                                   (static_cast<unsigned long long>(rg & 0xFFu) << 32) | (static_cast<unsigned long long>(rg >> 8) << 40) |
+                                   (static_cast<unsigned long long>(nfaces - nh + e) << 48); // creation serial
         }
         if (bad)
         {
