@@ -175,9 +175,10 @@ STAGE_BYTES_DOC = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
-# `ncu --set full` capture of this workload at side 100 (profiles/r1_epa_c3_1M.md); null otherwise
-NCU_TRAFFIC_BYTES = {"epa": 29_770_394_000}
+# dram__bytes_read.sum + dram__bytes_write.sum per step of the dominant stage from the committed
+# `ncu --set full` capture of this workload at side 100 (profiles/r1_epa_scan_fullsize.md: both instances
+# of epa_scan_kernel, 5.99 GB + 1.65 GB; the thread-per-pair epa_kernel it replaced moved 31 GB); null otherwise
+NCU_TRAFFIC_BYTES = {"epa": 7_637_408_000}
 
 
 def stage_bytes(name, n, pairs, hits):

@@ -32,20 +32,30 @@ namespace pk
 
 constexpr int ES_THREADS = 64;
 constexpr int ES_SLOTS = 136;  // live faces = 2V − 4 ≤ 132
-constexpr int ES_KEYS = 92;    // slots with a float key in shared memory (the rest is scanned from the slab);
+#ifndef PK_ES_KEYS
+#define PK_ES_KEYS 92
+#endif
+#ifndef PK_ES_HORIZON
+#define PK_ES_HORIZON 16
+#endif
+#ifndef PK_ES_HCAP
+#define PK_ES_HCAP 30
+#endif
+constexpr int ES_KEYS = PK_ES_KEYS; // slots with a float key in shared memory (the rest is scanned from the slab);
                                // 92/4 is odd: a thread's keys are contiguous and 128-bit loads are conflict-free
 constexpr int ES_VERTS = 68;   // 4 + 64 iterations
-constexpr int ES_HORIZON = 16; // observed max 10
+constexpr int ES_HORIZON = PK_ES_HORIZON; // observed max 10
 constexpr int ES_STACK = 8;    // observed max 4
 constexpr int ES_HEAP_MAX = EPA_MAX_FACES; // HEAP mode: heap entries (= faces ever created), as epa_kernel
 // per-thread slab: planes, topology, vertices (+ in HEAP mode the heap entries beyond the shared-memory top)
+constexpr int ES_GKEYS = (ES_SLOTS - ES_KEYS + 3) / 4 * 4; // float keys of the slots beyond shared memory
 __host__ __device__ constexpr size_t es_slab_bytes(bool heap)
 {
-    return static_cast<size_t>(ES_SLOTS) * (32 + 8) + static_cast<size_t>(ES_VERTS) * (32 + 48) +
+    return static_cast<size_t>(ES_SLOTS) * (32 + 8) + static_cast<size_t>(ES_VERTS) * (32 + 48) + static_cast<size_t>(ES_GKEYS) * 4 +
            (heap ? static_cast<size_t>(ES_HEAP_MAX) * (8 + 4) : 0);
 }
 
-constexpr int ES_HCAP = 30; // heap entries of the exact-heap mode kept in shared memory (polyhedron pairs: observed max 34)
+constexpr int ES_HCAP = PK_ES_HCAP; // heap entries of the exact-heap mode kept in shared memory (polyhedron pairs: observed max 34)
 
 // How pop_face finds the closest live face, chosen per pair.  SCAN (pairs with a sphere): float keys, no
 // heap — distances of distinct faces practically never tie.  HEAP (polyhedron pairs): the reference's
@@ -66,7 +76,7 @@ struct alignas(16) EsPopThread
         } heap;
     };
 };
-static_assert(sizeof(EsPopThread) == ES_KEYS * 4, "the heap must fit the key area");
+static_assert(sizeof(EsPopThread) == ES_KEYS * 4 && ES_KEYS % 8 == 4, "the heap must fit the key area; ES_KEYS/4 must be odd");
 struct EsPop
 {
     EsPopThread th[ES_THREADS];
@@ -76,8 +86,7 @@ struct EsSmem
 {
     EsPop pop;
     double f[2][10][ES_THREADS];     // shape views: p xyz, h xyz, q xyzw
-    const double *verts[2][ES_THREADS];
-    const float4 *vf[2][ES_THREADS];
+    uint32_t vert_off[2][ES_THREADS]; // HULL: first vertex in the context's vertex pool
     float hull_r[2][ES_THREADS];
     int kind[2][ES_THREADS];
     uint32_t nverts[2][ES_THREADS];
@@ -92,6 +101,7 @@ struct EsSlab
     unsigned long long *topo; // bytes 0-2 vertices, 3-5 adjacent slots (0xFF = none)
     double *vpos;             // p = pa − pb, padded to 32 bytes
     double *vab;              // pa xyz, pb xyz
+    float *gkey;              // SCAN mode: float keys of slots ≥ ES_KEYS (polytopes past ≈45 iterations)
     double *hd;               // HEAP mode: heap entries ≥ ES_HCAP (distance)
     uint32_t *hf;             // HEAP mode: heap entries ≥ ES_HCAP (slot | creation serial << 8)
     __device__ __forceinline__ EsSlab(unsigned char *base, bool heap)
@@ -105,6 +115,8 @@ struct EsSlab
         base += static_cast<size_t>(ES_VERTS) * 32;
         vab = reinterpret_cast<double *>(base);
         base += static_cast<size_t>(ES_VERTS) * 48;
+        gkey = reinterpret_cast<float *>(base);
+        base += static_cast<size_t>(ES_GKEYS) * 4;
         hd = reinterpret_cast<double *>(base);
         base += static_cast<size_t>(ES_HEAP_MAX) * 8;
         hf = reinterpret_cast<uint32_t *>(base);
@@ -158,27 +170,26 @@ __device__ __forceinline__ int fo4(int f) { return (0x0213 >> (4 * f)) & 0xF; }
 __device__ __forceinline__ void es_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float es_inf() { return __int_as_float(0x7F800000); }
 
-template <class SM> __device__ __forceinline__ void es_put_shape(SM &sm, int which, const ShapeView &v)
+template <class SM> __device__ __forceinline__ void es_put_shape(SM &sm, int which, const ShapeView &v, const BodyArrays &ba)
 {
     const int t = threadIdx.x;
     sm.f[which][0][t] = v.p.x; sm.f[which][1][t] = v.p.y; sm.f[which][2][t] = v.p.z;
     sm.f[which][3][t] = v.h.x; sm.f[which][4][t] = v.h.y; sm.f[which][5][t] = v.h.z;
     sm.f[which][6][t] = v.q.x; sm.f[which][7][t] = v.q.y; sm.f[which][8][t] = v.q.z; sm.f[which][9][t] = v.q.w;
-    sm.verts[which][t] = v.verts;
-    sm.vf[which][t] = v.vf;
+    sm.vert_off[which][t] = static_cast<uint32_t>(v.vf - ba.verts_f);
     sm.hull_r[which][t] = v.hull_r;
     sm.kind[which][t] = v.kind;
     sm.nverts[which][t] = v.nverts;
 }
-template <class SM> __device__ __forceinline__ ShapeView es_get_shape(const SM &sm, int which)
+template <class SM> __device__ __forceinline__ ShapeView es_get_shape(const SM &sm, int which, const BodyArrays &ba)
 {
     const int t = threadIdx.x;
     ShapeView v;
     v.p = {sm.f[which][0][t], sm.f[which][1][t], sm.f[which][2][t]};
     v.h = {sm.f[which][3][t], sm.f[which][4][t], sm.f[which][5][t]};
     v.q = {sm.f[which][6][t], sm.f[which][7][t], sm.f[which][8][t], sm.f[which][9][t]};
-    v.verts = sm.verts[which][t];
-    v.vf = sm.vf[which][t];
+    v.verts = ba.verts + 3ull * sm.vert_off[which][t];
+    v.vf = ba.verts_f + sm.vert_off[which][t];
     v.hull_r = sm.hull_r[which][t];
     v.kind = sm.kind[which][t];
     v.nverts = sm.nverts[which][t];
@@ -356,6 +367,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
     bool active = false, done = false;
     int nverts = 0, iter = 0, hi = 0; // hi: slots [0, hi) have been used by the current polytope
     bool keys_dirty = true;           // the key area does not hold +inf beyond the current polytope
+    int gdirty = ES_SLOTS;            // slab keys [ES_KEYS, gdirty) may hold something else than +inf
     unsigned long long fm0 = 0, fm1 = 0, fm2 = 0; // free slots, 64 per word
     uint32_t out_slot = 0, cur_sidx = 0;
     uint64_t key = 0;
@@ -377,7 +389,10 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
     {
         if constexpr (!HEAP)
         {
-            if (f < ES_KEYS) shm.pop.th[t].key[f] = INF;
+            if (f < ES_KEYS)
+                shm.pop.th[t].key[f] = INF;
+            else
+                sl.gkey[f - ES_KEYS] = INF;
         }
         if (f < 64)
             fm0 |= 1ull << f;
@@ -387,14 +402,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
             fm2 |= 1ull << (f - 128);
     };
     // float key of slot s: shared memory for the first ES_KEYS slots, derived from the slab beyond
-    auto key_of = [&](int s) -> float
-    {
-        if constexpr (!HEAP)
-        {
-            if (s < ES_KEYS) return shm.pop.th[t].key[s];
-        }
-        return is_free(s) ? INF : __double2float_rd(sl.plane[4 * s + 3]);
-    };
+    auto key_of = [&](int s) -> float { return (s < ES_KEYS) ? shm.pop.th[t].key[s] : sl.gkey[s - ES_KEYS]; };
     // slot of a new face.  SCAN: lowest free first (keeps the live polytope dense at the start of the slab
     // and inside the keyed slots).  HEAP: never-used slots first, so that as long as the polytope has
     // created at most ES_SLOTS faces a heap entry's slot equals its serial and "slot free" is the whole
@@ -467,8 +475,8 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                     {
                         ShapeView A = load_shape(bodies, ia);
                         ShapeView B = load_shape(bodies, ib);
-                        es_put_shape(shm, 0, A);
-                        es_put_shape(shm, 1, B);
+                        es_put_shape(shm, 0, A, bodies);
+                        es_put_shape(shm, 1, B, bodies);
                     }
                     d3 pv[4];
 #pragma unroll
@@ -486,6 +494,8 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                         // whose heap occupied the same shared memory
                         const int dirty = keys_dirty ? ES_KEYS : (hi < ES_KEYS ? hi : ES_KEYS);
                         for (int s = 4; s < dirty; ++s) shm.pop.th[t].key[s] = INF;
+                        for (int s = ES_KEYS; s < gdirty; ++s) sl.gkey[s - ES_KEYS] = INF;
+                        gdirty = ES_KEYS;
                         keys_dirty = false;
                     }
                     else
@@ -573,7 +583,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         else
         {
             float m = INF;
-            int cnt = 0;
+            int cnt = 0, second = -1;
             const int hs = hi < ES_KEYS ? hi : ES_KEYS;
             const float4 *kq = reinterpret_cast<const float4 *>(shm.pop.th[t].key);
             for (int s = 0; s < hs; s += 4) // slots in [hs, s+4) hold +inf: they never win and never count
@@ -590,38 +600,68 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                         cnt = 1;
                     }
                     else if (kk[u] == m)
+                    {
+                        if (cnt == 1) second = s + u;
                         ++cnt;
+                    }
                 }
             }
-            for (int s = ES_KEYS; s < hi; ++s) // only polytopes past 46 iterations
+            if (hi > ES_KEYS) // only polytopes past ≈45 iterations: same scan over the keys kept in the slab
             {
-                const float k = key_of(s);
-                if (k < m)
+                const float4 *gq = reinterpret_cast<const float4 *>(sl.gkey);
+                for (int s = ES_KEYS; s < hi; s += 4)
                 {
-                    m = k;
-                    min_face = s;
-                    cnt = 1;
+                    const float4 k4 = gq[(s - ES_KEYS) >> 2];
+                    const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                    {
+                        if (kk[u] < m)
+                        {
+                            m = kk[u];
+                            min_face = s + u;
+                            cnt = 1;
+                        }
+                        else if (kk[u] == m)
+                        {
+                            if (cnt == 1) second = s + u;
+                            ++cnt;
+                        }
+                    }
                 }
-                else if (k == m)
-                    ++cnt;
             }
             if (min_face >= 0 && cnt > 1)
             {
-                // several live faces share the minimal float key: compare the exact distances
+                // several live faces share the minimal float key (mirror-image faces of sphere–sphere polytopes
+                // differ in the last bits only): compare the exact distances
                 double best = sl.plane[4 * min_face + 3];
                 bool tie = false;
-                for (int s = min_face + 1; s < hi; ++s)
+                if (cnt == 2)
                 {
-                    if (key_of(s) != m) continue;
-                    const double d = sl.plane[4 * s + 3];
+                    const double d = sl.plane[4 * second + 3];
                     if (d < best)
                     {
                         best = d;
-                        min_face = s;
-                        tie = false;
+                        min_face = second;
                     }
                     else if (d == best)
                         tie = true;
+                }
+                else
+                {
+                    for (int s = min_face + 1; s < hi; ++s)
+                    {
+                        if (key_of(s) != m) continue;
+                        const double d = sl.plane[4 * s + 3];
+                        if (d < best)
+                        {
+                            best = d;
+                            min_face = s;
+                            tie = false;
+                        }
+                        else if (d == best)
+                            tie = true;
+                    }
                 }
                 if (tie)
                 {
@@ -702,11 +742,11 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         if (!finished)
         {
             {
-                const ShapeView A = es_get_shape(shm, 0);
+                const ShapeView A = es_get_shape(shm, 0, bodies);
                 sp.pa = support(A, mn);
             }
             {
-                const ShapeView B = es_get_shape(shm, 1);
+                const ShapeView B = es_get_shape(shm, 1, bodies);
                 sp.pb = support(B, -mn);
             }
         }
@@ -845,7 +885,13 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
             }
             else
             {
-                if (slot < ES_KEYS) shm.pop.th[t].key[slot] = __double2float_rd(dist);
+                if (slot < ES_KEYS)
+                    shm.pop.th[t].key[slot] = __double2float_rd(dist);
+                else
+                {
+                    sl.gkey[slot - ES_KEYS] = __double2float_rd(dist);
+                    if (slot >= gdirty) gdirty = slot + 1;
+                }
             }
             ++nfaces;
             shm.hz[e][t] = hc | (static_cast<uint32_t>(slot) << 24);

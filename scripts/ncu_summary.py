@@ -50,8 +50,15 @@ def launches(path, out):
 
 
 def kernel(rep, kern, out, lib):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    # first launch whose (template-argument-normalised) name contains `kern`, e.g. "epa_scan_kernel<0>"
+    base = kern.split("<")[0]
+    allraw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "-k", "regex:" + base], capture_output=True, text=True).stdout
+    names = [r[4] for r in list(csv.reader(io.StringIO(allraw)))[2:] if len(r) > 4]
+    norm = [re.sub(r"\((?:bool|int)\)", "", n).replace("pk::", "") for n in names]
+    skip = next(i for i, n in enumerate(norm) if kern in n)
+    sel = ["-k", "regex:" + base, "--launch-skip", str(skip), "-c", "1"]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rr[0], rr[1], rr[2]
     lines = [f"# ncu --set full: `{vals[4].split('(')[0]}`  ({os.path.basename(rep)})\n", f"grid {vals[8]} block {vals[7]}\n", "| metric | value | unit |\n|---|---:|---|\n"]
@@ -70,10 +77,11 @@ def kernel(rep, kern, out, lib):
     lines.append("\nStall reasons (PC samples): " + ", ".join(f"{n} {100 * v / tot:.1f} %" for v, n in sorted(stalls, reverse=True)[:6]) + "\n")
     # per-line attribution
     with tempfile.TemporaryDirectory() as td:
-        subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=td, capture_output=True)
+        subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=td, capture_output=True)
         cub = [os.path.join(td, f) for f in os.listdir(td) if f.endswith(".cubin")]
         dis = subprocess.run(["nvdisasm", "-g", "-c"] + cub, capture_output=True, text=True).stdout.split("\n")
-    start = next((i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l and l.endswith(":")), None)
+    mangled = re.sub(r"<(\d)>", lambda m: "ILb%sE" % m.group(1), kern)  # epa_scan_kernel<0> → epa_scan_kernelILb0E
+    start = next((i for i, l in enumerate(dis) if l.startswith(".text.") and mangled in l and l.endswith(":")), None)
     off2line, cur = {}, None
     if start is not None:
         for l in dis[start + 1:]:
@@ -87,12 +95,16 @@ def kernel(rep, kern, out, lib):
             if m and cur:
                 off2line[int(m.group(1), 16)] = cur
     sr = list(csv.reader(io.StringIO(src)))
+    hi = next(i for i, r in enumerate(sr) if r and r[0] == "Address")
+    sr = sr[hi - 1:]  # [kernel name row, header, instructions ...] of the first matching launch
     sh = sr[1]
     ia, isamp, iinst, ithr, ilsb = sh.index("Address"), sh.index("# Samples"), sh.index("Instructions Executed"), sh.index("Thread Instructions Executed"), sh.index("stall_long_sb")
     base = int(sr[2][ia], 16)
     agg = collections.defaultdict(lambda: [0, 0, 0, 0])
     t = [0, 0, 0, 0]
     for r in sr[2:]:
+        if not r or not r[ia].startswith("0x"):
+            break  # next launch
         key = off2line.get(int(r[ia], 16) - base, ("?", 0))
         v = [int(r[isamp]), int(r[iinst]), int(r[ithr]), int(r[ilsb])]
         for k in range(4):
