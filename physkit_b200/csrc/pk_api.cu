@@ -100,6 +100,9 @@ struct pk_ctx
 {
     pk_config cfg{};
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // pk_collide: pair keys go to the host while the narrowphase runs
+    cudaEvent_t ev_sorted = nullptr, ev_pairs_copied = nullptr;
+    bool want_host_results = false, pairs_in_flight = false;
     std::string last_error;
     int sm_count = 0;
 
@@ -363,6 +366,18 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
     return PK_OK;
 }
 
+int ensure_host_pairs(pk_ctx *ctx, uint64_t n)
+{
+    if (n <= ctx->h_pairs_cap) return PK_OK;
+    if (ctx->h_pairs) cudaFreeHost(ctx->h_pairs);
+    ctx->h_pairs = nullptr;
+    ctx->h_pairs_cap = 0;
+    size_t cap = std::min<size_t>(ctx->cfg.max_pairs, std::max<size_t>(n * 5 / 4, 1024));
+    PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pairs), cap * sizeof(uint64_t), cudaHostAllocDefault));
+    ctx->h_pairs_cap = cap;
+    return PK_OK;
+}
+
 int read_counters(pk_ctx *ctx)
 {
     PK_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, C_COUNT * sizeof(unsigned long long),
@@ -417,6 +432,13 @@ int pk_destroy(pk_ctx *ctx)
     if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream)
+    {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
+    if (ctx->ev_pairs_copied) cudaEventDestroy(ctx->ev_pairs_copied);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PK_OK;
@@ -452,6 +474,9 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(PK_E_NO_DEVICE);
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(PK_E_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(PK_E_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming) != cudaSuccess) return fail(PK_E_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->ev_pairs_copied, cudaEventDisableTiming) != cudaSuccess) return fail(PK_E_CUDA);
     for (auto &e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return fail(PK_E_CUDA);
 
@@ -722,6 +747,13 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
 {
     if (!ctx) return PK_E_INVALID;
     cudaSetDevice(ctx->cfg.device);
+    if (ctx->pairs_in_flight)
+    {
+        // a previous pk_collide failed between the pair sort and pk_fetch_results: let its copy finish
+        // before the pair buffers are written again
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_pairs_copied, 0);
+        ctx->pairs_in_flight = false;
+    }
     PK_TRY(upload_shapes(ctx));
     ctx->have_results = false;
     ctx->fetched = false;
@@ -810,6 +842,18 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         for (int k = ST_BODY_SORT; k <= ST_PAIR_SORT; ++k) cudaEventRecord(ctx->ev[k], s);
     }
     ctx->d_pairs_sorted = ctx->d_pkeys[pair_buf];
+    ctx->pairs_in_flight = false;
+    if (ctx->want_host_results && npairs)
+    {
+        // pk_collide: the sorted pair keys are final here; ship them to the host on a second stream while
+        // the narrowphase (which only reads them) runs
+        PK_TRY(ensure_host_pairs(ctx, npairs));
+        cudaEventRecord(ctx->ev_sorted, s);
+        cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sorted, 0);
+        PK_CUDA(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs_sorted, npairs * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        cudaEventRecord(ctx->ev_pairs_copied, ctx->copy_stream);
+        ctx->pairs_in_flight = true;
+    }
     PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true));
     PK_TRY(read_counters(ctx));
     uint64_t hits = ctx->h_counters[C_HITS];
@@ -881,14 +925,7 @@ int pk_fetch_results(pk_ctx *ctx)
     if (!ctx->have_results) return PK_E_STATE;
     cudaSetDevice(ctx->cfg.device);
     cudaEventRecord(ctx->ev[ST_FETCH], ctx->stream);
-    if (ctx->num_pairs > ctx->h_pairs_cap)
-    {
-        if (ctx->h_pairs) cudaFreeHost(ctx->h_pairs);
-        ctx->h_pairs = nullptr;
-        size_t cap = std::min<size_t>(ctx->cfg.max_pairs, std::max<size_t>(ctx->num_pairs * 5 / 4, 1024));
-        PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pairs), cap * sizeof(uint64_t), cudaHostAllocDefault));
-        ctx->h_pairs_cap = cap;
-    }
+    PK_TRY(ensure_host_pairs(ctx, ctx->num_pairs));
     if (ctx->num_contacts > ctx->h_contacts_cap)
     {
         if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
@@ -897,9 +934,12 @@ int pk_fetch_results(pk_ctx *ctx)
         PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_contacts), cap * sizeof(pk_contact), cudaHostAllocDefault));
         ctx->h_contacts_cap = cap;
     }
-    if (ctx->num_pairs)
+    if (ctx->pairs_in_flight)
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_pairs_copied, 0); // already on their way since the pair sort
+    else if (ctx->num_pairs)
         PK_CUDA(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs_sorted, ctx->num_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                 ctx->stream));
+    ctx->pairs_in_flight = false;
     if (ctx->num_contacts)
         PK_CUDA(cudaMemcpyAsync(ctx->h_contacts, ctx->d_contacts_final, ctx->num_contacts * sizeof(pk_contact),
                                 cudaMemcpyDeviceToHost, ctx->stream));
@@ -912,7 +952,10 @@ int pk_fetch_results(pk_ctx *ctx)
 
 int pk_collide(pk_ctx *ctx, pk_step_result *out)
 {
+    if (!ctx) return PK_E_INVALID;
+    ctx->want_host_results = true;
     int s = pk_collide_resident(ctx, out);
+    ctx->want_host_results = false;
     if (s != PK_OK && s != PK_E_EPA_OVERFLOW) return s;
     int f = pk_fetch_results(ctx);
     return f != PK_OK ? f : s;

@@ -318,7 +318,7 @@ __device__ __forceinline__ uint32_t es_heap_pop(const EsHeapRef &h, int &size)
 #define PK_ES_MIN_BLOCKS 4
 #endif
 #ifndef PK_ES_FETCH_MIN
-#define PK_ES_FETCH_MIN 6
+#define PK_ES_FETCH_MIN 12
 #endif
 
 // The hit list is grouped by cost class (order[]: sphere–sphere, sphere–polyhedron, polyhedron–polyhedron);
