@@ -160,6 +160,11 @@ int pk_stored_bounds(pk_ctx *ctx, double *out6, uint32_t first, uint32_t count);
 int pk_stage_times_get(pk_ctx *ctx, pk_stage_times *out);
 /* CUDA stream of the ctx as a void* (cudaStream_t) so a host can order its own work after it. */
 int pk_stream(pk_ctx *ctx, void **stream);
+/* Diagnostic: the library divides the three components of a vector by one norm through a shared, correctly
+ * rounded reciprocal (Markstein's division) instead of three IEEE divisions; results must be bit-identical
+ * (reference: Eigen normalized(), lin_alg.h:232-240).  Draws `samples` operand pairs on the device — random
+ * ones and ones constructed next to exact quotients — and reports how many quotients differ from `/`. */
+int pk_selftest_division(pk_ctx *ctx, uint64_t seed, uint64_t samples, uint64_t *mismatches);
 
 /* ---- narrowphase only: gjk_epa over an explicit pair list (BASELINE config C4) ----------------
  * pair_a/pair_b index the uploaded bodies; out[k] / hit[k] are written for every k (host pointers).

@@ -73,7 +73,7 @@ class _StageTimes(C.Structure):
 _lib = None
 
 EXPORTS = [
-    "pk_abi_version", "pk_create", "pk_destroy", "pk_strerror", "pk_last_error",
+    "pk_abi_version", "pk_selftest_division", "pk_create", "pk_destroy", "pk_strerror", "pk_last_error",
     "pk_shape_box", "pk_shape_sphere", "pk_shape_hull", "pk_shape_aabb", "pk_shapes_bulk",
     "pk_bodies_resize", "pk_bodies_upload", "pk_bodies_update_pose",
     "pk_collide_resident", "pk_fetch_results", "pk_collide", "pk_pairs", "pk_contacts",
@@ -101,6 +101,7 @@ def load_library():
     L.pk_last_error.restype = C.c_char_p
     L.pk_last_error.argtypes = [vp]
     L.pk_create.argtypes = [vp, vp]
+    L.pk_selftest_division.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     L.pk_destroy.argtypes = [vp]
     L.pk_shape_box.argtypes = [vp, vp, vp]
     L.pk_shape_sphere.argtypes = [vp, C.c_double, vp]
@@ -309,6 +310,11 @@ class Context:
         d = {st.name[k].decode(): float(st.ms[k]) for k in range(NUM_STAGES)}
         self.epa_fallback = int(st.epa_fallback)
         return d, int(st.launches)
+
+    def selftest_division(self, seed, samples):
+        bad = C.c_uint64()
+        self._check(self.L.pk_selftest_division(self.h, C.c_uint64(seed), C.c_uint64(samples), C.byref(bad)))
+        return int(bad.value)
 
     def stream(self):
         s = C.c_void_p()

@@ -176,6 +176,61 @@ struct pk_ctx
 namespace
 {
 
+// Self-test of pk_div_by_rcp (pk_common.cuh) against IEEE division: every thread draws `per_thread` operand
+// pairs from a counter-based generator and counts quotients that differ in any bit.  Families of operands:
+// random mantissas; numerators constructed next to an exact multiple of the divisor (quotients next to a
+// representable value or next to a rounding boundary); divisors with all-ones / all-zero mantissas.
+__device__ __forceinline__ uint64_t st_mix(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void division_selftest_kernel(uint64_t seed, uint32_t per_thread, unsigned long long *mismatches)
+{
+    const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    unsigned long long bad = 0;
+    for (uint32_t i = 0; i < per_thread; ++i)
+    {
+        const uint64_t u = st_mix(seed ^ (tid * 0x100000001B3ull + i));
+        const uint64_t w = st_mix(u);
+        const uint64_t sel = st_mix(w);
+        // divisor: exponent within ±60 of 1.0, mantissa random / all ones / all zeros / one bit
+        uint64_t sm = u & 0xFFFFFFFFFFFFFull;
+        switch (sel & 7u)
+        {
+        case 0: sm = 0xFFFFFFFFFFFFFull; break;
+        case 1: sm = 0; break;
+        case 2: sm = 1ull << (sel >> 8) % 52; break;
+        case 3: sm = 0xFFFFFFFFFFFFFull ^ (1ull << (sel >> 8) % 52); break;
+        default: break;
+        }
+        const uint64_t se = 1023 - 60 + (u >> 52) % 121;
+        const double s = __longlong_as_double(static_cast<long long>((se << 52) | sm));
+        double a;
+        if ((sel >> 3) & 1u)
+        {
+            // a = RN(q·s) moved by −2..+2 ulp: quotient next to the representable q
+            const uint64_t qe = 1023 - 60 + (w >> 52) % 121;
+            const double q = __longlong_as_double(static_cast<long long>((qe << 52) | (w & 0xFFFFFFFFFFFFFull)));
+            const double p = __dmul_rn(q, s);
+            const long long d = static_cast<long long>((sel >> 16) % 5) - 2;
+            a = __longlong_as_double(__double_as_longlong(p) + d);
+        }
+        else
+        {
+            const uint64_t ae = 1023 - 60 + (w >> 52) % 121;
+            a = __longlong_as_double(static_cast<long long>((ae << 52) | (w & 0xFFFFFFFFFFFFFull)));
+        }
+        if ((sel >> 4) & 1u) a = -a;
+        const double want = a / s;
+        const double got = pk_div_by_rcp(a, s, __drcp_rn(s));
+        if (__double_as_longlong(want) != __double_as_longlong(got)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 #define PK_CUDA(call)                                                                                     \
     do                                                                                                    \
     {                                                                                                     \
@@ -1020,14 +1075,25 @@ int pk_stage_times_get(pk_ctx *ctx, pk_stage_times *out)
     out->epa_fallback = static_cast<uint32_t>(ctx->h_counters ? ctx->h_counters[C_EPA_FALLBACK + 1] : 0);
 #ifdef PK_ES_REASONS
     if (ctx->h_counters)
-        fprintf(stderr, "[epa fallback] total %llu: pad %llu tie %llu capacity %llu improper %llu; iterations thrown away %llu\n",
+        fprintf(stderr, "[epa fallback] to epa_kernel %llu; handed back by either instance: pad %llu tie %llu capacity %llu improper %llu; SCAN iterations thrown away %llu\n",
                 static_cast<unsigned long long>(out->epa_fallback), ctx->h_counters[C_EPA_REASONS], ctx->h_counters[C_EPA_REASONS + 1],
                 ctx->h_counters[C_EPA_REASONS + 2], ctx->h_counters[C_EPA_REASONS + 3], ctx->h_counters[C_EPA_REASONS + 4]);
-    if (ctx->h_counters)
-        fprintf(stderr, "[epa fallback] SCAN handed back %llu; HEAP handed back: pad %llu capacity %llu improper %llu\n",
-                ctx->h_counters[C_EPA_FALLBACK], ctx->h_counters[C_EPA_REASONS + 6], ctx->h_counters[C_EPA_REASONS + 8],
-                ctx->h_counters[C_EPA_REASONS + 9]);
 #endif
+    return PK_OK;
+}
+
+int pk_selftest_division(pk_ctx *ctx, uint64_t seed, uint64_t samples, uint64_t *mismatches)
+{
+    if (!ctx || !mismatches) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    const uint32_t threads = 256, blocks = static_cast<uint32_t>(ctx->sm_count) * 16;
+    const uint32_t per_thread = static_cast<uint32_t>(std::max<uint64_t>(1, samples / (static_cast<uint64_t>(threads) * blocks)));
+    PK_CUDA(cudaMemsetAsync(ctx->d_counters + C_COUNT - 1, 0, sizeof(unsigned long long), ctx->stream));
+    division_selftest_kernel<<<blocks, threads, 0, ctx->stream>>>(seed, per_thread, ctx->d_counters + C_COUNT - 1);
+    unsigned long long h = 0;
+    PK_CUDA(cudaMemcpyAsync(&h, ctx->d_counters + C_COUNT - 1, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *mismatches = h;
     return PK_OK;
 }
 

@@ -434,7 +434,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
             unsigned long long i = atomicAdd(fallback_count, 1ull);
             if (i < fb_capacity) fallback_list[i] = cur_sidx; // one word: publication needs no fence
 #ifdef PK_ES_REASONS
-            atomicAdd(fallback_count - (HEAP ? 1 : 0) + 9 + fb + (HEAP ? 6 : 0), 1ull); // debug build only
+            atomicAdd(fallback_count - (HEAP ? 1 : 0) + 9 + fb, 1ull); // debug build only: C_EPA_REASONS + reason
             if (!HEAP) atomicAdd(fallback_count + 14, static_cast<unsigned long long>(iter));
 #endif
             fb = 0;
