@@ -9,7 +9,6 @@
 #include "pk_broadphase.cuh"
 #include "pk_common.cuh"
 #include "pk_narrowphase.cuh"
-#include "pk_epa_group.cuh"
 #include "pk_epa_scan.cuh"
 #include "pk_sort.cuh"
 
@@ -24,33 +23,8 @@
 
 using namespace pk;
 
-// EPA implementation: 2 = scan kernel (pk_epa_scan.cuh) + epa_kernel for its fallback list (default),
-// 1 = group kernel (pk_epa_group.cuh, measured slower: kept as an experiment), 0 = epa_kernel only
-#ifndef PK_EPA_IMPL
-#ifdef PK_EPA_LEGACY_ONLY
-#define PK_EPA_IMPL 0
-#else
-#define PK_EPA_IMPL 2
-#endif
-#endif
-// group EPA configuration: lanes per pair, shared-memory capacities (faces, heap entries, vertices)
-#ifndef PK_EPA_G
-#define PK_EPA_G 4
-#endif
-#ifndef PK_EPA_FS
-#define PK_EPA_FS 64
-#endif
-#ifndef PK_EPA_HS
-#define PK_EPA_HS 126
-#endif
-#ifndef PK_EPA_VS
-#define PK_EPA_VS 36
-#endif
-using EpaGroupSpill = EgSpillLayout<PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>;
-constexpr int EG_GROUPS_PER_BLOCK = eg_groups_per_block<PK_EPA_G, PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>();
-constexpr size_t EpaGroupSmemBytes = sizeof(EgSmem<PK_EPA_G, PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>) * EG_GROUPS_PER_BLOCK;
-static_assert(EpaGroupSmemBytes <= 232448, "group EPA shared memory exceeds the 227 KB per-block limit");
-
+// EPA implementation: epa_scan_kernel (pk_epa_scan.cuh) + epa_kernel for what it hands back (default);
+// -DPK_EPA_LEGACY_ONLY builds the thread-per-pair epa_kernel alone (the r1 baseline, kept for A/B runs)
 namespace
 {
 
@@ -154,7 +128,6 @@ struct pk_ctx
     unsigned char *d_slabs = nullptr;
     unsigned char *d_epa_spill = nullptr;
     uint32_t *d_epa_fallback = nullptr, *d_epa_fallback2 = nullptr;
-    uint32_t epa_group_blocks = 0;
     uint32_t epa_scan_blocks = 0;
     uint32_t epa_blocks = 0;
     uint32_t gjk_blocks = 0;
@@ -371,32 +344,17 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
         epa_order_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
                                                                      ctx->d_counters + C_CLASS_COUNT, ctx->d_counters + C_CLASS_FILL,
                                                                      ctx->d_epa_order);
-#if PK_EPA_IMPL == 0
+#ifdef PK_EPA_LEGACY_ONLY
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs, ctx->d_counters + C_EPA_CURSOR,
             ctx->d_counters + C_VALID);
         ctx->launches += 2;
 #else
-        // fast kernel first; what it cannot take (exact distance ties, padded simplices, improper horizons,
-        // capacity) lands in d_epa_fallback and is done by epa_kernel, which restates the reference's heap
-#if PK_EPA_IMPL == 1
-        epa_group_kernel<PK_EPA_G, PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>
-            <<<ctx->epa_group_blocks, EG_GROUPS_PER_BLOCK * PK_EPA_G, EpaGroupSmemBytes, ctx->stream>>>(
-                body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
-                ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
-                ctx->d_counters + C_EPA_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
-                ctx->d_counters + C_EPA_FALLBACK);
-        epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
-            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK, ctx->max_contacts,
-            ctx->d_out_index, ctx->d_epa_fallback, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
-            ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID);
-        ctx->launches += 3;
-#else
         // Pairs with a sphere: heap-free pop (SCAN instance).  What it hands back (exact distance ties that
         // only the heap's history can break) goes first into the HEAP instance, which restates the heap and
         // then does the polyhedron pairs; what that one hands back (padded simplices, improper horizons,
-        // polytopes past 255 faces: a handful) is left to epa_kernel.
+        // polytopes past 768 faces: a handful) is left to epa_kernel.
         epa_scan_kernel<false><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
@@ -413,7 +371,6 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
             ctx->d_out_index, ctx->d_epa_fallback2, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
             ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID);
         ctx->launches += 4;
-#endif
 #endif
     }
     if (timed) cudaEventRecord(ctx->ev[ST_COMPACT], ctx->stream);
@@ -599,20 +556,8 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
         uint64_t threads = std::min(want_threads, std::max<uint64_t>(need_threads, EPA_THREADS));
         ctx->epa_blocks = static_cast<uint32_t>(threads / EPA_THREADS);
         A(ctx->d_slabs, threads * EPA_SLAB_BYTES);
-#if PK_EPA_IMPL == 1
-        // group EPA: one persistent block per SM (its shared memory holds EG_GROUPS_PER_BLOCK polytopes)
-        if (cudaFuncSetAttribute(epa_group_kernel<PK_EPA_G, PK_EPA_FS, PK_EPA_HS, PK_EPA_VS>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EpaGroupSmemBytes)) != cudaSuccess)
-        {
-            ctx->last_error = "epa_group_kernel: shared-memory carve-out refused";
-            return fail(PK_E_CUDA);
-        }
-        uint64_t want_blocks = static_cast<uint64_t>(ctx->sm_count);
-        uint64_t need_blocks = (nc + EG_GROUPS_PER_BLOCK - 1) / EG_GROUPS_PER_BLOCK;
-        ctx->epa_group_blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min(want_blocks, need_blocks)));
-        A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_group_blocks) * EG_GROUPS_PER_BLOCK * EpaGroupSpill::BYTES);
-#elif PK_EPA_IMPL == 2
-        // scan EPA: 48 KB of shared memory per 64-thread block, as many blocks per SM as the carve-out allows
+#ifndef PK_EPA_LEGACY_ONLY
+        // epa_scan_kernel: 41 KB of shared memory per 64-thread block, as many blocks per SM as fit
         cudaFuncSetAttribute(epa_scan_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(epa_scan_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int es_per_sm = 0;
