@@ -65,7 +65,8 @@ enum Counter
     C_EPA_SCAN_CURSOR = C_EPA_FALLBACK + 3, // [2] work cursors of those two launches
     C_EPA_FB_CURSOR = C_EPA_SCAN_CURSOR + 3, // work cursor of epa_kernel on the second fallback list
     C_EPA_REASONS = C_EPA_FALLBACK + 10, // [6] debug builds (PK_ES_REASONS)
-    C_COUNT = 32
+    C_GJK_CLASS = 32, // [4] GJK prefilter survivors per shape-kind class
+    C_COUNT = 40
 };
 
 } // namespace
@@ -323,9 +324,9 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
     if (npairs)
     {
         gjk_prefilter_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit,
-                                                                          ctx->d_gjk_work, ctx->d_counters + C_GJK_CURSOR);
+                                                                          ctx->d_gjk_work, ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS);
         gjk_kernel<<<div_up(npairs, PK_GJK_THREADS), PK_GJK_THREADS, 0, ctx->stream>>>(
-            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_gjk_work, ctx->d_counters + C_GJK_CURSOR, ctx->d_hit, ctx->d_simplices,
+            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_gjk_work, ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, ctx->d_hit, ctx->d_simplices,
             ctx->d_counters + C_HITS, ctx->max_contacts, ctx->d_counters + C_CLASS_COUNT);
         ctx->launches += 2;
     }
@@ -538,7 +539,7 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     A(ctx->d_valid, nc + 16);
     A(ctx->d_valid_index, nc);
     A(ctx->d_epa_order, nc);
-    A(ctx->d_gjk_work, np);
+    A(ctx->d_gjk_work, 4 * np); // one survivor list per shape-kind class
     // persistent EPA grid: enough resident threads to fill the machine, never more than the work
     {
         int gjk_per_sm = 0;
@@ -776,7 +777,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
     const uint32_t *d_world = (ctx->cfg.num_worlds > 1 && ctx->have_world) ? ctx->d_world : nullptr;
 
     cudaEventRecord(ctx->ev[ST_BOUNDS], s);
-    scene_reset_kernel<<<1, 32, 0, s>>>(ctx->d_scene, ctx->d_counters, C_COUNT);
+    scene_reset_kernel<<<1, 64, 0, s>>>(ctx->d_scene, ctx->d_counters, C_COUNT);
     ctx->launches += 1;
     if (n)
     {
@@ -1061,7 +1062,7 @@ int pk_gjk_epa_batch_device(pk_ctx *ctx, const uint32_t *d_a, const uint32_t *d_
     cudaStream_t s = ctx->stream;
     ctx->launches = 0;
     cudaEventRecord(ctx->ev[ST_BOUNDS], s);
-    scene_reset_kernel<<<1, 32, 0, s>>>(ctx->d_scene, ctx->d_counters, C_COUNT);
+    scene_reset_kernel<<<1, 64, 0, s>>>(ctx->d_scene, ctx->d_counters, C_COUNT);
     PK_TRY(run_narrowphase(ctx, nullptr, d_a, d_b, n, true));
     if (n)
         expand_contacts_kernel<<<div_up(n, 256), 256, 0, s>>>(ctx->d_hit, ctx->d_out_index, ctx->d_valid, ctx->d_contacts[0],

@@ -262,19 +262,25 @@ __device__ __forceinline__ void load_pair(const uint64_t *__restrict__ keys, con
 // hit = 0 and never reach the divergent part.  All lanes do identical work, so this kernel runs at full
 // lane efficiency; survivors are appended to a work list and redone from scratch by gjk_kernel (the
 // two redundant supports cost less than carrying 120 bytes of state per survivor through HBM).
+// Survivors are listed per shape-kind class (bit 0: A is a sphere, bit 1: B is a sphere) so that the
+// lanes of a gjk_kernel warp run the same support code: with the pair list in key order a warp held a
+// random mix of sphere and box supports and executed both paths for every call.
 __global__ void __launch_bounds__(128)
 gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
                      const uint32_t *__restrict__ pair_b, uint64_t npairs, uint8_t *__restrict__ hit,
-                     uint32_t *__restrict__ work, unsigned long long *__restrict__ work_count)
+                     uint32_t *__restrict__ work /*[4][work_stride]*/, uint64_t work_stride,
+                     unsigned long long *__restrict__ work_count /*[4]*/)
 {
     const uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     bool survive = false;
+    uint32_t cls = 0;
     if (k < npairs)
     {
         uint32_t ia, ib;
         load_pair(keys, pair_a, pair_b, k, ia, ib);
         ShapeView A = load_shape(bodies, ia);
         ShapeView B = load_shape(bodies, ib);
+        cls = (A.kind == KIND_SPHERE ? 1u : 0u) | (B.kind == KIND_SPHERE ? 2u : 0u);
         d3 p0 = P(minkowski_support(A, B, d3{1.0, 0.0, 0.0}));
         if (sqnorm(p0) < 1e-12)
             survive = true; // origin hit on the first point: full path decides (collision.cpp:174)
@@ -286,14 +292,16 @@ gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const
         }
         if (!survive) hit[k] = 0;
     }
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, survive);
-    if (m)
+    // one atomic per (warp, class); dead lanes take a class of their own
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, survive ? cls : 4u);
+    if (survive)
     {
         const int lane = threadIdx.x & 31;
+        const int leader = __ffs(peers) - 1;
         unsigned long long base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(work_count, static_cast<unsigned long long>(__popc(m)));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-        if (survive) work[base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint32_t>(k);
+        if (lane == leader) base = atomicAdd(work_count + cls, static_cast<unsigned long long>(__popc(peers)));
+        base = __shfl_sync(peers, base, leader);
+        work[cls * work_stride + base + __popc(peers & ((1u << lane) - 1u))] = static_cast<uint32_t>(k);
     }
 }
 
@@ -302,14 +310,16 @@ gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const
 // path — two gathered body loads — then sits on the critical path of every round.)
 __global__ void __launch_bounds__(PK_GJK_THREADS, PK_GJK_MIN_BLOCKS)
 gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
-           const uint32_t *__restrict__ pair_b, const uint32_t *__restrict__ work,
-           const unsigned long long *__restrict__ work_count, uint8_t *__restrict__ hit,
+           const uint32_t *__restrict__ pair_b, const uint32_t *__restrict__ work, uint64_t work_stride,
+           const unsigned long long *__restrict__ work_count /*[4]*/, uint8_t *__restrict__ hit,
            SimplexRec *__restrict__ simplices, unsigned long long *__restrict__ hit_count, uint64_t hit_capacity,
            unsigned long long *__restrict__ class_count /*[3]*/)
 {
-    const uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (w >= *work_count) return;
-    const uint64_t k = work[w];
+    uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    int c = 0; // class lists back to back: thread w works on entry w of their concatenation
+    while (c < 4 && w >= work_count[c]) w -= work_count[c++];
+    if (c == 4) return;
+    const uint64_t k = work[c * work_stride + w];
     uint32_t ia, ib;
     load_pair(keys, pair_a, pair_b, k, ia, ib);
     ShapeView A = load_shape(bodies, ia);
@@ -333,8 +343,12 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                     d[2] = make_double2(s.pt[i].pb.y, s.pt[i].pb.z);
                 }
             }
-            // EPA cost class: smooth (sphere) supports need many more EPA iterations than polyhedra
-            const uint32_t cls = (A.kind == KIND_SPHERE ? 1u : 0u) + (B.kind == KIND_SPHERE ? 1u : 0u);
+            // EPA cost class = number of "smooth" shapes of the pair: spheres and hulls with many vertices
+            // need many more EPA iterations than boxes, and their face distances practically never tie
+            // (epa_scan_kernel: classes 1-2 heap-free pop, class 0 exact heap)
+            const bool smooth_a = A.kind == KIND_SPHERE || (A.kind == KIND_HULL && A.nverts > HULL_PREFILTER_MIN);
+            const bool smooth_b = B.kind == KIND_SPHERE || (B.kind == KIND_HULL && B.nverts > HULL_PREFILTER_MIN);
+            const uint32_t cls = (smooth_a ? 1u : 0u) + (smooth_b ? 1u : 0u);
             {
                 const unsigned peers = __match_any_sync(__activemask(), cls);
                 if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(class_count + cls, static_cast<unsigned long long>(__popc(peers)));
