@@ -87,6 +87,15 @@ typedef struct pk_contact
     double depth;
 } pk_contact;
 
+/* contact_point (collision_phases.h:75-88) minus the fields pk_contact already has: the witness points in
+ * the bodies' own frames, local = orientation.conjugate() * (world - pos) (core/particle.h:107-108).  This
+ * is what narrow_phase::calculate keeps in its manifolds. */
+typedef struct pk_contact_point
+{
+    double local_a[3];
+    double local_b[3];
+} pk_contact_point;
+
 typedef struct pk_step_result
 {
     uint64_t num_pairs;      /* candidate pairs produced by the broadphase (this shard) */
@@ -153,6 +162,10 @@ int pk_collide(pk_ctx *ctx, pk_step_result *out);
 int pk_pairs(pk_ctx *ctx, const uint64_t **keys, uint64_t *n);
 int pk_contacts(pk_ctx *ctx, const pk_contact **recs, uint64_t *n);
 /* Device-side views for a caller that exchanges results itself (NCCL all-gather of contacts). */
+/* Body-local witness points of the contacts of the last step, record k belonging to pk_contacts()[k]
+ * (narrow_phase::calculate → contact_point, collision_phases.h:257-263).  Computed on the device on request
+ * from the poses of that step; the host pointer stays valid until the next pk_collide*. */
+int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n);
 int pk_pairs_device(pk_ctx *ctx, const void **dptr, uint64_t *n);
 int pk_contacts_device(pk_ctx *ctx, const void **dptr, uint64_t *n);
 /* Stored (fat) boxes of the broadphase, [count][6] = min xyz, max xyz (dynamic_bvh::bounds, bvh.h:452-456). */

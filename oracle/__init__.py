@@ -61,6 +61,7 @@ def lib():
         L.pko_support.argtypes = [vp, vp, vp, vp, u32, vp, vp]
         L.pko_gjk_epa_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp, i32]
         L.pko_gjk_epa_pairs.restype = u64
+        L.pko_contact_points.argtypes = [vp, vp, vp, vp, vp, u64, vp]
         L.pko_bvh_create.restype = vp
         L.pko_bvh_destroy.argtypes = [vp]
         L.pko_bvh_add.argtypes = [vp, u32, vp]
@@ -193,6 +194,18 @@ def gjk_epa_pairs(shapes, pos, quat, shape_id, pair_a, pair_b, stats=False, nthr
         _p(t.tab), _p(t.verts), _p(pos), _p(quat), _p(sid), _p(pa), _p(pb), n, _p(out), _p(hit), _p(st), int(nthreads)
     )
     return hit, out, st
+
+
+def contact_points(pos, quat, pair_a, pair_b, contacts10):
+    """contact_point (collision_phases.h:78-82): witness points of every contact in body-local frames → [n,6]."""
+    pos = _f64(pos, (-1, 3))
+    quat = _f64(quat, (-1, 4))
+    pa = np.ascontiguousarray(pair_a, dtype=np.uint32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.uint32)
+    c = _f64(contacts10, (-1, 10))
+    out = np.empty((len(pa), 6))
+    lib().pko_contact_points(_p(pos), _p(quat), _p(pa), _p(pb), _p(c), len(pa), _p(out))
+    return out
 
 
 def gjk_epa(shape_a, pose_a, shape_b, pose_b):

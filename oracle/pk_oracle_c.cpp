@@ -183,6 +183,23 @@ uint64_t pko_gjk_epa_pairs(const pko_shape_desc *shapes, const double *verts, co
     return nhit.load();
 }
 
+// contact_point(info, a, b) for every contact (collision_phases.h:78-82): the witness points in the bodies'
+// own frames, particle::project_to_local = orientation.conjugate() * (world_point - pos) (core/particle.h:107-108).
+//   pair_a/pair_b: bodies of contact k; contacts10[k] = normal(3) world_a(3) world_b(3) depth; out6[k] = local_a local_b
+void pko_contact_points(const double *pos, const double *quat_xyzw, const uint32_t *pair_a, const uint32_t *pair_b,
+                        const double *contacts10, uint64_t n, double *out6)
+{
+    for (uint64_t k = 0; k < n; ++k)
+    {
+        const uint32_t ia = pair_a[k], ib = pair_b[k];
+        const quat qa{quat_xyzw[4 * ia], quat_xyzw[4 * ia + 1], quat_xyzw[4 * ia + 2], quat_xyzw[4 * ia + 3]};
+        const quat qb{quat_xyzw[4 * ib], quat_xyzw[4 * ib + 1], quat_xyzw[4 * ib + 2], quat_xyzw[4 * ib + 3]};
+        const double *c = contacts10 + 10 * k;
+        st3(out6 + 6 * k, rotate(conjugate(qa), ld3(c + 3) - ld3(pos + 3 * ia)));
+        st3(out6 + 6 * k + 3, rotate(conjugate(qb), ld3(c + 6) - ld3(pos + 3 * ib)));
+    }
+}
+
 // ------------------------------- dynamic_bvh handle API ---------------------------------------
 void *pko_bvh_create() { return new dynamic_bvh(); }
 void pko_bvh_destroy(void *t) { delete static_cast<dynamic_bvh *>(t); }

@@ -73,7 +73,7 @@ class _StageTimes(C.Structure):
 _lib = None
 
 EXPORTS = [
-    "pk_abi_version", "pk_selftest_division", "pk_create", "pk_destroy", "pk_strerror", "pk_last_error",
+    "pk_abi_version", "pk_selftest_division", "pk_contact_points", "pk_create", "pk_destroy", "pk_strerror", "pk_last_error",
     "pk_shape_box", "pk_shape_sphere", "pk_shape_hull", "pk_shape_aabb", "pk_shapes_bulk",
     "pk_bodies_resize", "pk_bodies_upload", "pk_bodies_update_pose",
     "pk_collide_resident", "pk_fetch_results", "pk_collide", "pk_pairs", "pk_contacts",
@@ -102,6 +102,7 @@ def load_library():
     L.pk_last_error.argtypes = [vp]
     L.pk_create.argtypes = [vp, vp]
     L.pk_selftest_division.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
+    L.pk_contact_points.argtypes = [vp, vp, vp]
     L.pk_destroy.argtypes = [vp]
     L.pk_shape_box.argtypes = [vp, vp, vp]
     L.pk_shape_sphere.argtypes = [vp, C.c_double, vp]
@@ -310,6 +311,16 @@ class Context:
         d = {st.name[k].decode(): float(st.ms[k]) for k in range(NUM_STAGES)}
         self.epa_fallback = int(st.epa_fallback)
         return d, int(st.launches)
+
+    def contact_points(self):
+        """Body-local witness points [n, 6] (local_a, local_b) of the last step's contacts."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.L.pk_contact_points(self.h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros((0, 6))
+        buf = (C.c_double * (6 * n.value)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float64).reshape(-1, 6).copy()
 
     def selftest_division(self, seed, samples):
         bad = C.c_uint64()

@@ -141,6 +141,9 @@ struct pk_ctx
     size_t h_pairs_cap = 0;
     pk_contact *h_contacts = nullptr;
     size_t h_contacts_cap = 0;
+    ContactPointRec *d_points = nullptr; // pk_contact_points: allocated on first use
+    pk_contact_point *h_points = nullptr;
+    size_t points_cap = 0;
 
     cudaEvent_t ev[ST_COUNT + 1]{};
     float stage_ms[ST_COUNT]{};
@@ -443,6 +446,8 @@ int pk_destroy(pk_ctx *ctx)
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_pairs) cudaFreeHost(ctx->h_pairs);
     if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
+    if (ctx->d_points) cudaFree(ctx->d_points);
+    if (ctx->h_points) cudaFreeHost(ctx->h_points);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->copy_stream)
@@ -930,6 +935,8 @@ int pk_fetch_results(pk_ctx *ctx)
     if (ctx->num_contacts > ctx->h_contacts_cap)
     {
         if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
+    if (ctx->d_points) cudaFree(ctx->d_points);
+    if (ctx->h_points) cudaFreeHost(ctx->h_points);
         ctx->h_contacts = nullptr;
         size_t cap = std::min<size_t>(ctx->max_contacts, std::max<size_t>(ctx->num_contacts * 5 / 4, 1024));
         PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_contacts), cap * sizeof(pk_contact), cudaHostAllocDefault));
@@ -986,6 +993,37 @@ int pk_pairs_device(pk_ctx *ctx, const void **dptr, uint64_t *n)
     if (!ctx->have_results) return PK_E_STATE;
     *dptr = ctx->d_pairs_sorted;
     *n = ctx->num_pairs;
+    return PK_OK;
+}
+
+int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n)
+{
+    if (!ctx || !pts || !n) return PK_E_INVALID;
+    if (!ctx->have_results) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    static_assert(sizeof(ContactPointRec) == sizeof(pk_contact_point), "contact point layouts differ");
+    const uint64_t m = ctx->num_contacts;
+    if (m > ctx->points_cap)
+    {
+        if (ctx->d_points) cudaFree(ctx->d_points);
+        if (ctx->h_points) cudaFreeHost(ctx->h_points);
+        ctx->d_points = nullptr;
+        ctx->h_points = nullptr;
+        ctx->points_cap = 0;
+        const size_t cap = std::min<size_t>(ctx->max_contacts, std::max<size_t>(m * 5 / 4, 1024));
+        PK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_points), cap * sizeof(ContactPointRec)));
+        PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_points), cap * sizeof(pk_contact_point), cudaHostAllocDefault));
+        ctx->points_cap = cap;
+    }
+    if (m)
+    {
+        contact_points_kernel<<<div_up(m, 256), 256, 0, ctx->stream>>>(ctx->d_contacts_final, m, ctx->d_pos, ctx->d_quat, ctx->d_points);
+        PK_CUDA(cudaGetLastError());
+        PK_CUDA(cudaMemcpyAsync(ctx->h_points, ctx->d_points, m * sizeof(pk_contact_point), cudaMemcpyDeviceToHost, ctx->stream));
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *pts = ctx->h_points;
+    *n = m;
     return PK_OK;
 }
 

@@ -1044,6 +1044,32 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
     if (n_over) atomicAdd(counters + 1, n_over);
 }
 
+// contact_point(info, a, b) (collision_phases.h:78-82): the witness points of every contact in the bodies' own
+// frames, particle::project_to_local = orientation.conjugate() * (world_point - pos) (core/particle.h:107-108).
+// This is what narrow_phase::calculate stores in its manifolds; computed on request, one thread per contact.
+struct ContactPointRec
+{
+    double local_a[3];
+    double local_b[3];
+};
+__global__ void __launch_bounds__(256)
+contact_points_kernel(const ContactRec *__restrict__ contacts, uint64_t n, const double *__restrict__ pos,
+                      const double *__restrict__ quat, ContactPointRec *__restrict__ out)
+{
+    const uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    const ContactRec c = contacts[k];
+    const uint32_t ia = static_cast<uint32_t>(c.key >> 32), ib = static_cast<uint32_t>(c.key & 0xFFFFFFFFu);
+    const dq qa{quat[4ull * ia], quat[4ull * ia + 1], quat[4ull * ia + 2], quat[4ull * ia + 3]};
+    const dq qb{quat[4ull * ib], quat[4ull * ib + 1], quat[4ull * ib + 2], quat[4ull * ib + 3]};
+    const d3 la = rotate(conjugate(qa), d3{c.world_a[0], c.world_a[1], c.world_a[2]} - d3{pos[3ull * ia], pos[3ull * ia + 1], pos[3ull * ia + 2]});
+    const d3 lb = rotate(conjugate(qb), d3{c.world_b[0], c.world_b[1], c.world_b[2]} - d3{pos[3ull * ib], pos[3ull * ib + 1], pos[3ull * ib + 2]});
+    ContactPointRec r;
+    r.local_a[0] = la.x; r.local_a[1] = la.y; r.local_a[2] = la.z;
+    r.local_b[0] = lb.x; r.local_b[1] = lb.y; r.local_b[2] = lb.z;
+    out[k] = r;
+}
+
 // pk_gjk_epa_batch: one record per requested pair (zeros + hit = 0 for misses).
 __global__ void expand_contacts_kernel(const uint8_t *__restrict__ hit, const uint32_t *__restrict__ index,
                                        const uint8_t *__restrict__ valid, const ContactRec *__restrict__ compact,

@@ -246,3 +246,28 @@ def test_pair_sharding_partitions_the_set(shards):
     allc = allc[np.argsort(allc["key"], kind="stable")]
     assert np.array_equal(allc.view(np.uint8), con_full.view(np.uint8))
     assert min(len(p) for p in parts) > 0.3 * len(keys_full) / shards  # no empty / degenerate shard
+
+
+def test_contact_points_in_body_frames():
+    """narrow_phase::calculate stores contact_point(info, a, b) (collision_phases.h:75-88, 257-263): the witness
+    points in the bodies' own frames.  pk_contact_points against the oracle's restatement, bit for bit."""
+    from gpu_util import make_context
+
+    sc = scene_c3(side=12)
+    ctx = make_context(sc, max_pairs=400_000, mode=pk.MODE_QUERY)
+    try:
+        ctx.collide()
+        con = ctx.contacts()
+        pts = ctx.contact_points()
+    finally:
+        ctx.close()
+    assert len(con) > 500 and pts.shape == (len(con), 6)
+    pa, pb = _split(con["key"])
+    c10 = np.concatenate([con["normal"], con["world_a"], con["world_b"], con["depth"][:, None]], axis=1)
+    want = oracle.contact_points(sc.pos, sc.quat, pa, pb, c10)
+    assert np.array_equal(pts.view(np.uint64), want.view(np.uint64))
+    # and they are what they claim to be: rotating back and translating returns the world points
+    from scipy.spatial.transform import Rotation
+
+    back = Rotation.from_quat(sc.quat[pa]).apply(pts[:, :3]) + sc.pos[pa]
+    assert np.allclose(back, con["world_a"], atol=1e-12)

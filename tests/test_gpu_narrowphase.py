@@ -158,3 +158,35 @@ def test_empty_and_single_pair_batches():
     ref_hit, ref_out, _ = oracle.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa[:1], pb[:1])
     assert np.array_equal(hit, ref_hit)
     ctx.close()
+
+
+def _symmetric_scene(kind_a, kind_b, n=1500, seed=77):
+    """Pairs built to make EPA face distances tie exactly: identity orientations, offsets on a coarse
+    binary grid (exactly representable, many exact symmetries), a few sizes only."""
+    from scenes import Scene, SplitMix64
+
+    rng = SplitMix64(seed)
+    sizes = [0.25, 0.5, 0.75]
+    shapes = []
+    for k in (kind_a, kind_b):
+        for s in sizes:
+            shapes.append(("sphere", s) if k == "sphere" else ("obb", np.array([s, s, 0.5 * s + 0.125])))
+    pos = np.zeros((2 * n, 3))
+    quat = np.tile(np.array([0.0, 0.0, 0.0, 1.0]), (2 * n, 1))
+    sid = np.zeros(2 * n, dtype=np.uint32)
+    sid[0::2] = rng.randint(n, 3)
+    sid[1::2] = 3 + rng.randint(n, 3)
+    pos[0::2] = np.round(rng.uniform(-4.0, 4.0, n, 3) * 8.0) / 8.0
+    pos[1::2] = pos[0::2] + (rng.randint(3 * n, 9).reshape(n, 3) - 4) / 8.0  # offsets in {-0.5 … 0.5}, step 1/8
+    sc = Scene(shapes, pos, quat, sid)
+    return sc, np.arange(0, 2 * n, 2, dtype=np.uint32), np.arange(1, 2 * n, 2, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("kinds", [("sphere", "sphere"), ("sphere", "obb"), ("obb", "obb")], ids=lambda k: "-".join(k))
+def test_epa_exact_ties_bit_exact(kinds):
+    """Which of several equidistant faces the reference pops is decided by the history of its heap
+    (collision.cpp:390-408).  The heap-free EPA path decides the provable cases itself and hands the rest to
+    the heap paths; symmetric configurations make such ties the rule rather than the exception."""
+    sc, pa, pb = _symmetric_scene(*kinds)
+    hit, out, st = _batch_vs_oracle(sc, pa, pb)
+    assert hit.sum() > 300

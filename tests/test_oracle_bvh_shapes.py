@@ -312,3 +312,25 @@ def test_world_first_step_quirk_and_stateless_equivalence():
         total_pairs += len(keys)
         pos = pos + disp * dyn[:, None]
     assert total_pairs > 0
+
+
+def test_contact_points_are_project_to_local():
+    """contact_point (collision_phases.h:78-82) = particle::project_to_local (core/particle.h:107-108) of the two
+    witness points: q* · (p − pos).  Checked against scipy's rotation (1e-12) and for the identity pose (exact)."""
+    from scipy.spatial.transform import Rotation
+
+    from scenes import SplitMix64
+
+    rng = SplitMix64(4242)
+    n = 64
+    pos = rng.uniform(-3.0, 3.0, 2 * n, 3)
+    quat = rng.quats(2 * n)
+    quat[0] = quat[1] = [0.0, 0.0, 0.0, 1.0]
+    pa = np.arange(0, 2 * n, 2, dtype=np.uint32)
+    pb = pa + 1
+    c10 = rng.uniform(-2.0, 2.0, n, 10)
+    out = oracle.contact_points(pos, quat, pa, pb, c10)
+    assert np.array_equal(out[0, :3], c10[0, 3:6] - pos[0]) and np.array_equal(out[0, 3:], c10[0, 6:9] - pos[1])
+    la = Rotation.from_quat(quat[pa]).inv().apply(c10[:, 3:6] - pos[pa])
+    lb = Rotation.from_quat(quat[pb]).inv().apply(c10[:, 6:9] - pos[pb])
+    assert np.allclose(out[:, :3], la, atol=1e-12) and np.allclose(out[:, 3:], lb, atol=1e-12)
