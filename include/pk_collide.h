@@ -96,6 +96,34 @@ typedef struct pk_contact_point
     double local_b[3];
 } pk_contact_point;
 
+/* Contact manifolds: narrow_phase's per-pair state (collision_phases.h:90-327).  A point is
+ * manifold::contact_info = contact_point {normal, local_a, local_b, depth} + the solver's cached impulses. */
+typedef struct pk_manifold_point
+{
+    double normal[3];
+    double local_a[3];
+    double local_b[3];
+    double depth;
+    double normal_impulse;
+    double tangent_impulses[2];
+} pk_manifold_point;
+
+typedef struct pk_manifold
+{
+    uint64_t key;   /* make_pair_key(a, b), a = lower id */
+    uint32_t count; /* 1..4 (manifold::max_contact_points); unused points are zero */
+    uint32_t _pad;
+    pk_manifold_point points[4];
+} pk_manifold;
+
+typedef struct pk_manifold_result
+{
+    uint64_t num_manifolds; /* non-empty manifolds after the update */
+    uint64_t num_began;     /* on_collision (empty → non-empty) */
+    uint64_t num_ended;     /* on_collision_exit (non-empty → empty while the pair is still in the pair set) */
+    float ms;               /* device time of the update */
+} pk_manifold_result;
+
 typedef struct pk_step_result
 {
     uint64_t num_pairs;      /* candidate pairs produced by the broadphase (this shard) */
@@ -166,6 +194,21 @@ int pk_contacts(pk_ctx *ctx, const pk_contact **recs, uint64_t *n);
  * (narrow_phase::calculate → contact_point, collision_phases.h:257-263).  Computed on the device on request
  * from the poses of that step; the host pointer stays valid until the next pk_collide*. */
 int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n);
+/* ---- manifolds (optional) -------------------------------------------------------------
+ * narrow_phase::calculate merges each pair's new contact into the manifold it kept from the last step: warm
+ * start of a point found at the same place, drift / breaking test of the old points under the new poses,
+ * add_reduce beyond four points (collision_phases.h:244-320).  pk_manifolds_enable reserves the state;
+ * pk_manifolds_update runs that merge on the device for the step pk_collide* just computed (once per step);
+ * manifolds come back sorted by key.  Pairs that left the pair set lose their manifold silently
+ * (on_pair_removed, :225-242); began / ended are the keys for which the reference would call on_coll_beg /
+ * on_coll_end (:314-318), sorted.  pk_manifolds_set_impulses stores what the constraint solver accumulated
+ * (normal, tangent 0, tangent 1 per point; [n][4][3], order of pk_manifolds) for next step's warm start. */
+int pk_manifolds_enable(pk_ctx *ctx, uint64_t capacity);
+int pk_manifolds_update(pk_ctx *ctx, pk_manifold_result *out);
+int pk_manifolds(pk_ctx *ctx, const pk_manifold **recs, uint64_t *n);
+int pk_manifolds_device(pk_ctx *ctx, const void **dptr, uint64_t *n);
+int pk_manifold_events(pk_ctx *ctx, const uint64_t **began, uint64_t *num_began, const uint64_t **ended, uint64_t *num_ended);
+int pk_manifolds_set_impulses(pk_ctx *ctx, const double *impulses, uint64_t n);
 int pk_pairs_device(pk_ctx *ctx, const void **dptr, uint64_t *n);
 int pk_contacts_device(pk_ctx *ctx, const void **dptr, uint64_t *n);
 /* Stored (fat) boxes of the broadphase, [count][6] = min xyz, max xyz (dynamic_bvh::bounds, bvh.h:452-456). */

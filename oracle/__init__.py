@@ -62,6 +62,13 @@ def lib():
         L.pko_gjk_epa_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp, i32]
         L.pko_gjk_epa_pairs.restype = u64
         L.pko_contact_points.argtypes = [vp, vp, vp, vp, vp, u64, vp]
+        L.pko_man_create.restype = vp
+        L.pko_man_destroy.argtypes = [vp]
+        L.pko_man_step.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp]
+        L.pko_man_step.restype = u64
+        L.pko_man_get.argtypes = [vp, vp, vp, vp, u64]
+        L.pko_man_get.restype = u64
+        L.pko_man_set_impulses.argtypes = [vp, vp]
         L.pko_bvh_create.restype = vp
         L.pko_bvh_destroy.argtypes = [vp]
         L.pko_bvh_add.argtypes = [vp, u32, vp]
@@ -308,3 +315,48 @@ class World:
         out = np.empty(6)
         lib().pko_world_stored(self.h, int(body), _p(out))
         return out
+
+
+class Manifolds:
+    """narrow_phase's manifold state (collision_phases.h:200-327): step() is narrow_phase::calculate for the
+    current pair set given this step's gjk_epa results."""
+
+    def __init__(self):
+        self.h = lib().pko_man_create()
+        self.count = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().pko_man_destroy(self.h)
+            self.h = None
+
+    def step(self, keys, hit, contacts10, pos, quat):
+        """→ (began keys, ended keys); keys sorted, hit[n], contacts10[n,10] (rows of hits)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        hit = np.ascontiguousarray(hit, dtype=np.uint8)
+        c = _f64(contacts10, (-1, 10))
+        pos = _f64(pos, (-1, 3))
+        quat = _f64(quat, (-1, 4))
+        n = len(keys)
+        began = np.empty(max(n, 1), dtype=np.uint64)
+        ended = np.empty(max(n, 1), dtype=np.uint64)
+        nb = C.c_uint64()
+        ne = C.c_uint64()
+        self.count = int(lib().pko_man_step(self.h, _p(keys), _p(hit), _p(c), n, _p(pos), _p(quat), _p(began), C.byref(nb),
+                                           _p(ended), C.byref(ne)))
+        return np.sort(began[: nb.value]), np.sort(ended[: ne.value])
+
+    def get(self):
+        """→ (keys[m], counts[m], points[m,4,13]) in key order; a point is normal(3) local_a(3) local_b(3) depth
+        normal_impulse tangent_impulses(2)."""
+        m = self.count
+        keys = np.empty(max(m, 1), dtype=np.uint64)
+        counts = np.empty(max(m, 1), dtype=np.uint32)
+        pts = np.zeros((max(m, 1), 4, 13))
+        lib().pko_man_get(self.h, _p(keys), _p(counts), _p(pts), max(m, 1))
+        return keys[:m], counts[:m], pts[:m]
+
+    def set_impulses(self, imp):
+        imp = _f64(imp, (-1, 4, 3))
+        assert len(imp) == self.count
+        lib().pko_man_set_impulses(self.h, _p(imp))

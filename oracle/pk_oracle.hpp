@@ -753,6 +753,126 @@ struct epa_solver
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// manifold / narrow_phase::calculate — include/physkit/collision/collision_phases.h:75-320
+// (the consumer of gjk_epa's result; restated for the device-side manifold update)
+// ---------------------------------------------------------------------------------------------
+struct contact_info_t // manifold::contact_info (:93-99) with contact_point (:75-88) flattened
+{
+    v3 normal{0, 0, 0}, local_a{0, 0, 0}, local_b{0, 0, 0};
+    double depth = 0.0;
+    double normal_impulse = 0.0;
+    double tangent_impulses[2] = {0.0, 0.0};
+};
+
+struct manifold_t
+{
+    static constexpr int max_contact_points = 4; // :101
+    contact_info_t c[4];
+    int n = 0;
+
+    // :127-133
+    void add_contact(const contact_info_t &info)
+    {
+        if (n < max_contact_points)
+            c[n++] = info;
+        else
+            add_reduce(info);
+    }
+    // :139-198 — keep the deepest point, the one farthest from it, the one spanning the largest triangle
+    // with those two, and the one farthest from the third
+    void add_reduce(const contact_info_t &new_pt)
+    {
+        contact_info_t pool[5];
+        for (int i = 0; i < 4; ++i) pool[i] = c[i];
+        pool[4] = new_pt;
+        int best[4] = {0, 1, 2, 3};
+        for (int i = 1; i < 5; ++i)
+            if (pool[i].depth > pool[best[0]].depth) best[0] = i;
+        double max_dist2 = -1.0;
+        for (int i = 0; i < 5; ++i)
+        {
+            if (i == best[0]) continue;
+            double dist2 = sqnorm(pool[i].local_a - pool[best[0]].local_a);
+            if (dist2 > max_dist2)
+            {
+                max_dist2 = dist2;
+                best[1] = i;
+            }
+        }
+        double max_area2 = -1.0;
+        v3 edge0 = pool[best[1]].local_a - pool[best[0]].local_a;
+        for (int i = 0; i < 5; ++i)
+        {
+            if (i == best[0] || i == best[1]) continue;
+            v3 edge1 = pool[i].local_a - pool[best[0]].local_a;
+            double area2 = sqnorm(cross(edge0, edge1));
+            if (area2 > max_area2)
+            {
+                max_area2 = area2;
+                best[2] = i;
+            }
+        }
+        max_dist2 = -1.0;
+        for (int i = 0; i < 5; ++i)
+        {
+            if (i == best[0] || i == best[1] || i == best[2]) continue;
+            double dist2 = sqnorm(pool[i].local_a - pool[best[2]].local_a);
+            if (dist2 > max_dist2)
+            {
+                max_dist2 = dist2;
+                best[3] = i;
+            }
+        }
+        n = 0;
+        for (int b : best) c[n++] = pool[b];
+    }
+};
+
+// One pair's share of narrow_phase::calculate (:252-318): merge this step's contact (if any) with the
+// manifold kept from the previous step.  pos/q of the two bodies as of this step (particle.h:107-111).
+inline manifold_t manifold_merge(const manifold_t &old_man, const contact_info_t *new_contact_in, v3 pos_a, quat q_a, v3 pos_b,
+                                 quat q_b)
+{
+    constexpr double distance2_eps = .005 * .005;         // :212
+    constexpr double contact_breaking_threshold = 0.05;  // :213
+    constexpr double drift2_eps = 0.06;                  // :267
+    contact_info_t nc;
+    const bool have_new = new_contact_in != nullptr;
+    if (have_new) nc = *new_contact_in;
+    manifold_t new_man;
+    for (int k = 0; k < old_man.n; ++k)
+    {
+        contact_info_t old_contact = old_man.c[k];
+        if (have_new)
+        {
+            // warm start the new point from an old one at (nearly) the same place on either body
+            if (sqnorm(nc.local_a - old_contact.local_a) < distance2_eps || sqnorm(nc.local_b - old_contact.local_b) < distance2_eps)
+            {
+                nc.normal_impulse = old_contact.normal_impulse;
+                nc.tangent_impulses[0] = old_contact.tangent_impulses[0];
+                nc.tangent_impulses[1] = old_contact.tangent_impulses[1];
+                continue;
+            }
+        }
+        v3 world_old_a = rotate(q_a, old_contact.local_a) + pos_a; // project_to_world
+        v3 world_old_b = rotate(q_b, old_contact.local_b) + pos_b;
+        v3 normal = have_new ? nc.normal : old_contact.normal;
+        v3 relative = world_old_b - world_old_a;
+        double depth = dot(relative, normal);
+        v3 projected_a = world_old_a + normal * depth;
+        double drift2 = sqnorm(projected_a - world_old_b);
+        if (depth > -contact_breaking_threshold && drift2 < drift2_eps)
+        {
+            old_contact.depth = depth;
+            old_contact.normal = normal;
+            new_man.add_contact(old_contact);
+        }
+    }
+    if (have_new) new_man.add_contact(nc);
+    return new_man;
+}
+
 // collision.cpp:512-518
 inline std::optional<collision_info> gjk_epa(const shape &a, const shape &b, gjk_stats *st = nullptr)
 {

@@ -2,6 +2,8 @@
 // (see the header of pk_oracle.hpp).  Nothing in physkit_b200/ may link or load this.
 #include "pk_oracle.hpp"
 
+#include <map>
+
 #include <atomic>
 #include <cstdio>
 #include <thread>
@@ -197,6 +199,100 @@ void pko_contact_points(const double *pos, const double *quat_xyzw, const uint32
         const double *c = contacts10 + 10 * k;
         st3(out6 + 6 * k, rotate(conjugate(qa), ld3(c + 3) - ld3(pos + 3 * ia)));
         st3(out6 + 6 * k + 3, rotate(conjugate(qb), ld3(c + 6) - ld3(pos + 3 * ib)));
+    }
+}
+
+// ------------------------------- manifolds (narrow_phase state) --------------------------------
+// narrow_phase keeps one manifold per pair of the pair set (collision_phases.h:218-242, 322-327); only the
+// non-empty ones carry state, so that is what is stored here, keyed by make_pair_key.
+struct pko_manifolds
+{
+    std::map<uint64_t, manifold_t> mans;
+};
+void *pko_man_create() { return new pko_manifolds(); }
+void pko_man_destroy(void *h) { delete static_cast<pko_manifolds *>(h); }
+
+// narrow_phase::calculate (collision_phases.h:244-320) for the current pair set.
+//   keys[n] sorted pair keys, hit[n], contacts10[n] (rows of hits: normal, world_a, world_b, depth; others ignored)
+//   began / ended: keys whose manifold went empty → non-empty / non-empty → empty this step (on_coll_beg / on_coll_end)
+// Pairs that left the pair set are dropped without a callback (on_pair_removed, :225-242).  Returns the number
+// of non-empty manifolds.
+uint64_t pko_man_step(void *h, const uint64_t *keys, const uint8_t *hit, const double *contacts10, uint64_t n, const double *pos,
+                      const double *quat_xyzw, uint64_t *began, uint64_t *nbegan, uint64_t *ended, uint64_t *nended)
+{
+    pko_manifolds &st = *static_cast<pko_manifolds *>(h);
+    std::map<uint64_t, manifold_t> next;
+    uint64_t nb = 0, ne = 0;
+    for (uint64_t k = 0; k < n; ++k)
+    {
+        const uint64_t key = keys[k];
+        const uint32_t ia = static_cast<uint32_t>(key >> 32), ib = static_cast<uint32_t>(key & 0xFFFFFFFFu);
+        auto it = st.mans.find(key);
+        if (it == st.mans.end() && !hit[k]) continue; // empty manifold, no new contact: nothing happens
+        const manifold_t old_man = (it == st.mans.end()) ? manifold_t{} : it->second;
+        const v3 pa = ld3(pos + 3 * ia), pb = ld3(pos + 3 * ib);
+        const quat qa = ldq(quat_xyzw + 4 * ia), qb = ldq(quat_xyzw + 4 * ib);
+        contact_info_t nc;
+        if (hit[k])
+        {
+            const double *c = contacts10 + 10 * k;
+            nc.normal = ld3(c);
+            nc.local_a = rotate(conjugate(qa), ld3(c + 3) - pa); // contact_point (:78-82)
+            nc.local_b = rotate(conjugate(qb), ld3(c + 6) - pb);
+            nc.depth = c[9];
+        }
+        manifold_t nm = manifold_merge(old_man, hit[k] ? &nc : nullptr, pa, qa, pb, qb);
+        const bool was = old_man.n > 0, is = nm.n > 0;
+        if (!was && is && began) began[nb++] = key;
+        if (was && !is && ended) ended[ne++] = key;
+        if (is) next.emplace(key, nm);
+    }
+    st.mans.swap(next);
+    if (nbegan) *nbegan = nb;
+    if (nended) *nended = ne;
+    return st.mans.size();
+}
+// keys_out[m], counts_out[m], pts[m][4][13] = normal(3) local_a(3) local_b(3) depth normal_impulse tangent(2), key order
+uint64_t pko_man_get(void *h, uint64_t *keys_out, uint32_t *counts_out, double *pts, uint64_t cap)
+{
+    pko_manifolds &st = *static_cast<pko_manifolds *>(h);
+    uint64_t m = 0;
+    for (const auto &[key, man] : st.mans)
+    {
+        if (m >= cap) break;
+        keys_out[m] = key;
+        counts_out[m] = static_cast<uint32_t>(man.n);
+        for (int j = 0; j < 4; ++j)
+        {
+            double *o = pts + (m * 4 + j) * 13;
+            const contact_info_t &c = man.c[j];
+            const bool used = j < man.n;
+            st3(o, used ? c.normal : v3{0, 0, 0});
+            st3(o + 3, used ? c.local_a : v3{0, 0, 0});
+            st3(o + 6, used ? c.local_b : v3{0, 0, 0});
+            o[9] = used ? c.depth : 0.0;
+            o[10] = used ? c.normal_impulse : 0.0;
+            o[11] = used ? c.tangent_impulses[0] : 0.0;
+            o[12] = used ? c.tangent_impulses[1] : 0.0;
+        }
+        ++m;
+    }
+    return st.mans.size();
+}
+// what the constraint solver leaves behind (constraint.h:1107-1201 accumulates them): imp[m][4][3] in key order
+void pko_man_set_impulses(void *h, const double *imp)
+{
+    pko_manifolds &st = *static_cast<pko_manifolds *>(h);
+    uint64_t m = 0;
+    for (auto &[key, man] : st.mans)
+    {
+        for (int j = 0; j < man.n; ++j)
+        {
+            man.c[j].normal_impulse = imp[(m * 4 + j) * 3];
+            man.c[j].tangent_impulses[0] = imp[(m * 4 + j) * 3 + 1];
+            man.c[j].tangent_impulses[1] = imp[(m * 4 + j) * 3 + 2];
+        }
+        ++m;
     }
 }
 

@@ -66,6 +66,16 @@ class StepResult(C.Structure):
     ]
 
 
+class _ManifoldResult(C.Structure):
+    _fields_ = [("num_manifolds", C.c_uint64), ("num_began", C.c_uint64), ("num_ended", C.c_uint64), ("ms", C.c_float)]
+
+
+manifold_point_dtype = np.dtype([("normal", "<f8", (3,)), ("local_a", "<f8", (3,)), ("local_b", "<f8", (3,)), ("depth", "<f8"),
+                                 ("normal_impulse", "<f8"), ("tangent_impulses", "<f8", (2,))])
+manifold_dtype = np.dtype([("key", "<u8"), ("count", "<u4"), ("_pad", "<u4"), ("points", manifold_point_dtype, (4,))])
+assert manifold_dtype.itemsize == 432
+
+
 class _StageTimes(C.Structure):
     _fields_ = [("ms", C.c_float * NUM_STAGES), ("name", C.c_char_p * NUM_STAGES), ("launches", C.c_uint32), ("epa_fallback", C.c_uint32)]
 
@@ -73,7 +83,8 @@ class _StageTimes(C.Structure):
 _lib = None
 
 EXPORTS = [
-    "pk_abi_version", "pk_selftest_division", "pk_contact_points", "pk_create", "pk_destroy", "pk_strerror", "pk_last_error",
+    "pk_abi_version", "pk_selftest_division", "pk_contact_points", "pk_manifolds_enable", "pk_manifolds_update",
+    "pk_manifolds", "pk_manifolds_device", "pk_manifold_events", "pk_manifolds_set_impulses", "pk_create", "pk_destroy", "pk_strerror", "pk_last_error",
     "pk_shape_box", "pk_shape_sphere", "pk_shape_hull", "pk_shape_aabb", "pk_shapes_bulk",
     "pk_bodies_resize", "pk_bodies_upload", "pk_bodies_update_pose",
     "pk_collide_resident", "pk_fetch_results", "pk_collide", "pk_pairs", "pk_contacts",
@@ -103,6 +114,12 @@ def load_library():
     L.pk_create.argtypes = [vp, vp]
     L.pk_selftest_division.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     L.pk_contact_points.argtypes = [vp, vp, vp]
+    L.pk_manifolds_enable.argtypes = [vp, C.c_uint64]
+    L.pk_manifolds_update.argtypes = [vp, vp]
+    L.pk_manifolds.argtypes = [vp, vp, vp]
+    L.pk_manifolds_device.argtypes = [vp, vp, vp]
+    L.pk_manifold_events.argtypes = [vp, vp, vp, vp, vp]
+    L.pk_manifolds_set_impulses.argtypes = [vp, vp, C.c_uint64]
     L.pk_destroy.argtypes = [vp]
     L.pk_shape_box.argtypes = [vp, vp, vp]
     L.pk_shape_sphere.argtypes = [vp, C.c_double, vp]
@@ -321,6 +338,43 @@ class Context:
             return np.zeros((0, 6))
         buf = (C.c_double * (6 * n.value)).from_address(p.value)
         return np.frombuffer(buf, dtype=np.float64).reshape(-1, 6).copy()
+
+    # -- manifolds (narrow_phase state on the device)
+    def manifolds_enable(self, capacity):
+        self._check(self.L.pk_manifolds_enable(self.h, C.c_uint64(int(capacity))))
+
+    def manifolds_update(self):
+        """→ (num_manifolds, num_began, num_ended, device ms) for the step just computed."""
+        r = _ManifoldResult()
+        self._check(self.L.pk_manifolds_update(self.h, C.byref(r)))
+        return int(r.num_manifolds), int(r.num_began), int(r.num_ended), float(r.ms)
+
+    def manifolds(self):
+        """Structured array (manifold_dtype), sorted by key."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.L.pk_manifolds(self.h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=manifold_dtype)
+        buf = (C.c_char * (manifold_dtype.itemsize * n.value)).from_address(p.value)
+        return np.frombuffer(buf, dtype=manifold_dtype).copy()
+
+    def manifold_events(self):
+        """→ (began keys, ended keys), each sorted."""
+        pb, pe = C.c_void_p(), C.c_void_p()
+        nb, ne = C.c_uint64(), C.c_uint64()
+        self._check(self.L.pk_manifold_events(self.h, C.byref(pb), C.byref(nb), C.byref(pe), C.byref(ne)))
+
+        def take(p, n):
+            if n.value == 0:
+                return np.zeros(0, dtype=np.uint64)
+            return np.frombuffer((C.c_uint64 * n.value).from_address(p.value), dtype=np.uint64).copy()
+
+        return take(pb, nb), take(pe, ne)
+
+    def manifolds_set_impulses(self, imp):
+        imp = np.ascontiguousarray(imp, dtype=np.float64).reshape(-1, 4, 3)
+        self._check(self.L.pk_manifolds_set_impulses(self.h, _p(imp), C.c_uint64(len(imp))))
 
     def selftest_division(self, seed, samples):
         bad = C.c_uint64()

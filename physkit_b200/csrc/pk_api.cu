@@ -10,6 +10,7 @@
 #include "pk_common.cuh"
 #include "pk_narrowphase.cuh"
 #include "pk_epa_scan.cuh"
+#include "pk_manifold.cuh"
 #include "pk_sort.cuh"
 
 #include <algorithm>
@@ -141,6 +142,22 @@ struct pk_ctx
     size_t h_pairs_cap = 0;
     pk_contact *h_contacts = nullptr;
     size_t h_contacts_cap = 0;
+    // manifolds (pk_manifolds_enable): sorted array of non-empty manifolds, double-buffered
+    uint64_t man_cap = 0, man_count = 0, man_began = 0, man_ended = 0;
+    int man_cur = 0;
+    int32_t man_epoch = -1; // step the manifolds were last updated for
+    ManifoldRec *d_man[2] = {nullptr, nullptr};
+    ManifoldRec *d_man_stage = nullptr;
+    uint64_t *d_man_ckeys[2] = {nullptr, nullptr}; // candidate keys (radix sort double buffer)
+    uint32_t *d_man_csrc[2] = {nullptr, nullptr};
+    uint64_t *d_man_began[2] = {nullptr, nullptr}, *d_man_ended[2] = {nullptr, nullptr};
+    uint8_t *d_man_consumed = nullptr;
+    unsigned long long *d_man_counters = nullptr;
+    double *d_man_imp = nullptr;
+    pk_manifold *h_man = nullptr;
+    uint64_t *h_man_events = nullptr; // began keys, then ended keys
+    size_t h_man_cap = 0, h_man_events_cap = 0;
+    int man_began_buf = 0, man_ended_buf = 0;
     ContactPointRec *d_points = nullptr; // pk_contact_points: allocated on first use
     pk_contact_point *h_points = nullptr;
     size_t points_cap = 0;
@@ -446,6 +463,15 @@ int pk_destroy(pk_ctx *ctx)
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_pairs) cudaFreeHost(ctx->h_pairs);
     if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
+    {
+        void *man[] = {ctx->d_man[0], ctx->d_man[1], ctx->d_man_stage, ctx->d_man_ckeys[0], ctx->d_man_ckeys[1], ctx->d_man_csrc[0],
+                       ctx->d_man_csrc[1], ctx->d_man_began[0], ctx->d_man_began[1], ctx->d_man_ended[0], ctx->d_man_ended[1],
+                       ctx->d_man_consumed, ctx->d_man_counters, ctx->d_man_imp};
+        for (void *q : man)
+            if (q) cudaFree(q);
+        if (ctx->h_man) cudaFreeHost(ctx->h_man);
+        if (ctx->h_man_events) cudaFreeHost(ctx->h_man_events);
+    }
     if (ctx->d_points) cudaFree(ctx->d_points);
     if (ctx->h_points) cudaFreeHost(ctx->h_points);
     for (auto &e : ctx->ev)
@@ -935,8 +961,6 @@ int pk_fetch_results(pk_ctx *ctx)
     if (ctx->num_contacts > ctx->h_contacts_cap)
     {
         if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
-    if (ctx->d_points) cudaFree(ctx->d_points);
-    if (ctx->h_points) cudaFreeHost(ctx->h_points);
         ctx->h_contacts = nullptr;
         size_t cap = std::min<size_t>(ctx->max_contacts, std::max<size_t>(ctx->num_contacts * 5 / 4, 1024));
         PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_contacts), cap * sizeof(pk_contact), cudaHostAllocDefault));
@@ -1024,6 +1048,182 @@ int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n)
     }
     *pts = ctx->h_points;
     *n = m;
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ manifolds
+int pk_manifolds_enable(pk_ctx *ctx, uint64_t capacity)
+{
+    if (!ctx || capacity == 0) return PK_E_INVALID;
+    if (ctx->man_cap) return PK_E_STATE;
+    if (capacity > std::max<uint64_t>(ctx->cfg.max_pairs, ctx->cfg.max_bodies))
+    {
+        ctx->last_error = "manifold capacity exceeds pk_config.max_pairs (the sort scratch is sized by it)";
+        return PK_E_INVALID;
+    }
+    cudaSetDevice(ctx->cfg.device);
+    int s;
+#define A(ptr, count)                                   \
+    if ((s = dev_alloc(ctx, &(ptr), (count))) != PK_OK) \
+    return s
+    A(ctx->d_man[0], capacity);
+    A(ctx->d_man[1], capacity);
+    A(ctx->d_man_stage, 2 * capacity);
+    for (int b = 0; b < 2; ++b)
+    {
+        A(ctx->d_man_ckeys[b], capacity);
+        A(ctx->d_man_csrc[b], capacity);
+        A(ctx->d_man_began[b], capacity);
+        A(ctx->d_man_ended[b], capacity);
+    }
+    A(ctx->d_man_consumed, ctx->max_contacts + 16);
+    A(ctx->d_man_counters, 4);
+    A(ctx->d_man_imp, capacity * 12);
+#undef A
+    ctx->man_cap = capacity;
+    ctx->man_count = 0;
+    ctx->man_epoch = -1;
+    return PK_OK;
+}
+
+// narrow_phase::calculate's manifold part (collision_phases.h:252-318) for the step pk_collide* just computed.
+int pk_manifolds_update(pk_ctx *ctx, pk_manifold_result *out)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (!ctx->man_cap || !ctx->have_results || ctx->man_epoch == ctx->epoch) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t s = ctx->stream;
+    const uint64_t m_prev = ctx->man_count;
+    const uint64_t nslots = std::min<uint64_t>(ctx->h_counters[C_HITS], ctx->max_contacts);
+    const ManifoldRec *prev = ctx->d_man[ctx->man_cur];
+    ManifoldRec *next = ctx->d_man[ctx->man_cur ^ 1];
+    cudaEventRecord(ctx->ev[0], s);
+    PK_CUDA(cudaMemsetAsync(ctx->d_man_counters, 0, 4 * sizeof(unsigned long long), s));
+    if (nslots) PK_CUDA(cudaMemsetAsync(ctx->d_man_consumed, 0, nslots, s));
+    if (m_prev)
+        manifold_old_kernel<<<div_up(m_prev, 128), 128, 0, s>>>(prev, m_prev, ctx->d_pairs_sorted, ctx->num_pairs, ctx->d_hit,
+                                                               ctx->d_out_index, ctx->d_valid, ctx->d_contacts[0], ctx->d_pos,
+                                                               ctx->d_quat, ctx->d_man_stage, ctx->d_man_consumed,
+                                                               ctx->d_man_ckeys[0], ctx->d_man_csrc[0], ctx->man_cap, ctx->d_man_ended[0],
+                                                               ctx->d_man_counters);
+    if (nslots)
+        manifold_new_kernel<<<div_up(nslots, 128), 128, 0, s>>>(ctx->d_contacts[0], ctx->d_valid, ctx->d_man_consumed, nslots, ctx->d_pos,
+                                                               ctx->d_quat, ctx->d_man_stage, m_prev, 2 * ctx->man_cap,
+                                                               ctx->d_man_ckeys[0], ctx->d_man_csrc[0], ctx->man_cap, ctx->d_man_began[0],
+                                                               ctx->d_man_counters);
+    PK_CUDA(cudaGetLastError());
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    PK_CUDA(cudaMemcpyAsync(cnt, ctx->d_man_counters, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaStreamSynchronize(s));
+    // the candidate list has man_cap entries: survivors of the old array + new manifolds must fit
+    if (cnt[0] > ctx->man_cap || cnt[2] > ctx->man_cap || m_prev + cnt[1] > 2 * ctx->man_cap)
+    {
+        ctx->last_error = "manifold capacity exceeded (pk_manifolds_enable)";
+        return PK_E_PAIR_OVERFLOW;
+    }
+    const int idbits = bits_for(std::max<uint32_t>(ctx->n_bodies, 2));
+    std::vector<int> shifts;
+    for (int b = 0; b < idbits; b += 8) shifts.push_back(b);
+    for (int b = 0; b < idbits; b += 8) shifts.push_back(32 + b);
+    int buf = 0;
+    if (cnt[0] > 1) PK_TRY(radix_sort(ctx, ctx->d_man_ckeys, ctx->d_man_csrc, cnt[0], shifts, &buf));
+    if (cnt[0])
+        manifold_gather_kernel<<<div_up(cnt[0], 128), 128, 0, s>>>(ctx->d_man_csrc[buf], cnt[0], ctx->d_man_stage, next);
+    ctx->man_began_buf = ctx->man_ended_buf = 0;
+    if (cnt[2] > 1) PK_TRY(radix_sort(ctx, ctx->d_man_began, nullptr, cnt[2], shifts, &ctx->man_began_buf));
+    if (cnt[3] > 1) PK_TRY(radix_sort(ctx, ctx->d_man_ended, nullptr, cnt[3], shifts, &ctx->man_ended_buf));
+    PK_CUDA(cudaGetLastError());
+    cudaEventRecord(ctx->ev[1], s);
+    PK_CUDA(cudaStreamSynchronize(s));
+    ctx->man_cur ^= 1;
+    ctx->man_count = cnt[0];
+    ctx->man_began = cnt[2];
+    ctx->man_ended = cnt[3];
+    ctx->man_epoch = ctx->epoch;
+    if (out)
+    {
+        out->num_manifolds = cnt[0];
+        out->num_began = cnt[2];
+        out->num_ended = cnt[3];
+        cudaEventElapsedTime(&out->ms, ctx->ev[0], ctx->ev[1]);
+    }
+    return PK_OK;
+}
+
+int pk_manifolds(pk_ctx *ctx, const pk_manifold **recs, uint64_t *n)
+{
+    if (!ctx || !recs || !n) return PK_E_INVALID;
+    if (!ctx->man_cap) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    static_assert(sizeof(pk_manifold) == sizeof(ManifoldRec), "manifold layouts differ");
+    const uint64_t m = ctx->man_count;
+    if (m > ctx->h_man_cap)
+    {
+        if (ctx->h_man) cudaFreeHost(ctx->h_man);
+        ctx->h_man = nullptr;
+        ctx->h_man_cap = 0;
+        const size_t cap = std::min<size_t>(ctx->man_cap, std::max<size_t>(m * 5 / 4, 256));
+        PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_man), cap * sizeof(pk_manifold), cudaHostAllocDefault));
+        ctx->h_man_cap = cap;
+    }
+    if (m)
+    {
+        PK_CUDA(cudaMemcpyAsync(ctx->h_man, ctx->d_man[ctx->man_cur], m * sizeof(pk_manifold), cudaMemcpyDeviceToHost, ctx->stream));
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *recs = ctx->h_man;
+    *n = m;
+    return PK_OK;
+}
+
+int pk_manifolds_device(pk_ctx *ctx, const void **dptr, uint64_t *n)
+{
+    if (!ctx || !dptr || !n) return PK_E_INVALID;
+    if (!ctx->man_cap) return PK_E_STATE;
+    *dptr = ctx->d_man[ctx->man_cur];
+    *n = ctx->man_count;
+    return PK_OK;
+}
+
+int pk_manifold_events(pk_ctx *ctx, const uint64_t **began, uint64_t *num_began, const uint64_t **ended, uint64_t *num_ended)
+{
+    if (!ctx || !began || !num_began || !ended || !num_ended) return PK_E_INVALID;
+    if (!ctx->man_cap) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    const uint64_t nb = ctx->man_began, ne = ctx->man_ended;
+    if (nb + ne > ctx->h_man_events_cap)
+    {
+        if (ctx->h_man_events) cudaFreeHost(ctx->h_man_events);
+        ctx->h_man_events = nullptr;
+        ctx->h_man_events_cap = 0;
+        const size_t cap = std::max<size_t>((nb + ne) * 5 / 4, 256);
+        PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_man_events), cap * sizeof(uint64_t), cudaHostAllocDefault));
+        ctx->h_man_events_cap = cap;
+    }
+    if (nb)
+        PK_CUDA(cudaMemcpyAsync(ctx->h_man_events, ctx->d_man_began[ctx->man_began_buf], nb * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    if (ne)
+        PK_CUDA(cudaMemcpyAsync(ctx->h_man_events + nb, ctx->d_man_ended[ctx->man_ended_buf], ne * sizeof(uint64_t),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *began = ctx->h_man_events;
+    *num_began = nb;
+    *ended = ctx->h_man_events ? ctx->h_man_events + nb : nullptr;
+    *num_ended = ne;
+    return PK_OK;
+}
+
+int pk_manifolds_set_impulses(pk_ctx *ctx, const double *impulses, uint64_t n)
+{
+    if (!ctx || (!impulses && n)) return PK_E_INVALID;
+    if (!ctx->man_cap || n != ctx->man_count) return PK_E_STATE;
+    if (!n) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    PK_CUDA(cudaMemcpyAsync(ctx->d_man_imp, impulses, n * 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    manifold_impulses_kernel<<<div_up(4 * n, 256), 256, 0, ctx->stream>>>(ctx->d_man[ctx->man_cur], n, ctx->d_man_imp);
+    PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
 
