@@ -293,6 +293,17 @@ def run_ours(args, rank, world, local_rank):
     h2d = n * (3 + 4 + 3) * 8
     d2h = int(res_e.num_pairs) * 8 + int(res_e.num_contacts) * 88
 
+    # ---- optional: manifold update on top of the step, not part of the headline ----------
+    manifold_info = None
+    if args.manifolds and world == 1:
+        ctx.manifolds_enable(min(max_contacts, 4 * max(contacts, 1) + 1024))
+        ms = []
+        for s in range(6):
+            ctx.update_pose(h_pos[s % 2], h_quat, h_disp)
+            ctx.collide_resident()
+            ms.append(ctx.manifolds_update())
+        manifold_info = {"manifolds": ms[-1][0], "ms_first_step": ms[0][3], "ms_steady": float(np.median([m[3] for m in ms[2:]]))}
+
     # ---- reduce over ranks (max time, sum pairs) ---------------------------------------------------
     tot_pairs, tot_contacts, max_wall, max_e2e = pairs, contacts, wall_ms, e2e_ms
     if world > 1:
@@ -344,6 +355,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"C3: {n}-body jittered lattice (side {args.side}), analytic spheres + OBBs, world-mode fat-AABB pairs",
                        "bodies": n, "pairs_per_step": tot_pairs, "contacts_per_step": tot_contacts,
                        "epa_fallback_pairs": getattr(ctx, "epa_fallback", None),
+                       **({"manifold_update": manifold_info} if manifold_info else {}),
                        "sharding": "pairs by sorted-leaf range, tree rebuilt per rank, one all-gather of contacts" if world > 1 else "none",
                        "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush",
                        "timing": "wall clock around K synchronous steps bracketed by barrier+synchronize, max over ranks; "
@@ -483,6 +495,7 @@ def main():
     ap.add_argument("--cpu-side", type=int, default=50, help="lattice side of the cpu_baseline sample")
     ap.add_argument("--ref-side", type=int, default=40, help="lattice side of the --impl reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--manifolds", action="store_true", help="also time pk_manifolds_update (reported under config)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"], help="c3 is the headline; c4/c5 are extra configs")
     ap.add_argument("--pairs", type=int, default=2_000_000, help="c4: number of hull pairs")
     ap.add_argument("--worlds", type=int, default=4096, help="c5: number of independent worlds")
