@@ -7,6 +7,8 @@
 //   pk::world::step(dt-scaled displacements)    ↔ the ★ calls of world::step_impl           src/world.cpp:30-46
 //   pk::world::active_pairs()                   ↔ pair_manager::active_pairs() (sorted)      collision_phases.h:54
 //   pk::world::contacts()                       ↔ one collision_info per colliding pair     collision.h:52-59
+//   pk::world::enable_manifolds / manifolds()   ↔ narrow_phase::calculate + manifolds()     collision_phases.h:244-322
+//   pk::world::collisions_began / _ended        ↔ the on_coll_beg / on_coll_end callbacks   collision_phases.h:314-318
 //   pk::make_pair_key / extract_ids             ↔ pair_manager::make_pair_key / extract_ids collision_phases.h:56-69
 //   pk::gjk_epa(a, b)                           ↔ physkit::gjk_epa                          collision.h:61-62
 //
@@ -40,6 +42,23 @@ struct collision_info // collision.h:52-59
 {
     vec3 normal{}, world_a{}, world_b{};
     double depth{};
+};
+
+struct contact_point // collision_phases.h:75-88
+{
+    vec3 normal{}, local_a{}, local_b{};
+    double depth{};
+};
+struct contact_info // manifold::contact_info, collision_phases.h:93-99
+{
+    contact_point point;
+    double normal_impulse{};
+    std::array<double, 2> tangent_impulses{};
+};
+struct manifold_info // narrow_phase::manifold_info, collision_phases.h:203-209
+{
+    std::uint32_t a{}, b{};
+    std::vector<contact_info> contacts; // 1..4 (manifold::max_contact_points)
 };
 
 constexpr std::uint64_t make_pair_key(std::uint32_t a, std::uint32_t b)
@@ -162,8 +181,50 @@ public:
         dirty_ = false;
         pk_step_result r{};
         check(pk_collide(ctx_, &r), "pk_collide");
+        if (manifolds_) check(pk_manifolds_update(ctx_, nullptr), "pk_manifolds_update");
         return r;
     }
+
+    // narrow_phase keeps a manifold per pair and merges every step's contact into it; with this switched on
+    // step() runs that merge on the device after the collision stage
+    void enable_manifolds(std::uint64_t capacity)
+    {
+        check(pk_manifolds_enable(ctx_, capacity), "pk_manifolds_enable");
+        manifolds_ = true;
+    }
+    // narrow_phase::manifolds(): the non-empty ones, sorted by pair key
+    std::vector<manifold_info> manifolds() const
+    {
+        const pk_manifold *m = nullptr;
+        std::uint64_t n = 0;
+        check(pk_manifolds(ctx_, &m, &n), "pk_manifolds");
+        std::vector<manifold_info> out(n);
+        for (std::uint64_t i = 0; i < n; ++i)
+        {
+            auto ids = extract_ids(m[i].key);
+            out[i].a = ids.first;
+            out[i].b = ids.second;
+            out[i].contacts.resize(m[i].count);
+            for (std::uint32_t j = 0; j < m[i].count; ++j)
+            {
+                const pk_manifold_point &p = m[i].points[j];
+                contact_info &c = out[i].contacts[j];
+                for (int k = 0; k < 3; ++k)
+                {
+                    c.point.normal[k] = p.normal[k];
+                    c.point.local_a[k] = p.local_a[k];
+                    c.point.local_b[k] = p.local_b[k];
+                }
+                c.point.depth = p.depth;
+                c.normal_impulse = p.normal_impulse;
+                c.tangent_impulses = {p.tangent_impulses[0], p.tangent_impulses[1]};
+            }
+        }
+        return out;
+    }
+    // keys for which the reference would have called on_coll_beg / on_coll_end in this step
+    std::vector<std::uint64_t> collisions_began() const { return events(true); }
+    std::vector<std::uint64_t> collisions_ended() const { return events(false); }
 
     std::vector<std::uint64_t> active_pairs() const
     {
@@ -210,6 +271,16 @@ public:
     }
 
     pk_ctx *native() const { return ctx_; }
+
+private:
+    std::vector<std::uint64_t> events(bool began) const
+    {
+        const std::uint64_t *b = nullptr, *e = nullptr;
+        std::uint64_t nb = 0, ne = 0;
+        check(pk_manifold_events(ctx_, &b, &nb, &e, &ne), "pk_manifold_events");
+        return began ? std::vector<std::uint64_t>(b, b + nb) : std::vector<std::uint64_t>(e, e + ne);
+    }
+    bool manifolds_ = false;
 
 private:
     template <typename F> std::uint32_t shape(F &&f)

@@ -15,13 +15,15 @@ int main()
         d.max_bodies = 64;
         d.max_pairs = 1024;
         pk::world w(d);
+        w.enable_manifolds(256);
         auto box = w.shape_box({0.5, 0.5, 0.5});
         auto a = w.create_rigid(box, {-2.0, 0.0, 0.0});
         auto b = w.create_rigid(box, {2.0, 0.0, 0.0});
         auto ground = w.create_rigid(w.shape_box({50.0, 0.5, 50.0}), {0.0, -5.0, 0.0}, {0, 0, 0, 1}, true);
         (void)ground;
         const double dt = 1.0 / 60.0, v = 3.0;
-        bool seen_pair = false, seen_contact = false;
+        bool seen_pair = false, seen_contact = false, seen_begin = false;
+        std::size_t max_points = 0;
         double xa = -2.0, xb = 2.0;
         for (int step = 0; step < 36; ++step) // stop at 0.5 m overlap: the x axis is still the unique shallowest one
         {
@@ -43,9 +45,20 @@ int main()
                 if (std::fabs(std::fabs(c.second.normal[0]) - 1.0) > 1e-9) return std::printf("FAIL: normal not along x\n"), 1;
                 seen_contact = true;
             }
+            // narrow_phase::calculate: the pair's manifold starts with on_coll_beg and gathers points as the
+            // boxes slide into each other (collision_phases.h:244-320)
+            for (auto k : w.collisions_began())
+                if (k == pk::make_pair_key(a, b)) seen_begin = true;
+            for (auto &m : w.manifolds())
+                if (pk::make_pair_key(m.a, m.b) == pk::make_pair_key(a, b))
+                {
+                    if (m.contacts.empty() || m.contacts.size() > 4) return std::printf("FAIL: manifold size\n"), 1;
+                    if (m.contacts.size() > max_points) max_points = m.contacts.size();
+                }
             xa += v * dt;
             xb -= v * dt;
         }
+        if (!seen_begin || max_points < 1) return std::printf("FAIL: manifold begin %d points %zu\n", seen_begin, max_points), 1;
         auto one = w.gjk_epa(a, b);
         if (!seen_pair || !seen_contact || !one) return std::printf("FAIL: pair %d contact %d gjk %d\n", seen_pair, seen_contact, (int)one.has_value()), 1;
         std::printf("host shim ok\n");
