@@ -130,6 +130,7 @@ struct pk_ctx
     unsigned char *d_slabs = nullptr;
     unsigned char *d_epa_spill = nullptr;
     uint32_t *d_epa_fallback = nullptr, *d_epa_fallback2 = nullptr;
+    EpaInit *d_epa_init = nullptr;
     uint32_t epa_scan_blocks = 0;
     uint32_t epa_blocks = 0;
     uint32_t gjk_blocks = 0;
@@ -376,22 +377,27 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
         // only the heap's history can break) goes first into the HEAP instance, which restates the heap and
         // then does the polyhedron pairs; what that one hands back (padded simplices, improper horizons,
         // polytopes past 768 faces: a handful) is left to epa_kernel.
+        {
+            const uint64_t most = std::min<uint64_t>(npairs, ctx->max_contacts);
+            epa_init_kernel<<<div_up(most, 128), 128, 0, ctx->stream>>>(ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
+                                                                       ctx->d_epa_init);
+        }
         epa_scan_kernel<false><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
             ctx->d_counters + C_EPA_SCAN_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr);
+            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr, ctx->d_epa_init);
         epa_scan_kernel<true><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
             ctx->d_counters + C_EPA_SCAN_CURSOR + 1, ctx->d_counters + C_VALID, ctx->d_epa_fallback2,
             ctx->d_counters + C_EPA_FALLBACK + 1, ctx->d_counters + C_CLASS_COUNT, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK);
+            ctx->d_counters + C_EPA_FALLBACK, ctx->d_epa_init);
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK + 1, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_fallback2, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
             ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID);
-        ctx->launches += 4;
+        ctx->launches += 5;
 #endif
     }
     if (timed) cudaEventRecord(ctx->ev[ST_COMPACT], ctx->stream);
@@ -457,7 +463,7 @@ int pk_destroy(pk_ctx *ctx)
                    ctx->d_merge_flag,  ctx->d_pkeys[0],     ctx->d_pkeys[1],    ctx->d_hit,          ctx->d_out_index,
                    ctx->d_scan_tiles,  ctx->d_simplices,    ctx->d_contacts[0], ctx->d_contacts[1],  ctx->d_valid,
                    ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order,    ctx->d_gjk_work,
-                   ctx->d_epa_spill,   ctx->d_epa_fallback, ctx->d_epa_fallback2};
+                   ctx->d_epa_spill,   ctx->d_epa_fallback, ctx->d_epa_fallback2, ctx->d_epa_init};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -607,6 +613,7 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
         // the two instances run one after the other and share the slab area
         A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_scan_blocks) * ES_THREADS * std::max(es_slab_bytes(false), es_slab_bytes(true)));
         A(ctx->d_epa_fallback2, nc);
+        A(ctx->d_epa_init, nc);
 #endif
         A(ctx->d_epa_fallback, nc);
     }

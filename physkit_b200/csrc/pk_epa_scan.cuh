@@ -314,11 +314,89 @@ __device__ __forceinline__ uint32_t es_heap_pop(const EsHeapRef &h, int &size)
     return top;
 }
 
+// The initial tetrahedron of every GJK hit (build_initial_tetrahedron, collision.cpp:355-388), computed by a
+// kernel of its own: four face planes and the brute-force adjacency are ≈600 instructions that all threads
+// execute in step here, instead of a divergent set-up path that stalls a warp of epa_scan_kernel every time
+// one of its lanes starts a pair.
+struct alignas(16) EpaInit
+{
+    double plane[4][4];         // normal xyz, distance of faces (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0)
+    unsigned long long topo[4]; // vertices (flipped where the normal faced the opposite vertex), neighbours, serial
+    uint32_t bad;               // a distance is NaN / inf: not for the heap-free path
+    uint32_t _pad[3];
+};
+static_assert(sizeof(EpaInit) == 176, "EpaInit layout");
+
+__global__ void __launch_bounds__(128)
+epa_init_kernel(const SimplexRec *__restrict__ simplices, const unsigned long long *__restrict__ hit_count_ptr, uint64_t hit_capacity,
+                EpaInit *__restrict__ init)
+{
+    const uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    unsigned long long nhits = *hit_count_ptr;
+    if (nhits > hit_capacity) nhits = hit_capacity;
+    if (s >= nhits) return;
+    const SimplexRec *r = simplices + s;
+    if ((r->n & 0xFFu) != 4u) return; // padded simplices are set up by epa_kernel
+    d3 pv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        SupportPt sp;
+        sp.pa = d3{r->v[i][0], r->v[i][1], r->v[i][2]};
+        sp.pb = d3{r->v[i][3], r->v[i][4], r->v[i][5]};
+        pv[i] = P(sp);
+    }
+    EpaInit o;
+    uint32_t tv[4]; // vertex triples, one byte each
+    bool bad = false;
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+    {
+        bool flip;
+        const double4 pl = es_face_plane(pv[fi4(f)], pv[fj4(f)], pv[fk4(f)], true, pv[fo4(f)], flip);
+        tv[f] = static_cast<uint32_t>(fi4(f)) | (static_cast<uint32_t>(flip ? fk4(f) : fj4(f)) << 8) |
+                (static_cast<uint32_t>(flip ? fj4(f) : fk4(f)) << 16);
+        o.plane[f][0] = pl.x;
+        o.plane[f][1] = pl.y;
+        o.plane[f][2] = pl.z;
+        o.plane[f][3] = pl.w;
+        if (!(fabs(pl.w) < 1e30)) bad = true; // NaN / inf: the key order would not be the heap's
+    }
+    // brute-force adjacency (collision.cpp:373-388).  An undirected tetrahedron edge belongs to exactly two
+    // faces, so a directed edge has at most one reversed partner and the reference's i<j visiting order
+    // cannot matter: each face looks its three partners up independently.
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+    {
+        unsigned long long w = tv[f];
+#pragma unroll
+        for (int e1 = 0; e1 < 3; ++e1)
+        {
+            const uint32_t u1 = (tv[f] >> (8 * e1)) & 0xFFu, v1 = (tv[f] >> (8 * ((e1 + 1) % 3))) & 0xFFu;
+            unsigned long long adj = 0xFFull;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const uint32_t q = tv[j];
+                const bool m = (j != f) && (((q & 0xFFu) == v1 && ((q >> 8) & 0xFFu) == u1) ||
+                                            (((q >> 8) & 0xFFu) == v1 && ((q >> 16) & 0xFFu) == u1) ||
+                                            (((q >> 16) & 0xFFu) == v1 && (q & 0xFFu) == u1));
+                if (m) adj = static_cast<unsigned long long>(j);
+            }
+            w |= adj << (24 + 8 * e1);
+        }
+        o.topo[f] = w | (static_cast<unsigned long long>(f) << 48); // creation serial
+    }
+    o.bad = bad ? 1u : 0u;
+    o._pad[0] = o._pad[1] = o._pad[2] = 0;
+    init[s] = o;
+}
+
 #ifndef PK_ES_MIN_BLOCKS
 #define PK_ES_MIN_BLOCKS 4
 #endif
 #ifndef PK_ES_FETCH_MIN
-#define PK_ES_FETCH_MIN 12
+#define PK_ES_FETCH_MIN 6
 #endif
 
 // The hit list is grouped by cost class (order[]: sphere–sphere, sphere–polyhedron, polyhedron–polyhedron);
@@ -336,7 +414,8 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 uint8_t *__restrict__ valid, unsigned char *__restrict__ slabs, unsigned long long *__restrict__ cursor,
                 unsigned long long *__restrict__ counters /* [0]=valid contacts */, uint32_t *__restrict__ fallback_list,
                 unsigned long long *__restrict__ fallback_count, const unsigned long long *__restrict__ class_count,
-                const uint32_t *__restrict__ leftovers, const unsigned long long *__restrict__ leftover_count)
+                const uint32_t *__restrict__ leftovers, const unsigned long long *__restrict__ leftover_count,
+                const EpaInit *__restrict__ init)
 {
     // Work of the HEAP instance: first the pairs the SCAN instance handed back (leftovers[], complete at
     // launch: mostly sphere–sphere pairs with an exact distance tie, long ones — started first so that
@@ -478,15 +557,14 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                         es_put_shape(shm, 0, A, bodies);
                         es_put_shape(shm, 1, B, bodies);
                     }
-                    d3 pv[4];
+                    const EpaInit *in = init + cur_sidx; // epa_init_kernel: planes and topology of the tetrahedron
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                     {
                         SupportPt s;
                         s.pa = d3{r->v[i][0], r->v[i][1], r->v[i][2]};
                         s.pb = d3{r->v[i][3], r->v[i][4], r->v[i][5]};
-                        pv[i] = P(s);
-                        sl.set_vert(i, s, pv[i]);
+                        sl.set_vert(i, s, P(s));
                     }
                     if constexpr (!HEAP)
                     {
@@ -501,55 +579,24 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                     else
                         keys_dirty = true;
                     heap_size = 0;
-                    // build_initial_tetrahedron (collision.cpp:355-388): faces (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0)
-                    uint32_t tv[4]; // vertex triples, one byte each
-                    bool bad = false;
+                    const bool bad = in->bad != 0u;
 #pragma unroll
                     for (int f = 0; f < 4; ++f)
                     {
-                        bool flip;
-                        const double4 pl = es_face_plane(pv[fi4(f)], pv[fj4(f)], pv[fk4(f)], true, pv[fo4(f)], flip);
-                        const d3 n{pl.x, pl.y, pl.z};
-                        const double dist = pl.w;
-                        tv[f] = static_cast<uint32_t>(fi4(f)) | (static_cast<uint32_t>(flip ? fk4(f) : fj4(f)) << 8) |
-                                (static_cast<uint32_t>(flip ? fj4(f) : fk4(f)) << 16);
-                        sl.store_plane(f, n, dist);
-                        if (!(fabs(dist) < 1e30)) bad = true; // NaN / inf: the key order would not be the heap's
+                        const double2 *q = reinterpret_cast<const double2 *>(in->plane[f]);
+                        const double2 n01 = q[0], n2d = q[1];
+                        sl.store_plane(f, d3{n01.x, n01.y, n2d.x}, n2d.y);
+                        sl.topo[f] = in->topo[f];
                         if constexpr (HEAP)
                         {
-                            es_sift_up(hp, heap_size, dist, static_cast<uint32_t>(f) | (static_cast<uint32_t>(f) << 8)); // push_face
+                            es_sift_up(hp, heap_size, n2d.y, static_cast<uint32_t>(f) | (static_cast<uint32_t>(f) << 8)); // push_face
                             ++heap_size;
                         }
                         else
                         {
-                            shm.pop.th[t].key[f] = __double2float_rd(dist);
-                            shm.hz[f][t] = static_cast<uint32_t>(f) << 24; // push order of this batch (zero-distance ties)
+                            shm.pop.th[t].key[f] = __double2float_rd(n2d.y);
+                            shm.hz[f][t] = static_cast<uint32_t>(f) << 24; // push order of this batch (tie breaking)
                         }
-                    }
-                    // brute-force adjacency (collision.cpp:373-388).  An undirected tetrahedron edge belongs to
-                    // exactly two faces, so a directed edge has at most one reversed partner and the reference's
-                    // i<j visiting order cannot matter: each face looks its three partners up independently.
-#pragma unroll
-                    for (int f = 0; f < 4; ++f)
-                    {
-                        unsigned long long w = tv[f];
-#pragma unroll
-                        for (int e1 = 0; e1 < 3; ++e1)
-                        {
-                            const uint32_t u1 = (tv[f] >> (8 * e1)) & 0xFFu, v1 = (tv[f] >> (8 * ((e1 + 1) % 3))) & 0xFFu;
-                            unsigned long long adj = 0xFFull;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                            {
-                                const uint32_t o = tv[j];
-                                const bool m = (j != f) && (((o & 0xFFu) == v1 && ((o >> 8) & 0xFFu) == u1) ||
-                                                            (((o >> 8) & 0xFFu) == v1 && ((o >> 16) & 0xFFu) == u1) ||
-                                                            (((o >> 16) & 0xFFu) == v1 && (o & 0xFFu) == u1));
-                                if (m) adj = static_cast<unsigned long long>(j);
-                            }
-                            w |= adj << (24 + 8 * e1);
-                        }
-                        sl.topo[f] = w | (static_cast<unsigned long long>(f) << 48); // creation serial
                     }
                     fm0 = ~0xFull;
                     fm1 = ~0ull;
