@@ -96,6 +96,18 @@ typedef struct pk_contact_point
     double local_b[3];
 } pk_contact_point;
 
+/* One entry of a world ray cast: what world_base::raycast yields (core/world.h:260-319, a pair of body
+ * handle and distance), tagged with the ray of the batch it belongs to. */
+typedef struct pk_ray_hit
+{
+    uint32_t ray;
+    uint32_t body;
+    double distance; /* ray::intersect_distance of the body's stored box (bvh.h:59-98): 0 when the origin is inside */
+} pk_ray_hit;
+
+#define PK_RAY_ALL 0     /* every body whose stored box the ray enters within max_distance */
+#define PK_RAY_CLOSEST 1 /* per ray the entry with the smallest distance, lowest body id among equals */
+
 /* Contact manifolds: narrow_phase's per-pair state (collision_phases.h:90-327).  A point is
  * manifold::contact_info = contact_point {normal, local_a, local_b, depth} + the solver's cached impulses. */
 typedef struct pk_manifold_point
@@ -194,6 +206,21 @@ int pk_contacts(pk_ctx *ctx, const pk_contact **recs, uint64_t *n);
  * (narrow_phase::calculate → contact_point, collision_phases.h:257-263).  Computed on the device on request
  * from the poses of that step; the host pointer stays valid until the next pk_collide*. */
 int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n);
+/* ---- ray casts --------------------------------------------------------------------------
+ * Replaces world_base::raycast(ray, max_dist) (core/world.h:260-319), i.e. dynamic_bvh::raycast (bvh.h:346-450)
+ * over the static and the dynamic tree, for a batch of rays against the tree of the LAST step (call after
+ * pk_collide / pk_collide_resident; PK_E_STATE otherwise).  origins / directions are nrays xyz triples in host
+ * memory (directions need not be normalised: the ray constructor does that, bvh.h:47-50), max_distance one
+ * value per ray, world the ray's world in a batched context (NULL: world 0).  The reference yields its
+ * entries in an order that depends on the shape of its trees; here they come sorted by (ray, body), with
+ * bit-identical distances.  PK_RAY_CLOSEST is the closest-leaf search a caller builds from the callback form
+ * (bvh.h:346-398) by returning the entry distance as the new max_distance.
+ * hits receives at most `capacity` records; *nhits is the number found.  PK_E_PAIR_OVERFLOW: nothing was
+ * written, *nhits is the capacity to retry with.  capacity may not exceed max(max_bodies, max_pairs). */
+int pk_raycast(pk_ctx *ctx, const double *origins, const double *directions, const double *max_distance, const uint32_t *world,
+               uint32_t nrays, int mode, pk_ray_hit *hits, uint64_t capacity, uint64_t *nhits);
+/* Device time of the last pk_raycast (traversal + sort + gather, without the copies), CUDA events. */
+int pk_raycast_device_ms(pk_ctx *ctx, float *ms);
 /* ---- manifolds (optional) -------------------------------------------------------------
  * narrow_phase::calculate merges each pair's new contact into the manifold it kept from the last step: warm
  * start of a point found at the same place, drift / breaking test of the old points under the new poses,

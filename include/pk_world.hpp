@@ -24,6 +24,7 @@
 
 #include "pk_collide.h"
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <optional>
@@ -250,6 +251,26 @@ public:
             }
             out[i].second.depth = c[i].depth;
         }
+        return out;
+    }
+
+    // world_base::raycast(ray, max_dist) (core/world.h:260-319): every body whose stored box the ray enters within
+    // max_dist, with the entry distance, ordered by (distance, handle).  (The reference yields each tree's
+    // entries in traversal order and merges the two streams by distance.)
+    std::vector<std::pair<handle, double>> raycast(const vec3 &origin, const vec3 &direction, double max_dist) const
+    {
+        std::vector<pk_ray_hit> buf(64);
+        std::uint64_t n = 0;
+        int s = pk_raycast(ctx_, origin.data(), direction.data(), &max_dist, nullptr, 1, PK_RAY_ALL, buf.data(), buf.size(), &n);
+        if (s == PK_E_PAIR_OVERFLOW)
+        {
+            buf.resize(n);
+            s = pk_raycast(ctx_, origin.data(), direction.data(), &max_dist, nullptr, 1, PK_RAY_ALL, buf.data(), buf.size(), &n);
+        }
+        check(s, "pk_raycast");
+        std::vector<std::pair<handle, double>> out(n);
+        for (std::uint64_t i = 0; i < n; ++i) out[i] = {buf[i].body, buf[i].distance};
+        std::sort(out.begin(), out.end(), [](const auto &a, const auto &b) { return a.second < b.second || (a.second == b.second && a.first < b.first); });
         return out;
     }
 

@@ -105,6 +105,13 @@ def lib():
         L.pko_brute_pairs.argtypes = [vp, u64, vp, u64]
         L.pko_brute_pairs.restype = u64
         L.pko_max_threads.restype = i32
+        f64 = C.c_double
+        L.pko_ray_box.argtypes = [vp, vp, vp, f64, vp]
+        L.pko_ray_box.restype = i32
+        L.pko_bvh_raycast.argtypes = [vp, vp, vp, f64, i32, vp, vp, u64]
+        L.pko_bvh_raycast.restype = u64
+        L.pko_world_raycast.argtypes = [vp, vp, vp, f64, vp, vp, u64]
+        L.pko_world_raycast.restype = u64
         _lib = L
     return _lib
 
@@ -243,6 +250,13 @@ def brute_pairs(boxes6):
     return out
 
 
+def ray_box(origin, direction, box6, max_distance):
+    """ray::intersect_distance (bvh.h:59-98): distance or None."""
+    out = np.empty(1)
+    hit = lib().pko_ray_box(_p(_f64(origin, (3,))), _p(_f64(direction, (3,))), _p(_f64(box6, (6,))), float(max_distance), _p(out))
+    return float(out[0]) if hit else None
+
+
 def max_threads():
     return int(lib().pko_max_threads())
 
@@ -277,6 +291,16 @@ class DynamicBVH:
 
     def validate(self):
         return bool(lib().pko_bvh_validate(self.h))
+
+    def raycast(self, origin, direction, max_distance, closest=False, cap=1 << 16):
+        """dynamic_bvh::raycast (bvh.h:346-450): (ids, distances) in traversal order; closest=True drives the
+        callback form as a closest-leaf search (the last entry is the closest leaf)."""
+        ids = np.empty(cap, dtype=np.uint32)
+        d = np.empty(cap, dtype=np.float64)
+        n = lib().pko_bvh_raycast(self.h, _p(_f64(origin, (3,))), _p(_f64(direction, (3,))), float(max_distance), int(closest),
+                                  _p(ids), _p(d), cap)
+        n = min(n, cap)
+        return ids[:n].copy(), d[:n].copy()
 
     def query_aabb(self, box6, stop_after=0, cap=1 << 16):
         out = np.empty(cap, dtype=np.uint32)
@@ -315,6 +339,14 @@ class World:
         out = np.empty(6)
         lib().pko_world_stored(self.h, int(body), _p(out))
         return out
+
+    def raycast(self, origin, direction, max_distance, cap=1 << 16):
+        """world_base::raycast (core/world.h:260-319): (body ids, distances), merged by distance."""
+        ids = np.empty(cap, dtype=np.uint32)
+        d = np.empty(cap, dtype=np.float64)
+        n = lib().pko_world_raycast(self.h, _p(_f64(origin, (3,))), _p(_f64(direction, (3,))), float(max_distance), _p(ids), _p(d), cap)
+        n = min(n, cap)
+        return ids[:n].copy(), d[:n].copy()
 
 
 class Manifolds:

@@ -133,6 +133,35 @@ struct aabb
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// ray — include/physkit/collision/bvh.h:22-98 (slab test only; the triangle test is not on the path)
+// ---------------------------------------------------------------------------------------------
+inline double safe_inv(double x) { return 1.0 / x; } // bvh.h:27-35, IEC 559 branch: ±0 → ±inf
+
+struct ray
+{
+    v3 origin, direction;
+    ray(v3 o, v3 d) : origin(o), direction(normalized(d)) {} // bvh.h:47-50
+
+    // bvh.h:59-98.  0·inf = NaN is replaced by the limit (−inf for the near plane, +inf for the far one).
+    std::optional<double> intersect_distance(const aabb &box, double max_distance) const
+    {
+        auto slab = [](double lo, double hi)
+        {
+            if (std::isnan(lo)) lo = -std::numeric_limits<double>::infinity();
+            if (std::isnan(hi)) hi = std::numeric_limits<double>::infinity();
+            return std::pair{std::fmin(lo, hi), std::fmax(lo, hi)};
+        };
+        auto [tminx, tmaxx] = slab((box.min.x - origin.x) * safe_inv(direction.x), (box.max.x - origin.x) * safe_inv(direction.x));
+        auto [tminy, tmaxy] = slab((box.min.y - origin.y) * safe_inv(direction.y), (box.max.y - origin.y) * safe_inv(direction.y));
+        auto [tminz, tmaxz] = slab((box.min.z - origin.z) * safe_inv(direction.z), (box.max.z - origin.z) * safe_inv(direction.z));
+        double tmin = std::max({tminx, tminy, tminz});
+        double tmax = std::min({tmaxx, tmaxy, tmaxz});
+        if (tmax >= 0.0 && tmin <= tmax && tmin <= max_distance) return std::max(0.0, tmin);
+        return std::nullopt;
+    }
+};
+
 // bounds.h:94-102
 inline aabb aabb_union(const aabb &a, const aabb &b)
 {
@@ -973,6 +1002,64 @@ public:
         }
     }
 
+    // bvh.h:346-398 — callback form: callback(data, d_node, max_distance) returns the new max distance,
+    // ≤ 0 ends the cast.  Nearer child visited first.
+    template <typename F> void raycast(const ray &r, double max_distance, F &&callback) const
+    {
+        if (M_root == null) return;
+        std::array<uint32_t, stack_size> stack{};
+        int sp = 0;
+        stack[sp++] = M_root;
+        while (sp > 0)
+        {
+            uint32_t idx = stack[--sp];
+            const node &n = M_nodes[idx];
+            auto d_node = r.intersect_distance(n.bounds, max_distance);
+            if (!d_node.has_value()) continue;
+            if (n.is_leaf())
+            {
+                max_distance = callback(n.data, *d_node, max_distance);
+                if (max_distance <= 0.0) return;
+                continue;
+            }
+            assert(sp + 1 < static_cast<int>(stack_size));
+            uint32_t left = n.children.left, right = n.children.right;
+            auto d_left = r.intersect_distance(M_nodes[left].bounds, max_distance);
+            auto d_right = r.intersect_distance(M_nodes[right].bounds, max_distance);
+            if (d_left && d_right)
+            {
+                if (*d_left > *d_right)
+                {
+                    stack[sp++] = left;
+                    stack[sp++] = right;
+                }
+                else
+                {
+                    stack[sp++] = right;
+                    stack[sp++] = left;
+                }
+            }
+            else if (d_left)
+                stack[sp++] = left;
+            else if (d_right)
+                stack[sp++] = right;
+        }
+    }
+
+    // bvh.h:400-450 — generator form: every leaf whose box the ray enters within max_distance, in the
+    // order the coroutine yields them (same traversal, max_distance fixed).
+    std::vector<std::pair<uint32_t, double>> raycast(const ray &r, double max_distance) const
+    {
+        std::vector<std::pair<uint32_t, double>> out;
+        raycast(r, max_distance,
+                [&](uint32_t data, double d, double md)
+                {
+                    out.emplace_back(data, d);
+                    return md > 0.0 ? md : std::numeric_limits<double>::min(); // the generator never stops early
+                });
+        return out;
+    }
+
     const aabb &bounds(uint32_t leaf) const { return M_nodes[leaf].bounds; }
     uint32_t data(uint32_t leaf) const { return M_nodes[leaf].data; }
     uint32_t root() const { return M_root; }
@@ -1307,6 +1394,26 @@ public:
     {
         handle h = M_handles[object_id];
         return h.is_static ? M_static.bounds(h.node) : M_dynamic.bounds(h.node);
+    }
+
+    // world_base::raycast (core/world.h:260-319): the static and the dynamic tree's streams merged by
+    // distance, the static entry first on equal distances.
+    std::vector<std::pair<uint32_t, double>> raycast(const ray &r, double max_dist) const
+    {
+        auto st = M_static.raycast(r, max_dist);
+        auto dy = M_dynamic.raycast(r, max_dist);
+        std::vector<std::pair<uint32_t, double>> out;
+        std::size_t i = 0, j = 0;
+        while (i < st.size() && j < dy.size())
+        {
+            if (st[i].second <= dy[j].second)
+                out.push_back(st[i++]);
+            else
+                out.push_back(dy[j++]);
+        }
+        while (i < st.size()) out.push_back(st[i++]);
+        while (j < dy.size()) out.push_back(dy[j++]);
+        return out;
     }
 
     std::vector<uint64_t> sorted_pairs() const

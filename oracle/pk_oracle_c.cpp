@@ -331,6 +331,51 @@ uint64_t pko_bvh_query(void *t, const double *box6, uint32_t *out, uint64_t cap,
     return n;
 }
 
+// ------------------------------- ray casts --------------------------------------
+// ray::intersect_distance (bvh.h:59-98).  dir3 is normalised by the ray constructor.  Returns 1 on a hit.
+int pko_ray_box(const double *origin3, const double *dir3, const double *box6, double max_distance, double *dist_out)
+{
+    ray r(ld3(origin3), ld3(dir3));
+    auto d = r.intersect_distance(aabb{ld3(box6), ld3(box6 + 3)}, max_distance);
+    if (d && dist_out) *dist_out = *d;
+    return d ? 1 : 0;
+}
+// dynamic_bvh::raycast.  closest = 0: generator form (bvh.h:400-450), every entered leaf in yield order.
+// closest = 1: callback form (bvh.h:346-398) driven as a closest-leaf search: the callback shrinks
+// max_distance to the entry distance of the leaf it was given.
+// closest = 2: callback form, the callback returns 0 m: the cast ends after the first leaf (bvh.h:372).
+uint64_t pko_bvh_raycast(void *t, const double *origin3, const double *dir3, double max_distance, int closest, uint32_t *ids,
+                         double *dists, uint64_t cap)
+{
+    const dynamic_bvh &tree = *static_cast<dynamic_bvh *>(t);
+    ray r(ld3(origin3), ld3(dir3));
+    if (!closest)
+    {
+        auto v = tree.raycast(r, max_distance);
+        for (uint64_t i = 0; i < v.size() && i < cap; ++i)
+        {
+            ids[i] = v[i].first;
+            dists[i] = v[i].second;
+        }
+        return v.size();
+    }
+    uint64_t n = 0;
+    tree.raycast(r, max_distance,
+                 [&](uint32_t id, double d, double md)
+                 {
+                     if (n < cap)
+                     {
+                         ids[n] = id;
+                         dists[n] = d;
+                     }
+                     ++n;
+                     (void)md;
+                     if (closest == 2) return 0.0;
+                     return d > 0.0 ? d : std::numeric_limits<double>::min(); // 0 would end the cast (bvh.h:372)
+                 });
+    return n;
+}
+
 // ------------------------------- broad_phase handle API ---------------------------------------
 void *pko_bp_create() { return new broad_phase(); }
 void pko_bp_destroy(void *b) { delete static_cast<broad_phase *>(b); }
@@ -424,6 +469,20 @@ uint64_t pko_world_pairs(void *wp, uint64_t *out, uint64_t cap)
 void pko_world_stored(void *wp, uint32_t id, double *out6)
 {
     pko_bp_stored(&static_cast<pko_world *>(wp)->bp, id, out6);
+}
+
+// world_base::raycast (core/world.h:260-319) over the world's two trees, merged by distance.
+uint64_t pko_world_raycast(void *wp, const double *origin3, const double *dir3, double max_distance, uint32_t *ids, double *dists,
+                           uint64_t cap)
+{
+    ray r(ld3(origin3), ld3(dir3));
+    auto v = static_cast<pko_world *>(wp)->bp.raycast(r, max_distance);
+    for (uint64_t i = 0; i < v.size() && i < cap; ++i)
+    {
+        ids[i] = v[i].first;
+        dists[i] = v[i].second;
+    }
+    return v.size();
 }
 
 // ------------------------------- static-pose ("query") mode -----------------------------------

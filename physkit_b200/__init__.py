@@ -7,10 +7,13 @@ no CPU implementation of anything and raises if the library or a CUDA device is 
 from .api import (  # noqa: F401
     MODE_QUERY,
     MODE_WORLD,
+    RAY_ALL,
+    RAY_CLOSEST,
     CollisionWorld,
     Context,
     PkError,
     contact_dtype,
+    ray_hit_dtype,
     gjk_epa,
     library_path,
     load_library,

@@ -27,6 +27,9 @@ contact_dtype = np.dtype(
     [("key", np.uint64), ("normal", np.float64, 3), ("world_a", np.float64, 3), ("world_b", np.float64, 3), ("depth", np.float64)]
 )
 assert contact_dtype.itemsize == 88
+ray_hit_dtype = np.dtype([("ray", np.uint32), ("body", np.uint32), ("distance", np.float64)])
+assert ray_hit_dtype.itemsize == 16
+RAY_ALL, RAY_CLOSEST = 0, 1
 
 
 class PkError(RuntimeError):
@@ -89,7 +92,7 @@ EXPORTS = [
     "pk_bodies_resize", "pk_bodies_upload", "pk_bodies_update_pose",
     "pk_collide_resident", "pk_fetch_results", "pk_collide", "pk_pairs", "pk_contacts",
     "pk_pairs_device", "pk_contacts_device", "pk_stored_bounds", "pk_stage_times_get", "pk_stream",
-    "pk_gjk_epa_batch", "pk_gjk_epa_batch_device",
+    "pk_gjk_epa_batch", "pk_gjk_epa_batch_device", "pk_raycast", "pk_raycast_device_ms",
     "pk_device_alloc", "pk_device_free", "pk_memcpy_h2d", "pk_memcpy_d2h", "pk_memcpy_d2d", "pk_host_alloc", "pk_host_free",
 ]
 
@@ -114,6 +117,8 @@ def load_library():
     L.pk_create.argtypes = [vp, vp]
     L.pk_selftest_division.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     L.pk_contact_points.argtypes = [vp, vp, vp]
+    L.pk_raycast.argtypes = [vp, vp, vp, vp, vp, u32, i32, vp, u64, vp]
+    L.pk_raycast_device_ms.argtypes = [vp, vp]
     L.pk_manifolds_enable.argtypes = [vp, C.c_uint64]
     L.pk_manifolds_update.argtypes = [vp, vp]
     L.pk_manifolds.argtypes = [vp, vp, vp]
@@ -338,6 +343,33 @@ class Context:
             return np.zeros((0, 6))
         buf = (C.c_double * (6 * n.value)).from_address(p.value)
         return np.frombuffer(buf, dtype=np.float64).reshape(-1, 6).copy()
+
+    # -- ray casts over the tree of the last step (world_base::raycast, core/world.h:260-319)
+    def raycast(self, origins, directions, max_distance, world=None, mode=RAY_ALL, capacity=None):
+        """Batch of rays → structured array (ray, body, distance) sorted by (ray, body).  Grows the result
+        buffer and retries once when the library reports the capacity it needs."""
+        o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+        n = len(o)
+        assert len(d) == n
+        md = np.ascontiguousarray(np.broadcast_to(np.asarray(max_distance, dtype=np.float64), (n,)))
+        w = None if world is None else np.ascontiguousarray(world, dtype=np.uint32)
+        cap = int(capacity) if capacity is not None else max(4 * n, 1024)
+        for _ in range(2):
+            out = np.empty(cap, dtype=ray_hit_dtype)
+            found = C.c_uint64()
+            st = self.L.pk_raycast(self.h, _p(o), _p(d), _p(md), _p(w), n, int(mode), _p(out), cap, C.byref(found))
+            if st == PK_E_PAIR_OVERFLOW and capacity is None:
+                cap = int(found.value)
+                continue
+            self._check(st)
+            return out[: found.value].copy()
+        self._check(st)
+
+    def raycast_device_ms(self):
+        ms = C.c_float()
+        self._check(self.L.pk_raycast_device_ms(self.h, C.byref(ms)))
+        return float(ms.value)
 
     # -- manifolds (narrow_phase state on the device)
     def manifolds_enable(self, capacity):

@@ -11,6 +11,7 @@
 #include "pk_narrowphase.cuh"
 #include "pk_epa_scan.cuh"
 #include "pk_manifold.cuh"
+#include "pk_ray.cuh"
 #include "pk_sort.cuh"
 
 #include <algorithm>
@@ -162,6 +163,19 @@ struct pk_ctx
     ContactPointRec *d_points = nullptr; // pk_contact_points: allocated on first use
     pk_contact_point *h_points = nullptr;
     size_t points_cap = 0;
+
+    // ray casts (pk_raycast): buffers allocated on first use
+    uint32_t tree_m = 0;      // leaves of the tree the last step built (0: none, < 2 bodies alive)
+    bool tree_valid = false;  // a step has run since the context was created
+    double *d_ray_o = nullptr, *d_ray_d = nullptr, *d_ray_max = nullptr, *d_ray_dist = nullptr;
+    uint32_t *d_ray_world = nullptr;
+    size_t ray_cap = 0, ray_hit_cap = 0;
+    uint64_t *d_ray_keys[2] = {nullptr, nullptr};
+    uint32_t *d_ray_src[2] = {nullptr, nullptr};
+    RayHitRec *d_ray_hits = nullptr;
+    unsigned long long *d_ray_counter = nullptr;
+    cudaEvent_t ev_ray[2]{};
+    float ray_ms = 0.f;
 
     cudaEvent_t ev[ST_COUNT + 1]{};
     float stage_ms[ST_COUNT]{};
@@ -480,6 +494,13 @@ int pk_destroy(pk_ctx *ctx)
     }
     if (ctx->d_points) cudaFree(ctx->d_points);
     if (ctx->h_points) cudaFreeHost(ctx->h_points);
+    for (void *q : {static_cast<void *>(ctx->d_ray_o), static_cast<void *>(ctx->d_ray_d), static_cast<void *>(ctx->d_ray_max),
+                    static_cast<void *>(ctx->d_ray_world), static_cast<void *>(ctx->d_ray_keys[0]), static_cast<void *>(ctx->d_ray_keys[1]),
+                    static_cast<void *>(ctx->d_ray_src[0]), static_cast<void *>(ctx->d_ray_src[1]), static_cast<void *>(ctx->d_ray_dist),
+                    static_cast<void *>(ctx->d_ray_hits), static_cast<void *>(ctx->d_ray_counter)})
+        if (q) cudaFree(q);
+    for (auto &e : ctx->ev_ray)
+        if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->copy_stream)
@@ -825,6 +846,8 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         ctx->launches += 1;
     }
     cudaEventRecord(ctx->ev[ST_MORTON], s);
+    ctx->tree_m = 0;
+    ctx->tree_valid = true;
     uint64_t npairs = 0;
     int pair_buf = 0;
     if (m >= 2)
@@ -842,6 +865,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         hierarchy_kernel<<<div_up(m, 256), 256, 0, s>>>(ctx->d_bkeys[bres], m, ctx->d_nodes, ctx->d_right, ctx->d_range_last,
                                                         ctx->d_merge_flag, ctx->d_root);
         rope_kernel<<<div_up(2ull * m - 1, 256), 256, 0, s>>>(m, ctx->d_nodes, ctx->d_right, ctx->d_range_last);
+        ctx->tree_m = m;
         cudaEventRecord(ctx->ev[ST_OVERLAP], s);
         uint32_t p_begin = static_cast<uint32_t>(static_cast<uint64_t>(m) * ctx->cfg.shard_rank / ctx->cfg.shard_count);
         uint32_t p_end = static_cast<uint32_t>(static_cast<uint64_t>(m) * (ctx->cfg.shard_rank + 1) / ctx->cfg.shard_count);
@@ -1055,6 +1079,130 @@ int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n)
     }
     *pts = ctx->h_points;
     *n = m;
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ ray casts
+int pk_raycast(pk_ctx *ctx, const double *origins, const double *directions, const double *max_distance, const uint32_t *world,
+               uint32_t nrays, int mode, pk_ray_hit *hits, uint64_t capacity, uint64_t *nhits)
+{
+    if (!ctx || !nhits || (nrays && (!origins || !directions || !max_distance)) || (capacity && !hits)) return PK_E_INVALID;
+    if (mode != PK_RAY_ALL && mode != PK_RAY_CLOSEST) return PK_E_INVALID;
+    if (!ctx->tree_valid)
+    {
+        ctx->last_error = "pk_raycast needs the tree of a step: call pk_collide / pk_collide_resident first";
+        return PK_E_STATE;
+    }
+    static_assert(sizeof(RayHitRec) == sizeof(pk_ray_hit), "ray hit layouts differ");
+    cudaSetDevice(ctx->cfg.device);
+    *nhits = 0;
+    if (nrays == 0) return PK_OK;
+    if (static_cast<size_t>(div_up(std::max<uint64_t>(capacity, 1), SORT_TILE)) * 256 > ctx->tile_hist_entries)
+    {
+        ctx->last_error = "pk_raycast: capacity exceeds max(max_bodies, max_pairs) of the context";
+        return PK_E_INVALID;
+    }
+    cudaStream_t s = ctx->stream;
+    if (!ctx->ev_ray[0])
+    {
+        PK_CUDA(cudaEventCreate(&ctx->ev_ray[0]));
+        PK_CUDA(cudaEventCreate(&ctx->ev_ray[1]));
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_counter, 1));
+    }
+    if (nrays > ctx->ray_cap)
+    {
+        for (void *p : {static_cast<void *>(ctx->d_ray_o), static_cast<void *>(ctx->d_ray_d), static_cast<void *>(ctx->d_ray_max),
+                        static_cast<void *>(ctx->d_ray_world)})
+            if (p) cudaFree(p);
+        ctx->d_ray_o = ctx->d_ray_d = ctx->d_ray_max = nullptr;
+        ctx->d_ray_world = nullptr;
+        ctx->ray_cap = 0;
+        const size_t cap = std::max<size_t>(static_cast<size_t>(nrays) * 5 / 4, 1024);
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_o, 3 * cap));
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_d, 3 * cap));
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_max, cap));
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_world, cap));
+        ctx->ray_cap = cap;
+    }
+    if (capacity > ctx->ray_hit_cap)
+    {
+        for (void *p : {static_cast<void *>(ctx->d_ray_keys[0]), static_cast<void *>(ctx->d_ray_keys[1]), static_cast<void *>(ctx->d_ray_src[0]),
+                        static_cast<void *>(ctx->d_ray_src[1]), static_cast<void *>(ctx->d_ray_dist), static_cast<void *>(ctx->d_ray_hits)})
+            if (p) cudaFree(p);
+        ctx->d_ray_keys[0] = ctx->d_ray_keys[1] = nullptr;
+        ctx->d_ray_src[0] = ctx->d_ray_src[1] = nullptr;
+        ctx->d_ray_dist = nullptr;
+        ctx->d_ray_hits = nullptr;
+        ctx->ray_hit_cap = 0;
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_keys[0], capacity));
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_keys[1], capacity));
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_src[0], capacity));
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_src[1], capacity));
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_dist, capacity));
+        PK_TRY(dev_alloc(ctx, &ctx->d_ray_hits, capacity));
+        ctx->ray_hit_cap = capacity;
+    }
+    PK_CUDA(cudaMemcpyAsync(ctx->d_ray_o, origins, 3ull * nrays * sizeof(double), cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(ctx->d_ray_d, directions, 3ull * nrays * sizeof(double), cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(ctx->d_ray_max, max_distance, static_cast<size_t>(nrays) * sizeof(double), cudaMemcpyHostToDevice, s));
+    const bool worlds = ctx->cfg.num_worlds > 1 && ctx->have_world;
+    if (worlds && world)
+        PK_CUDA(cudaMemcpyAsync(ctx->d_ray_world, world, static_cast<size_t>(nrays) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    else if (worlds)
+        PK_CUDA(cudaMemsetAsync(ctx->d_ray_world, 0, static_cast<size_t>(nrays) * sizeof(uint32_t), s));
+    PK_CUDA(cudaMemsetAsync(ctx->d_ray_counter, 0, sizeof(unsigned long long), s));
+    WorldTiling wt;
+    wt.num_worlds = worlds ? ctx->cfg.num_worlds : 1;
+    wt.grid = 1;
+    while (static_cast<uint64_t>(wt.grid) * wt.grid * wt.grid < wt.num_worlds) ++wt.grid;
+    cudaEventRecord(ctx->ev_ray[0], s);
+    if (ctx->tree_m >= 2)
+        ray_cast_kernel<<<div_up(nrays, RAY_THREADS), RAY_THREADS, 0, s>>>(ctx->d_nodes, ctx->d_leaves, ctx->tree_m, ctx->d_root, ctx->d_ray_o,
+                                                                          ctx->d_ray_d, ctx->d_ray_max, worlds ? ctx->d_ray_world : nullptr,
+                                                                          nrays, mode, wt, ctx->d_scene, ctx->d_ray_keys[0], ctx->d_ray_dist,
+                                                                          ctx->d_ray_src[0], capacity, ctx->d_ray_counter);
+    else
+        ray_brute_kernel<<<div_up(nrays, RAY_THREADS), RAY_THREADS, 0, s>>>(ctx->st.stored, ctx->st.alive, worlds ? ctx->d_world : nullptr,
+                                                                           ctx->n_bodies, ctx->d_ray_o, ctx->d_ray_d, ctx->d_ray_max,
+                                                                           worlds ? ctx->d_ray_world : nullptr, nrays, mode, ctx->d_ray_keys[0],
+                                                                           ctx->d_ray_dist, ctx->d_ray_src[0], capacity, ctx->d_ray_counter);
+    ctx->launches += 1;
+    PK_CUDA(cudaGetLastError());
+    unsigned long long found = 0;
+    PK_CUDA(cudaMemcpyAsync(&found, ctx->d_ray_counter, sizeof(found), cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaStreamSynchronize(s));
+    *nhits = found;
+    if (found > capacity)
+    {
+        ctx->last_error = "ray hits exceed the capacity passed to pk_raycast";
+        return PK_E_PAIR_OVERFLOW; // *nhits = required capacity
+    }
+    if (found)
+    {
+        int buf = 0;
+        if (found > 1)
+        {
+            std::vector<int> shifts;
+            const int idbits = bits_for(std::max<uint32_t>(ctx->n_bodies, 2)), raybits = bits_for(std::max<uint32_t>(nrays, 2));
+            for (int b = 0; b < idbits; b += 8) shifts.push_back(b);
+            for (int b = 0; b < raybits; b += 8) shifts.push_back(32 + b);
+            PK_TRY(radix_sort(ctx, ctx->d_ray_keys, ctx->d_ray_src, found, shifts, &buf));
+        }
+        ray_gather_kernel<<<div_up(found, 256), 256, 0, s>>>(ctx->d_ray_keys[buf], ctx->d_ray_src[buf], ctx->d_ray_dist, found, ctx->d_ray_hits);
+        ctx->launches += 1;
+        PK_CUDA(cudaGetLastError());
+    }
+    cudaEventRecord(ctx->ev_ray[1], s);
+    if (found) PK_CUDA(cudaMemcpyAsync(hits, ctx->d_ray_hits, found * sizeof(pk_ray_hit), cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ctx->ray_ms, ctx->ev_ray[0], ctx->ev_ray[1]);
+    return PK_OK;
+}
+
+int pk_raycast_device_ms(pk_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return PK_E_INVALID;
+    *ms = ctx->ray_ms;
     return PK_OK;
 }
 

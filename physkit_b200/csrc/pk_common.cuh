@@ -179,50 +179,45 @@ __device__ __forceinline__ ShapeView load_shape(const BodyArrays &ba, uint32_t b
     return v;
 }
 
-// ---- support of a many-vertex hull: float prefilter, exact decision, scanned by the lanes that need one ----
+// ---- support of a many-vertex hull: float prefilter, exact decision ----
 // F_i = float dot of the float-rounded vertex with the float-rounded direction differs from the reference's
 // FP64 dot D_i by at most
 //   E = 5·2⁻²⁴ · (|x·lx| + |y·ly| + |z·lz|)  ≤  1e-6 · R · ‖l‖₁      (R = hull's largest |coordinate|)
 // (two input roundings + three float operations, 1e-6 leaves a 3× margin).  Any vertex with
-// F_i < max F − 2E has D_i < D_argmaxF, so it can be neither the maximum nor tied with it; the remaining
-// candidates are compared with the reference's exact expression, lowest index first (strict '>',
-// src/mesh.cpp:341-358).  Result: bit-identical argmax for ~1/10 of the FP64 work and 16-byte vertex loads.
-//
-// Who scans: with one pair per lane every lane of a warp walks a different hull, so a 16-byte vertex load
-// touches 32 different cache lines and the kernel is bound by L1 tag throughput (BASELINE C4: ≈30× off the
-// instruction bound).  Instead, the lanes that arrive here together (the coalesced group) serve their
-// queries one after the other: the owner's query is broadcast, lane r of the group scans vertices
-// r, r+g, r+2g, … (consecutive 16-byte loads: one or two lines per request), the float maximum is a
-// redux.sync, and the exact comparison of the few candidates is merged over the lanes that hold one.
-// Correct for any group the hardware happens to form (a single lane degenerates to the serial scan).
+// F_i < max F − 2E has D_i < D_argmaxF, so it can be neither the maximum nor tied with it.  One pass keeps
+// the largest and the second largest F: when the runner-up is below the threshold the float argmax is the
+// only candidate and IS the reference's answer (the usual case: neighbouring vertices of a 32–256 vertex
+// hull differ by ≈1e-2, the threshold is ≈1e-6).  Otherwise a second pass compares the candidates with the
+// reference's exact expression, lowest index first (strict '>', src/mesh.cpp:341-358).
+// Measured dead end (profiles/r1_c4_hull_support_ab.json): letting the lanes that arrive here together
+// scan one hull at a time with consecutive 16-byte loads and a redux.sync maximum is bit-exact too but
+// slower (C4, 2 M pairs: 109.5 ms vs 76.3 ms) — the scan is bound by issued instructions, not by L1 lines,
+// and serving the group's queries one after the other adds a fixed cost per query.
 __device__ __forceinline__ float pk_hull_fdot(float4 w, float lx, float ly, float lz) { return fmaf(w.x, lx, fmaf(w.y, ly, w.z * lz)); }
-__device__ __forceinline__ int pk_float_order(float f) // monotonic float → int
-{
-    const int b = __float_as_int(f);
-    return b ^ ((b >> 31) & 0x7FFFFFFF);
-}
-__device__ __forceinline__ float pk_float_unorder(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7FFFFFFF)); }
-__device__ __forceinline__ double pk_shfl_f64(unsigned mask, double x, int src)
-{
-    const int lo = __shfl_sync(mask, __double2loint(x), src), hi = __shfl_sync(mask, __double2hiint(x), src);
-    return __hiloint2double(hi, lo);
-}
-__device__ __forceinline__ unsigned long long pk_shfl_u64(unsigned mask, unsigned long long x, int src)
-{
-    const unsigned lo = __shfl_sync(mask, static_cast<unsigned>(x), src), hi = __shfl_sync(mask, static_cast<unsigned>(x >> 32), src);
-    return (static_cast<unsigned long long>(hi) << 32) | lo;
-}
 
 __device__ __forceinline__ uint32_t hull_argmax(const float4 *__restrict__ vf, const double *__restrict__ v, uint32_t nverts, float hull_r, d3 l)
 {
     const float lx = static_cast<float>(l.x), ly = static_cast<float>(l.y), lz = static_cast<float>(l.z);
     const float E = 1e-6f * hull_r * (fabsf(lx) + fabsf(ly) + fabsf(lz)) + 1e-37f;
-#ifdef PK_HULL_PER_LANE
-    // every lane scans its own hull (the r1 baseline, kept for A/B runs)
     uint32_t best = 0;
-    float fm = -3.4e38f;
-    for (uint32_t i = 0; i < nverts; ++i) fm = fmaxf(fm, pk_hull_fdot(__ldg(vf + i), lx, ly, lz));
-    const float thr = fm - 2.0f * E;
+#ifdef PK_HULL_TWO_PASS
+    float f1 = -3.4e38f;
+    for (uint32_t i = 0; i < nverts; ++i) f1 = fmaxf(f1, pk_hull_fdot(__ldg(vf + i), lx, ly, lz));
+#else
+    float f1 = -3.4e38f, f2 = -3.4e38f; // largest, second largest (equal values count twice)
+#pragma unroll 4
+    for (uint32_t i = 0; i < nverts; ++i)
+    {
+        const float f = pk_hull_fdot(__ldg(vf + i), lx, ly, lz);
+        const bool gt = f > f1;
+        f2 = gt ? f1 : fmaxf(f2, f);
+        best = gt ? i : best;
+        f1 = gt ? f : f1;
+    }
+    if (f2 < f1 - 2.0f * E) return best; // a single candidate
+    best = 0;
+#endif
+    const float thr = f1 - 2.0f * E;
     double best_dot = 0.0;
     bool have = false;
     for (uint32_t i = 0; i < nverts; ++i)
@@ -239,63 +234,6 @@ __device__ __forceinline__ uint32_t hull_argmax(const float4 *__restrict__ vf, c
         }
     }
     return best;
-#else
-    const unsigned mask = __activemask();
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t g = static_cast<uint32_t>(__popc(mask));
-    const uint32_t r = static_cast<uint32_t>(__popc(mask & ((1u << lane) - 1u)));
-    uint32_t result = 0;
-    for (unsigned todo = mask; todo; todo &= todo - 1u)
-    {
-        const int src = __ffs(static_cast<int>(todo)) - 1;
-        const float4 *__restrict__ q = reinterpret_cast<const float4 *>(pk_shfl_u64(mask, reinterpret_cast<unsigned long long>(vf), src));
-        const uint32_t n = __shfl_sync(mask, nverts, src);
-        const float qx = __shfl_sync(mask, lx, src), qy = __shfl_sync(mask, ly, src), qz = __shfl_sync(mask, lz, src);
-        const float qE = __shfl_sync(mask, E, src);
-        float fm = -3.4e38f;
-        for (uint32_t i = r; i < n; i += g) fm = fmaxf(fm, pk_hull_fdot(__ldg(q + i), qx, qy, qz));
-        fm = pk_float_unorder(__reduce_max_sync(mask, pk_float_order(fm)));
-        const float thr = fm - 2.0f * qE;
-        // exact value of this lane's candidates, lowest index first
-        const double *__restrict__ qv = reinterpret_cast<const double *>(pk_shfl_u64(mask, reinterpret_cast<unsigned long long>(v), src));
-        const double dx = pk_shfl_f64(mask, l.x, src), dy = pk_shfl_f64(mask, l.y, src), dz = pk_shfl_f64(mask, l.z, src);
-        double my_dot = 0.0;
-        uint32_t my_i = 0;
-        bool have = false;
-        for (uint32_t i = r; i < n; i += g)
-        {
-            if (pk_hull_fdot(__ldg(q + i), qx, qy, qz) >= thr)
-            {
-                const double t = (qv[3 * i] * dx + qv[3 * i + 1] * dy) + qv[3 * i + 2] * dz;
-                if (!have || t > my_dot)
-                {
-                    my_dot = t;
-                    my_i = i;
-                    have = true;
-                }
-            }
-        }
-        // merge over the lanes that hold a candidate: largest exact dot, lowest index among equals
-        unsigned cand = __ballot_sync(mask, have);
-        double gd = 0.0;
-        uint32_t gi = 0;
-        bool ghave = false;
-        for (; cand; cand &= cand - 1u)
-        {
-            const int c = __ffs(static_cast<int>(cand)) - 1;
-            const double t = pk_shfl_f64(mask, my_dot, c);
-            const uint32_t i = __shfl_sync(mask, my_i, c);
-            if (!ghave || t > gd || (t == gd && i < gi))
-            {
-                gd = t;
-                gi = i;
-                ghave = true;
-            }
-        }
-        if (static_cast<int>(lane) == src) result = gi;
-    }
-    return result;
-#endif
 }
 
 // Farthest point of the shape along d.

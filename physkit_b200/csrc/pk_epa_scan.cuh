@@ -392,8 +392,9 @@ epa_init_kernel(const SimplexRec *__restrict__ simplices, const unsigned long lo
     init[s] = o;
 }
 
+// 5 blocks of 64 threads per SM (≤ 204 registers, 5 × 42 KB of shared memory): 15.6 → 15.1 ms at 1 M bodies against 4
 #ifndef PK_ES_MIN_BLOCKS
-#define PK_ES_MIN_BLOCKS 4
+#define PK_ES_MIN_BLOCKS 5
 #endif
 #ifndef PK_ES_FETCH_MIN
 #define PK_ES_FETCH_MIN 6

@@ -59,6 +59,11 @@ int main()
             xb -= v * dt;
         }
         if (!seen_begin || max_points < 1) return std::printf("FAIL: manifold begin %d points %zu\n", seen_begin, max_points), 1;
+        // world_base::raycast over the last step's tree: a ray along +x from far left enters a's fat box first, then b's
+        auto rc = w.raycast({-30.0, 0.0, 0.0}, {1.0, 0.0, 0.0}, 100.0);
+        if (rc.size() != 2 || rc[0].first != a || rc[1].first != b || !(rc[0].second > 20.0 && rc[0].second <= rc[1].second))
+            return std::printf("FAIL: raycast %zu\n", rc.size()), 1;
+        if (!w.raycast({-30.0, 20.0, 0.0}, {1.0, 0.0, 0.0}, 100.0).empty()) return std::printf("FAIL: raycast miss\n"), 1;
         auto one = w.gjk_epa(a, b);
         if (!seen_pair || !seen_contact || !one) return std::printf("FAIL: pair %d contact %d gjk %d\n", seen_pair, seen_contact, (int)one.has_value()), 1;
         std::printf("host shim ok\n");
