@@ -206,6 +206,29 @@ int pk_contacts(pk_ctx *ctx, const pk_contact **recs, uint64_t *n);
  * (narrow_phase::calculate → contact_point, collision_phases.h:257-263).  Computed on the device on request
  * from the poses of that step; the host pointer stays valid until the next pk_collide*. */
 int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n);
+/* ---- integrator (optional) ---------------------------------------------------------------
+ * The two per-body loops of world::step_impl on the device, so that poses need not travel every step:
+ *   loop A (src/world.cpp:22-34): apply_force(gravity · mass), semi_implicit_euler::integrate_vel
+ *          (detail/integrate.h:36-40), vel · dt handed to broad_phase::update_node, clear_forces;
+ *   loop B (src/world.cpp:50-55): semi_implicit_euler::integrate_pos (detail/integrate.h:42-46).
+ * A step of a gpu_world is then  pk_integrate_velocities → pk_collide → [solver] → pk_integrate_positions.
+ * pk_dynamics_enable allocates the state (velocities, force accumulators, mass, inertia tensors).
+ * pk_dynamics_upload sets it for bodies [first, first+count) whose poses are already uploaded: mass as in
+ * particle's constructor (inv_mass = 1 / mass, zero inverse tensor for infinite mass; core/particle.h:14-28),
+ * inertia_local = 9 doubles per body, row-major; the inverse is Matrix3d::inverse as the reference computes it.
+ * pk_dynamics_set_forces overwrites the accumulators M_acc (= Σ force · inv_mass) and M_torque_acc
+ * (particle.h:78-99); pk_dynamics_set_velocities brings a host solver's result back; pk_dynamics_download
+ * reads poses and velocities (any pointer may be NULL); pk_displacements reads vel · dt of the last loop A.
+ * Static and dead bodies are skipped like in the reference (src/world.cpp:24, 52). */
+int pk_dynamics_enable(pk_ctx *ctx);
+int pk_dynamics_upload(pk_ctx *ctx, const double *vel, const double *ang_vel, const double *mass, const double *inertia_local,
+                       uint32_t first, uint32_t count);
+int pk_dynamics_set_velocities(pk_ctx *ctx, const double *vel, const double *ang_vel, uint32_t first, uint32_t count);
+int pk_dynamics_set_forces(pk_ctx *ctx, const double *acc, const double *torque, uint32_t first, uint32_t count);
+int pk_integrate_velocities(pk_ctx *ctx, double dt, const double gravity[3]);
+int pk_integrate_positions(pk_ctx *ctx, double dt);
+int pk_dynamics_download(pk_ctx *ctx, double *pos, double *quat, double *vel, double *ang_vel, uint32_t first, uint32_t count);
+int pk_displacements(pk_ctx *ctx, double *disp, uint32_t first, uint32_t count);
 /* ---- ray casts --------------------------------------------------------------------------
  * Replaces world_base::raycast(ray, max_dist) (core/world.h:260-319), i.e. dynamic_bvh::raycast (bvh.h:346-450)
  * over the static and the dynamic tree, for a batch of rays against the tree of the LAST step (call after

@@ -106,6 +106,7 @@ def lib():
         L.pko_brute_pairs.restype = u64
         L.pko_max_threads.restype = i32
         f64 = C.c_double
+        L.pko_dynamics_step.argtypes = [u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp]
         L.pko_ray_box.argtypes = [vp, vp, vp, f64, vp]
         L.pko_ray_box.restype = i32
         L.pko_bvh_raycast.argtypes = [vp, vp, vp, f64, i32, vp, vp, u64]
@@ -248,6 +249,37 @@ def brute_pairs(boxes6):
     out = np.empty(n, dtype=np.uint64)
     lib().pko_brute_pairs(_p(b), len(b), _p(out), n)
     return out
+
+
+class Dynamics:
+    """Rigid-body state of n bodies and the two per-body loops of world::step_impl (src/world.cpp:22-34, 50-55)."""
+
+    def __init__(self, pos, quat, vel, ang_vel, mass, inertia, flags):
+        n = len(pos)
+        self.pos = _f64(pos, (n, 3)).copy()
+        self.quat = _f64(quat, (n, 4)).copy()
+        self.vel = _f64(vel, (n, 3)).copy()
+        self.ang_vel = _f64(ang_vel, (n, 3)).copy()
+        self.acc = np.zeros((n, 3))
+        self.torque = np.zeros((n, 3))
+        self.mass = _f64(mass, (n,)).copy()
+        self.inertia = _f64(inertia, (n, 9)).copy()
+        self.flags = np.ascontiguousarray(flags, dtype=np.uint8).copy()
+
+    def _step(self, phase, dt, gravity):
+        n = len(self.pos)
+        disp = np.zeros((n, 3))
+        g = _f64(gravity, (3,))
+        lib().pko_dynamics_step(n, _p(self.pos), _p(self.quat), _p(self.vel), _p(self.ang_vel), _p(self.acc), _p(self.torque),
+                                _p(self.mass), _p(self.inertia), None, _p(self.flags), _p(g), float(dt), phase, _p(disp))
+        return disp
+
+    def integrate_velocities(self, dt, gravity):
+        """loop A: returns vel·dt, the displacement handed to broad_phase::update_node."""
+        return self._step(0, dt, gravity)
+
+    def integrate_positions(self, dt):
+        self._step(1, dt, (0.0, 0.0, 0.0))
 
 
 def ray_box(origin, direction, box6, max_distance):

@@ -902,6 +902,140 @@ inline manifold_t manifold_merge(const manifold_t &old_man, const contact_info_t
     return new_man;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rigid-body state and the integrator — include/physkit/core/particle.h:12-150,
+// include/physkit/detail/integrate.h:17-47, the per-body loops of src/world.cpp:22-34, 50-55.
+// Eigen's fixed-size 3×3 kernels are restated as coefficient sums in k order, (k0 + k1) + k2, like dot();
+// the quaternion product and sin / cos are "parity unpinned" at the ulp level (Eigen has a SIMD path for
+// double quaternions; libm vs libdevice): tests compare these with a stated tolerance.
+// ---------------------------------------------------------------------------------------------
+struct m3
+{
+    double m[3][3]; // [row][col]
+};
+inline m3 mul(const m3 &a, const m3 &b)
+{
+    m3 c;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c.m[i][j] = (a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j]) + a.m[i][2] * b.m[2][j];
+    return c;
+}
+inline v3 mul(const m3 &a, v3 v)
+{
+    return {(a.m[0][0] * v.x + a.m[0][1] * v.y) + a.m[0][2] * v.z, (a.m[1][0] * v.x + a.m[1][1] * v.y) + a.m[1][2] * v.z,
+            (a.m[2][0] * v.x + a.m[2][1] * v.y) + a.m[2][2] * v.z};
+}
+inline m3 transpose(const m3 &a)
+{
+    m3 t;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) t.m[i][j] = a.m[j][i];
+    return t;
+}
+// Eigen compute_inverse_size3_helper: cofactors of column 0, determinant = their dot with column 0,
+// every entry = cofactor · (1 / det)   (lin_alg.h mat3::inverse → Eigen::Matrix3d::inverse)
+inline m3 inverse(const m3 &a)
+{
+    auto cof = [&](int i, int j)
+    {
+        int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return a.m[i1][j1] * a.m[i2][j2] - a.m[i1][j2] * a.m[i2][j1];
+    };
+    double c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+    double det = (c00 * a.m[0][0] + c10 * a.m[1][0]) + c20 * a.m[2][0];
+    double invdet = 1.0 / det;
+    m3 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.m[j][i] = cof(i, j) * invdet;
+    return r;
+}
+// Eigen QuaternionBase::toRotationMatrix (lin_alg.h:530-535)
+inline m3 to_rotation_matrix(quat q)
+{
+    double tx = 2.0 * q.x, ty = 2.0 * q.y, tz = 2.0 * q.z;
+    double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    m3 r;
+    r.m[0][0] = 1.0 - (tyy + tzz);
+    r.m[0][1] = txy - twz;
+    r.m[0][2] = txz + twy;
+    r.m[1][0] = txy + twz;
+    r.m[1][1] = 1.0 - (txx + tzz);
+    r.m[1][2] = tyz - twx;
+    r.m[2][0] = txz - twy;
+    r.m[2][1] = tyz + twx;
+    r.m[2][2] = 1.0 - (txx + tyy);
+    return r;
+}
+// Eigen quat_product (scalar form; lin_alg.h:478-483)
+inline quat qmul(quat a, quat b)
+{
+    return {((a.w * b.x + a.x * b.w) + a.y * b.z) - a.z * b.y, ((a.w * b.y + a.y * b.w) + a.z * b.x) - a.x * b.z,
+            ((a.w * b.z + a.z * b.w) + a.x * b.y) - a.y * b.x, ((a.w * b.w - a.x * b.x) - a.y * b.y) - a.z * b.z};
+}
+inline quat qnormalized(quat q)
+{
+    double n = std::sqrt(((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
+    return {q.x / n, q.y / n, q.z / n, q.w / n};
+}
+// detail::exp (integrate.h:21-32)
+inline quat exp_rotation(v3 ang_vel, double dt)
+{
+    v3 angle = ang_vel * dt;
+    double mag = norm(angle);
+    if (mag < 1e-12)
+    {
+        v3 half = angle * 0.5;
+        return qnormalized(quat{half.x, half.y, half.z, 1.0});
+    }
+    v3 axis = angle / mag;
+    double s = std::sin(0.5 * mag), c = std::cos(0.5 * mag); // Eigen AngleAxis → Quaternion (lin_alg.h:569-576)
+    return {s * axis.x, s * axis.y, s * axis.z, c};
+}
+
+struct rigid_state // particle.h:113-139
+{
+    v3 pos{}, vel{}, acc{}, ang_vel{}, torque{};
+    quat q{0, 0, 0, 1};
+    double mass = 1.0, inv_mass = 1.0;
+    m3 inertia_local{}, inv_inertia_local{};
+    m3 inertia_world{}, inv_inertia_world{};
+    bool is_static = false;
+
+    void update_derived_state() // particle.h:140-146
+    {
+        m3 r = to_rotation_matrix(q);
+        m3 rt = transpose(r);
+        inertia_world = mul(mul(r, inertia_local), rt);
+        inv_inertia_world = mul(mul(r, inv_inertia_local), rt);
+    }
+    v3 angular_accel() const // particle.h:72-76
+    {
+        return mul(inv_inertia_world, torque - cross(ang_vel, mul(inertia_world, ang_vel)));
+    }
+};
+
+// world::step_impl loop A without the broad-phase call (src/world.cpp:22-34): returns vel·dt, the
+// displacement handed to update_node
+inline v3 step_velocity(rigid_state &o, v3 gravity, double dt)
+{
+    o.acc = o.acc + (gravity * o.mass) * o.inv_mass;        // apply_force(gravity * mass), particle.h:78-79
+    o.vel = o.vel + o.acc * dt;                             // integrate_vel, integrate.h:36-40
+    o.ang_vel = o.ang_vel + o.angular_accel() * dt;
+    v3 disp = o.vel * dt;
+    o.acc = v3{0, 0, 0};                                    // clear_forces, particle.h:101-105
+    o.torque = v3{0, 0, 0};
+    return disp;
+}
+// loop B (src/world.cpp:50-55): integrate_pos, integrate.h:42-46
+inline void step_position(rigid_state &o, double dt)
+{
+    o.pos = o.pos + o.vel * dt;
+    o.q = qmul(exp_rotation(o.ang_vel, dt), o.q);
+    o.update_derived_state();
+}
+
 // collision.cpp:512-518
 inline std::optional<collision_info> gjk_epa(const shape &a, const shape &b, gjk_stats *st = nullptr)
 {

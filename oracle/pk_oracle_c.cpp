@@ -331,6 +331,58 @@ uint64_t pko_bvh_query(void *t, const double *box6, uint32_t *out, uint64_t cap,
     return n;
 }
 
+// ------------------------------- integrator -------------------------------------
+// The per-body loops of world::step_impl (src/world.cpp:22-34 and 50-55) on flat arrays, in place.
+// inertia9 / inv_inertia9: local tensors, row-major (inv_inertia9 = NULL: Matrix3d::inverse restated; a body
+// with inv_mass == 0 gets a zero inverse tensor, particle.h:25-26).  flags as pk_bodies_upload.
+// phase 0: loop A — apply_force(gravity·mass), integrate_vel, disp_out = vel·dt, clear_forces.
+// phase 1: loop B — integrate_pos.
+void pko_dynamics_step(uint64_t n, double *pos, double *quat_xyzw, double *vel, double *ang_vel, double *acc, double *torque,
+                       const double *mass, const double *inertia9, const double *inv_inertia9, const uint8_t *flags,
+                       const double *gravity3, double dt, int phase, double *disp_out)
+{
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        if (!(flags[i] & 2) || (flags[i] & 1)) continue; // slot.available() || is_static()
+        rigid_state o;
+        o.pos = ld3(pos + 3 * i);
+        o.q = ldq(quat_xyzw + 4 * i);
+        o.vel = ld3(vel + 3 * i);
+        o.ang_vel = ld3(ang_vel + 3 * i);
+        o.acc = ld3(acc + 3 * i);
+        o.torque = ld3(torque + 3 * i);
+        o.mass = mass[i];
+        o.inv_mass = 1.0 / mass[i];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) o.inertia_local.m[r][c] = inertia9[9 * i + 3 * r + c];
+        if (inv_inertia9)
+        {
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) o.inv_inertia_local.m[r][c] = inv_inertia9[9 * i + 3 * r + c];
+        }
+        else
+            o.inv_inertia_local = inverse(o.inertia_local);
+        if (o.inv_mass == 0.0) o.inv_inertia_local = m3{};
+        o.update_derived_state();
+        if (phase == 0)
+        {
+            v3 d = step_velocity(o, ld3(gravity3), dt);
+            if (disp_out) st3(disp_out + 3 * i, d);
+        }
+        else
+            step_position(o, dt);
+        st3(pos + 3 * i, o.pos);
+        quat_xyzw[4 * i + 0] = o.q.x;
+        quat_xyzw[4 * i + 1] = o.q.y;
+        quat_xyzw[4 * i + 2] = o.q.z;
+        quat_xyzw[4 * i + 3] = o.q.w;
+        st3(vel + 3 * i, o.vel);
+        st3(ang_vel + 3 * i, o.ang_vel);
+        st3(acc + 3 * i, o.acc);
+        st3(torque + 3 * i, o.torque);
+    }
+}
+
 // ------------------------------- ray casts --------------------------------------
 // ray::intersect_distance (bvh.h:59-98).  dir3 is normalised by the ray constructor.  Returns 1 on a hit.
 int pko_ray_box(const double *origin3, const double *dir3, const double *box6, double max_distance, double *dist_out)

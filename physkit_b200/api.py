@@ -93,6 +93,8 @@ EXPORTS = [
     "pk_collide_resident", "pk_fetch_results", "pk_collide", "pk_pairs", "pk_contacts",
     "pk_pairs_device", "pk_contacts_device", "pk_stored_bounds", "pk_stage_times_get", "pk_stream",
     "pk_gjk_epa_batch", "pk_gjk_epa_batch_device", "pk_raycast", "pk_raycast_device_ms",
+    "pk_dynamics_enable", "pk_dynamics_upload", "pk_dynamics_set_velocities", "pk_dynamics_set_forces",
+    "pk_integrate_velocities", "pk_integrate_positions", "pk_dynamics_download", "pk_displacements",
     "pk_device_alloc", "pk_device_free", "pk_memcpy_h2d", "pk_memcpy_d2h", "pk_memcpy_d2d", "pk_host_alloc", "pk_host_free",
 ]
 
@@ -119,6 +121,14 @@ def load_library():
     L.pk_contact_points.argtypes = [vp, vp, vp]
     L.pk_raycast.argtypes = [vp, vp, vp, vp, vp, u32, i32, vp, u64, vp]
     L.pk_raycast_device_ms.argtypes = [vp, vp]
+    L.pk_dynamics_enable.argtypes = [vp]
+    L.pk_dynamics_upload.argtypes = [vp, vp, vp, vp, vp, u32, u32]
+    L.pk_dynamics_set_velocities.argtypes = [vp, vp, vp, u32, u32]
+    L.pk_dynamics_set_forces.argtypes = [vp, vp, vp, u32, u32]
+    L.pk_integrate_velocities.argtypes = [vp, C.c_double, vp]
+    L.pk_integrate_positions.argtypes = [vp, C.c_double]
+    L.pk_dynamics_download.argtypes = [vp, vp, vp, vp, vp, u32, u32]
+    L.pk_displacements.argtypes = [vp, vp, u32, u32]
     L.pk_manifolds_enable.argtypes = [vp, C.c_uint64]
     L.pk_manifolds_update.argtypes = [vp, vp]
     L.pk_manifolds.argtypes = [vp, vp, vp]
@@ -343,6 +353,47 @@ class Context:
             return np.zeros((0, 6))
         buf = (C.c_double * (6 * n.value)).from_address(p.value)
         return np.frombuffer(buf, dtype=np.float64).reshape(-1, 6).copy()
+
+    # -- integrator: the two per-body loops of world::step_impl on the device (src/world.cpp:22-34, 50-55)
+    def dynamics_enable(self):
+        self._check(self.L.pk_dynamics_enable(self.h))
+
+    def dynamics_upload(self, vel, ang_vel, mass, inertia_local, first=0):
+        v = _arr(vel, np.float64).reshape(-1, 3)
+        w = _arr(ang_vel, np.float64).reshape(-1, 3)
+        m = _arr(mass, np.float64).reshape(-1)
+        it = _arr(inertia_local, np.float64).reshape(-1, 9)
+        assert len(v) == len(w) == len(m) == len(it)
+        self._check(self.L.pk_dynamics_upload(self.h, _p(v), _p(w), _p(m), _p(it), int(first), len(v)))
+
+    def dynamics_set_velocities(self, vel, ang_vel, first=0):
+        v = _arr(vel, np.float64).reshape(-1, 3)
+        w = _arr(ang_vel, np.float64).reshape(-1, 3)
+        self._check(self.L.pk_dynamics_set_velocities(self.h, _p(v), _p(w), int(first), len(v)))
+
+    def dynamics_set_forces(self, acc, torque, first=0):
+        a = _arr(acc, np.float64).reshape(-1, 3)
+        t = _arr(torque, np.float64).reshape(-1, 3)
+        self._check(self.L.pk_dynamics_set_forces(self.h, _p(a), _p(t), int(first), len(a)))
+
+    def integrate_velocities(self, dt, gravity=(0.0, -9.81, 0.0)):
+        g = np.ascontiguousarray(gravity, dtype=np.float64)
+        self._check(self.L.pk_integrate_velocities(self.h, float(dt), _p(g)))
+
+    def integrate_positions(self, dt):
+        self._check(self.L.pk_integrate_positions(self.h, float(dt)))
+
+    def dynamics_download(self, count, first=0):
+        """(pos, quat, vel, ang_vel) of bodies [first, first + count)."""
+        pos, quat = np.empty((count, 3)), np.empty((count, 4))
+        vel, w = np.empty((count, 3)), np.empty((count, 3))
+        self._check(self.L.pk_dynamics_download(self.h, _p(pos), _p(quat), _p(vel), _p(w), int(first), int(count)))
+        return pos, quat, vel, w
+
+    def displacements(self, count, first=0):
+        d = np.empty((count, 3))
+        self._check(self.L.pk_displacements(self.h, _p(d), int(first), int(count)))
+        return d
 
     # -- ray casts over the tree of the last step (world_base::raycast, core/world.h:260-319)
     def raycast(self, origins, directions, max_distance, world=None, mode=RAY_ALL, capacity=None):

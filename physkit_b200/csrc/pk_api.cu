@@ -11,6 +11,7 @@
 #include "pk_narrowphase.cuh"
 #include "pk_epa_scan.cuh"
 #include "pk_manifold.cuh"
+#include "pk_dynamics.cuh"
 #include "pk_ray.cuh"
 #include "pk_sort.cuh"
 
@@ -163,6 +164,12 @@ struct pk_ctx
     ContactPointRec *d_points = nullptr; // pk_contact_points: allocated on first use
     pk_contact_point *h_points = nullptr;
     size_t points_cap = 0;
+
+    // integrator (pk_dynamics_enable): velocities, force accumulators, mass properties
+    bool dyn_enabled = false;
+    DynArrays dyn{};
+    cudaEvent_t ev_dyn[2]{};
+    float dyn_ms = 0.f;
 
     // ray casts (pk_raycast): buffers allocated on first use
     uint32_t tree_m = 0;      // leaves of the tree the last step built (0: none, < 2 bodies alive)
@@ -500,6 +507,12 @@ int pk_destroy(pk_ctx *ctx)
                     static_cast<void *>(ctx->d_ray_hits), static_cast<void *>(ctx->d_ray_counter)})
         if (q) cudaFree(q);
     for (auto &e : ctx->ev_ray)
+        if (e) cudaEventDestroy(e);
+    for (void *q : {static_cast<void *>(ctx->dyn.vel), static_cast<void *>(ctx->dyn.ang_vel), static_cast<void *>(ctx->dyn.acc),
+                    static_cast<void *>(ctx->dyn.torque), static_cast<void *>(ctx->dyn.mass), static_cast<void *>(ctx->dyn.inertia),
+                    static_cast<void *>(ctx->dyn.inertia_w)})
+        if (q) cudaFree(q);
+    for (auto &e : ctx->ev_dyn)
         if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -1079,6 +1092,170 @@ int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n)
     }
     *pts = ctx->h_points;
     *n = m;
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ integrator
+namespace
+{
+// Eigen Matrix3d::inverse (compute_inverse_size3_helper): cofactors of column 0, det = their dot with column 0,
+// every entry = cofactor · (1 / det); particle.h:22-23.  Host side, once per upload, like the reference's
+// constructor.  -ffp-contract is off for host code of this file (nvcc passes -fmad only to the device).
+void invert3(const double *a, double *r)
+{
+    auto A = [&](int i, int j) { return a[3 * i + j]; };
+    auto cof = [&](int i, int j)
+    {
+        int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        volatile double p = A(i1, j1) * A(i2, j2), q = A(i1, j2) * A(i2, j1); // two roundings, no contraction
+        return p - q;
+    };
+    volatile double t0 = cof(0, 0) * A(0, 0), t1 = cof(1, 0) * A(1, 0), t2 = cof(2, 0) * A(2, 0);
+    const double det = (t0 + t1) + t2;
+    const double invdet = 1.0 / det;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r[3 * j + i] = cof(i, j) * invdet;
+}
+} // namespace
+
+int pk_dynamics_enable(pk_ctx *ctx)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (ctx->dyn_enabled) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    const size_t nb = ctx->cfg.max_bodies;
+    PK_TRY(dev_alloc(ctx, &ctx->dyn.vel, 3 * nb));
+    PK_TRY(dev_alloc(ctx, &ctx->dyn.ang_vel, 3 * nb));
+    PK_TRY(dev_alloc(ctx, &ctx->dyn.acc, 3 * nb));
+    PK_TRY(dev_alloc(ctx, &ctx->dyn.torque, 3 * nb));
+    PK_TRY(dev_alloc(ctx, &ctx->dyn.mass, 2 * nb));
+    PK_TRY(dev_alloc(ctx, &ctx->dyn.inertia, 18 * nb));
+    PK_TRY(dev_alloc(ctx, &ctx->dyn.inertia_w, 18 * nb));
+    for (double *p : {ctx->dyn.vel, ctx->dyn.ang_vel, ctx->dyn.acc, ctx->dyn.torque})
+        PK_CUDA(cudaMemsetAsync(p, 0, 3 * nb * sizeof(double), ctx->stream));
+    PK_CUDA(cudaEventCreate(&ctx->ev_dyn[0]));
+    PK_CUDA(cudaEventCreate(&ctx->ev_dyn[1]));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->dyn_enabled = true;
+    return PK_OK;
+}
+
+int pk_dynamics_upload(pk_ctx *ctx, const double *vel, const double *ang_vel, const double *mass, const double *inertia_local,
+                       uint32_t first, uint32_t count)
+{
+    if (!ctx || !vel || !ang_vel || !mass || !inertia_local) return PK_E_INVALID;
+    if (!ctx->dyn_enabled) return PK_E_STATE;
+    if (static_cast<uint64_t>(first) + count > ctx->n_bodies) return PK_E_INVALID;
+    if (count == 0) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t s = ctx->stream;
+    std::vector<double> mm(2ull * count), in(18ull * count);
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        mm[2ull * i] = mass[i];
+        mm[2ull * i + 1] = 1.0 / mass[i]; // particle.h:21
+        std::memcpy(&in[18ull * i], inertia_local + 9ull * i, 9 * sizeof(double));
+        if (mm[2ull * i + 1] == 0.0)
+            std::fill(&in[18ull * i + 9], &in[18ull * i + 18], 0.0); // infinite mass: zero inverse tensor (particle.h:25-26)
+        else
+            invert3(inertia_local + 9ull * i, &in[18ull * i + 9]);
+    }
+    PK_CUDA(cudaMemcpyAsync(ctx->dyn.vel + 3ull * first, vel, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(ctx->dyn.ang_vel + 3ull * first, ang_vel, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(ctx->dyn.mass + 2ull * first, mm.data(), mm.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    PK_CUDA(cudaMemcpyAsync(ctx->dyn.inertia + 18ull * first, in.data(), in.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    // update_derived_state from the poses already uploaded (particle.h:27): call after pk_bodies_upload
+    dynamics_derive_kernel<<<div_up(count, 256), 256, 0, s>>>(ctx->d_quat, ctx->dyn, first, count);
+    PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaStreamSynchronize(s)); // mm / in are stack-owned
+    return PK_OK;
+}
+
+int pk_dynamics_set_velocities(pk_ctx *ctx, const double *vel, const double *ang_vel, uint32_t first, uint32_t count)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (!ctx->dyn_enabled) return PK_E_STATE;
+    if (static_cast<uint64_t>(first) + count > ctx->n_bodies) return PK_E_INVALID;
+    if (count == 0) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    if (vel) PK_CUDA(cudaMemcpyAsync(ctx->dyn.vel + 3ull * first, vel, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (ang_vel)
+        PK_CUDA(cudaMemcpyAsync(ctx->dyn.ang_vel + 3ull * first, ang_vel, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return PK_OK;
+}
+
+int pk_dynamics_set_forces(pk_ctx *ctx, const double *acc, const double *torque, uint32_t first, uint32_t count)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (!ctx->dyn_enabled) return PK_E_STATE;
+    if (static_cast<uint64_t>(first) + count > ctx->n_bodies) return PK_E_INVALID;
+    if (count == 0) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    if (acc) PK_CUDA(cudaMemcpyAsync(ctx->dyn.acc + 3ull * first, acc, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (torque)
+        PK_CUDA(cudaMemcpyAsync(ctx->dyn.torque + 3ull * first, torque, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return PK_OK;
+}
+
+int pk_integrate_velocities(pk_ctx *ctx, double dt, const double gravity[3])
+{
+    if (!ctx || !gravity) return PK_E_INVALID;
+    if (!ctx->dyn_enabled) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    const uint32_t n = ctx->n_bodies;
+    cudaEventRecord(ctx->ev_dyn[0], ctx->stream);
+    if (n)
+    {
+        integrate_vel_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->d_flags, ctx->dyn, ctx->d_disp, n, dt,
+                                                                     d3{gravity[0], gravity[1], gravity[2]});
+        PK_CUDA(cudaGetLastError());
+    }
+    cudaEventRecord(ctx->ev_dyn[1], ctx->stream);
+    return PK_OK;
+}
+
+int pk_integrate_positions(pk_ctx *ctx, double dt)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (!ctx->dyn_enabled) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    const uint32_t n = ctx->n_bodies;
+    cudaEventRecord(ctx->ev_dyn[0], ctx->stream);
+    if (n)
+    {
+        integrate_pos_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->d_flags, ctx->dyn, ctx->d_pos, ctx->d_quat, n, dt);
+        PK_CUDA(cudaGetLastError());
+    }
+    cudaEventRecord(ctx->ev_dyn[1], ctx->stream);
+    return PK_OK;
+}
+
+int pk_dynamics_download(pk_ctx *ctx, double *pos, double *quat, double *vel, double *ang_vel, uint32_t first, uint32_t count)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (static_cast<uint64_t>(first) + count > ctx->n_bodies) return PK_E_INVALID;
+    if ((vel || ang_vel) && !ctx->dyn_enabled) return PK_E_STATE;
+    if (count == 0) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t s = ctx->stream;
+    if (pos) PK_CUDA(cudaMemcpyAsync(pos, ctx->d_pos + 3ull * first, 3ull * count * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (quat) PK_CUDA(cudaMemcpyAsync(quat, ctx->d_quat + 4ull * first, 4ull * count * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (vel) PK_CUDA(cudaMemcpyAsync(vel, ctx->dyn.vel + 3ull * first, 3ull * count * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (ang_vel)
+        PK_CUDA(cudaMemcpyAsync(ang_vel, ctx->dyn.ang_vel + 3ull * first, 3ull * count * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaStreamSynchronize(s));
+    if (ctx->dyn_enabled && ctx->ev_dyn[0]) cudaEventElapsedTime(&ctx->dyn_ms, ctx->ev_dyn[0], ctx->ev_dyn[1]);
+    return PK_OK;
+}
+
+int pk_displacements(pk_ctx *ctx, double *disp, uint32_t first, uint32_t count)
+{
+    if (!ctx || !disp) return PK_E_INVALID;
+    if (static_cast<uint64_t>(first) + count > ctx->n_bodies) return PK_E_INVALID;
+    if (count == 0) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    PK_CUDA(cudaMemcpyAsync(disp, ctx->d_disp + 3ull * first, 3ull * count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
 
