@@ -105,6 +105,30 @@ typedef struct pk_ray_hit
     double distance; /* ray::intersect_distance of the body's stored box (bvh.h:59-98): 0 when the origin is inside */
 } pk_ray_hit;
 
+/* jacobian_row (collision/constraint.h:29-47), the fields constraint_solver::setup_contacts fills.  The normal
+ * row's impulse bounds are [0, +inf) (contacts push only, :901), the tangent rows are bounded by the solver's
+ * friction cone (:1150-1199). */
+typedef struct pk_solver_row
+{
+    double J_v[3];
+    double J_w_a[3];
+    double J_w_b[3];
+    double M_eff;
+    double bias;
+} pk_solver_row;
+
+/* contact_solver_point (collision/constraint.h:1204-1214): one per manifold point with positive penetration. */
+typedef struct pk_solver_point
+{
+    uint64_t key;      /* make_pair_key(a, b): a = key >> 32, b = key & 0xffffffff */
+    uint32_t manifold; /* index into pk_manifolds() of this step: the reference's `cache` pointer */
+    uint32_t point;    /* index of the contact in that manifold */
+    pk_solver_row normal, tangent1, tangent2;
+    double friction_coeff; /* sqrt(friction_a · friction_b) */
+    double inv_m_11, inv_m_12, inv_m_22; /* inverse of the 2×2 friction block, or the diagonal fallback (:1084-1094) */
+    double accumulated[3]; /* warm start: normal_impulse, tangent_impulses[0..1] of the manifold point */
+} pk_solver_point;
+
 #define PK_RAY_ALL 0     /* every body whose stored box the ray enters within max_distance */
 #define PK_RAY_CLOSEST 1 /* per ray the entry with the smallest distance, lowest body id among equals */
 
@@ -229,6 +253,18 @@ int pk_integrate_velocities(pk_ctx *ctx, double dt, const double gravity[3]);
 int pk_integrate_positions(pk_ctx *ctx, double dt);
 int pk_dynamics_download(pk_ctx *ctx, double *pos, double *quat, double *vel, double *ang_vel, uint32_t first, uint32_t count);
 int pk_displacements(pk_ctx *ctx, double *disp, uint32_t first, uint32_t count);
+/* ---- contact rows (optional; needs pk_dynamics_enable and pk_manifolds_enable) -------------
+ * constraint_solver::setup_contacts (collision/constraint.h:1052-1104): build_contact_jacobian (:874-953) for
+ * every point of every manifold of the last pk_manifolds_update, from the poses and velocities on the device.
+ * gravity_norm is the solver's M_gravity (world_desc.gravity().norm(), core/world.h:383): the restitution
+ * threshold is 2 · gravity_norm · dt (:1071).  Rows come out ordered by (pair key, point index); points whose
+ * penetration is not positive yield no row (:893-894).  The Gauss-Seidel sweep that consumes the rows
+ * (:1107-1201) is serial in the reference and stays with the caller.
+ * pk_material_upload sets restitution / friction per body (defaults 0.5 / 0.5, core/object.h:107-108). */
+int pk_material_upload(pk_ctx *ctx, const double *restitution, const double *friction, uint32_t first, uint32_t count);
+int pk_contact_rows_setup(pk_ctx *ctx, double dt, double gravity_norm, uint64_t *nrows);
+int pk_contact_rows(pk_ctx *ctx, const pk_solver_point **rows, uint64_t *n);
+int pk_contact_rows_device(pk_ctx *ctx, const void **dptr, uint64_t *n, float *device_ms);
 /* ---- ray casts --------------------------------------------------------------------------
  * Replaces world_base::raycast(ray, max_dist) (core/world.h:260-319), i.e. dynamic_bvh::raycast (bvh.h:346-450)
  * over the static and the dynamic tree, for a batch of rays against the tree of the LAST step (call after

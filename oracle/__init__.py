@@ -107,6 +107,8 @@ def lib():
         L.pko_max_threads.restype = i32
         f64 = C.c_double
         L.pko_dynamics_step.argtypes = [u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp]
+        L.pko_setup_contacts.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp, u64]
+        L.pko_setup_contacts.restype = u64
         L.pko_ray_box.argtypes = [vp, vp, vp, f64, vp]
         L.pko_ray_box.restype = i32
         L.pko_bvh_raycast.argtypes = [vp, vp, vp, f64, i32, vp, vp, u64]
@@ -419,6 +421,18 @@ class Manifolds:
         pts = np.zeros((max(m, 1), 4, 13))
         lib().pko_man_get(self.h, _p(keys), _p(counts), _p(pts), max(m, 1))
         return keys[:m], counts[:m], pts[:m]
+
+    def setup_contacts(self, pos, quat, vel, ang_vel, mass, inertia, restitution, friction, dt, gravity_norm):
+        """constraint_solver::setup_contacts (constraint.h:1052-1104) → (keys, point index, rows[k, 40])."""
+        n = len(pos)
+        args = [_f64(pos, (n, 3)), _f64(quat, (n, 4)), _f64(vel, (n, 3)), _f64(ang_vel, (n, 3)), _f64(mass, (n,)), _f64(inertia, (n, 9)),
+                _f64(restitution, (n,)), _f64(friction, (n,))]
+        cap = 4 * max(1, len(self.get()[0]))
+        rows = np.zeros((cap, 40))
+        keys = np.zeros(cap, dtype=np.uint64)
+        pts = np.zeros(cap, dtype=np.uint32)
+        k = lib().pko_setup_contacts(self.h, *[_p(a) for a in args], float(dt), float(gravity_norm), _p(rows), _p(keys), _p(pts), cap)
+        return keys[:k].copy(), pts[:k].copy(), rows[:k].copy()
 
     def set_impulses(self, imp):
         imp = _f64(imp, (-1, 4, 3))

@@ -1036,6 +1036,115 @@ inline void step_position(rigid_state &o, double dt)
     o.update_derived_state();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Contact Jacobians — include/physkit/collision/constraint.h:104-113 (build_orthonormal_basis), :874-953
+// (build_contact_jacobian), :1052-1104 (setup_contacts).  SURVEY §8 f2.
+// ---------------------------------------------------------------------------------------------
+struct jacobian_row_t // constraint.h:29-47, the fields setup_contacts fills
+{
+    v3 J_v{}, J_w_a{}, J_w_b{};
+    double M_eff = 0.0, bias = 0.0;
+};
+struct contact_solver_point_t // constraint.h:1204-1214 + the warm-start impulses (:1096-1098)
+{
+    jacobian_row_t normal, tangent1, tangent2;
+    double friction_coeff = 0.0, inv_m_11 = 0.0, inv_m_12 = 0.0, inv_m_22 = 0.0;
+    double accumulated[3] = {0.0, 0.0, 0.0};
+};
+struct body_dyn_t // what build_contact_jacobian reads of an object
+{
+    v3 pos, vel, ang_vel;
+    quat q;
+    double inv_mass;
+    m3 inv_inertia_world;
+    double restitution, friction;
+};
+
+// constraint.h:104-113
+inline std::pair<v3, v3> build_orthonormal_basis(v3 n)
+{
+    double sign = std::copysign(1.0, n.z);
+    const double a = -1.0 / (sign + n.z);
+    const double b = n.x * n.y * a;
+    return {v3{1.0 + sign * n.x * n.x * a, sign * b, -sign * n.x}, v3{b, sign + n.y * n.y * a, -n.y}};
+}
+
+// constraint.h:874-953 followed by the per-contact part of setup_contacts (:1069-1099)
+inline std::optional<contact_solver_point_t> setup_contact(const body_dyn_t &a, const body_dyn_t &b, const contact_info_t &contact,
+                                                           double dt, double gravity_norm)
+{
+    constexpr double bias_factor = .1;
+    constexpr double linear_slop = 0.005;
+    const double restitution_threshold = 2 * gravity_norm * dt; // :1071
+    v3 nn = normalized(contact.normal);
+    v3 local_normal_b = rotate(conjugate(b.q), nn);
+    v3 r_a = rotate(a.q, contact.local_a);
+    v3 r_b = rotate(b.q, contact.local_b);
+    v3 n = rotate(b.q, local_normal_b);
+    double penetration = dot((b.pos + r_b) - (a.pos + r_a), n);
+    if (penetration <= 0.0) return std::nullopt;
+
+    contact_solver_point_t p;
+    auto m_eff = [&](const jacobian_row_t &row)
+    {
+        v3 k_a = mul(a.inv_inertia_world, row.J_w_a);
+        v3 k_b = mul(b.inv_inertia_world, row.J_w_b);
+        return 1.0 / (a.inv_mass + b.inv_mass + dot(row.J_w_a, k_a) + dot(row.J_w_b, k_b));
+    };
+    {
+        jacobian_row_t row;
+        row.J_v = n;
+        row.J_w_a = cross(r_a, n);
+        row.J_w_b = -cross(r_b, n);
+        row.M_eff = m_eff(row);
+        v3 v_ca = a.vel + cross(a.ang_vel, r_a);
+        v3 v_cb = b.vel + cross(b.ang_vel, r_b);
+        double v_rel_n = dot(v_ca - v_cb, n);
+        double restitution_coeff = std::max(a.restitution, b.restitution);
+        double restitution_bias = 0.0;
+        if (v_rel_n < -restitution_threshold) restitution_bias = restitution_coeff * v_rel_n;
+        double baumgarte_bias = (-bias_factor / dt) * std::max(0.0, penetration - linear_slop);
+        row.bias = std::min(baumgarte_bias, restitution_bias);
+        p.normal = row;
+    }
+    auto build_tangent = [&](v3 tangent)
+    {
+        jacobian_row_t row;
+        row.J_v = tangent;
+        row.J_w_a = cross(r_a, tangent);
+        row.J_w_b = -cross(r_b, tangent);
+        row.bias = 0.0;
+        row.M_eff = m_eff(row);
+        return row;
+    };
+    auto [t1, t2] = build_orthonormal_basis(n);
+    p.tangent1 = build_tangent(t1);
+    p.tangent2 = build_tangent(t2);
+
+    p.friction_coeff = std::sqrt(a.friction * b.friction);
+    double m11 = 1.0 / p.tangent1.M_eff;
+    double m22 = 1.0 / p.tangent2.M_eff;
+    double m12 = dot(p.tangent1.J_w_a, mul(a.inv_inertia_world, p.tangent2.J_w_a)) +
+                 dot(p.tangent1.J_w_b, mul(b.inv_inertia_world, p.tangent2.J_w_b));
+    double det = m11 * m22 - m12 * m12;
+    if (det > 0.0)
+    {
+        p.inv_m_11 = m22 / det;
+        p.inv_m_22 = m11 / det;
+        p.inv_m_12 = -m12 / det;
+    }
+    else
+    {
+        p.inv_m_11 = p.tangent1.M_eff;
+        p.inv_m_22 = p.tangent2.M_eff;
+        p.inv_m_12 = 0.0;
+    }
+    p.accumulated[0] = contact.normal_impulse;
+    p.accumulated[1] = contact.tangent_impulses[0];
+    p.accumulated[2] = contact.tangent_impulses[1];
+    return p;
+}
+
 // collision.cpp:512-518
 inline std::optional<collision_info> gjk_epa(const shape &a, const shape &b, gjk_stats *st = nullptr)
 {

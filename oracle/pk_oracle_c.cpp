@@ -296,6 +296,73 @@ void pko_man_set_impulses(void *h, const double *imp)
     }
 }
 
+// constraint_solver::setup_contacts (constraint.h:1052-1104) over the manifolds of h in key order, points in
+// manifold order; bodies from flat arrays (inertia9: local tensor, row-major; the world inverse tensor is
+// derived like particle::update_derived_state).  rows[k][44] = normal / tangent1 / tangent2 as
+// (J_v 3, J_w_a 3, J_w_b 3, M_eff, bias) + friction_coeff, inv_m_11, inv_m_12, inv_m_22 + accumulated[3] = 40,
+// padded to 44 with key (as two u32 halves stored in doubles would lose nothing, but keys_out carries it),
+// point_out[k] = index of the point in its manifold.  Returns the number of rows (may exceed cap).
+uint64_t pko_setup_contacts(void *h, const double *pos, const double *quat_xyzw, const double *vel, const double *ang_vel,
+                            const double *mass, const double *inertia9, const double *restitution, const double *friction,
+                            double dt, double gravity_norm, double *rows40, uint64_t *keys_out, uint32_t *point_out, uint64_t cap)
+{
+    pko_manifolds &st = *static_cast<pko_manifolds *>(h);
+    auto body = [&](uint32_t i)
+    {
+        body_dyn_t b;
+        b.pos = ld3(pos + 3 * i);
+        b.vel = ld3(vel + 3 * i);
+        b.ang_vel = ld3(ang_vel + 3 * i);
+        b.q = ldq(quat_xyzw + 4 * i);
+        b.inv_mass = 1.0 / mass[i];
+        rigid_state o;
+        o.q = b.q;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) o.inertia_local.m[r][c] = inertia9[9 * static_cast<uint64_t>(i) + 3 * r + c];
+        o.inv_inertia_local = (b.inv_mass == 0.0) ? m3{} : inverse(o.inertia_local);
+        o.update_derived_state();
+        b.inv_inertia_world = o.inv_inertia_world;
+        b.restitution = restitution[i];
+        b.friction = friction[i];
+        return b;
+    };
+    uint64_t k = 0;
+    for (const auto &[key, man] : st.mans)
+    {
+        const uint32_t ia = static_cast<uint32_t>(key >> 32), ib = static_cast<uint32_t>(key & 0xFFFFFFFFu);
+        const body_dyn_t a = body(ia), b = body(ib);
+        for (int j = 0; j < man.n; ++j)
+        {
+            auto p = setup_contact(a, b, man.c[j], dt, gravity_norm);
+            if (!p) continue;
+            if (k < cap)
+            {
+                double *o = rows40 + 40 * k;
+                const jacobian_row_t *rw[3] = {&p->normal, &p->tangent1, &p->tangent2};
+                for (int r = 0; r < 3; ++r)
+                {
+                    st3(o + 11 * r, rw[r]->J_v);
+                    st3(o + 11 * r + 3, rw[r]->J_w_a);
+                    st3(o + 11 * r + 6, rw[r]->J_w_b);
+                    o[11 * r + 9] = rw[r]->M_eff;
+                    o[11 * r + 10] = rw[r]->bias;
+                }
+                o[33] = p->friction_coeff;
+                o[34] = p->inv_m_11;
+                o[35] = p->inv_m_12;
+                o[36] = p->inv_m_22;
+                o[37] = p->accumulated[0];
+                o[38] = p->accumulated[1];
+                o[39] = p->accumulated[2];
+                keys_out[k] = key;
+                point_out[k] = static_cast<uint32_t>(j);
+            }
+            ++k;
+        }
+    }
+    return k;
+}
+
 // ------------------------------- dynamic_bvh handle API ---------------------------------------
 void *pko_bvh_create() { return new dynamic_bvh(); }
 void pko_bvh_destroy(void *t) { delete static_cast<dynamic_bvh *>(t); }

@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     PkError,
     contact_dtype,
     ray_hit_dtype,
+    solver_point_dtype,
     gjk_epa,
     library_path,
     load_library,

@@ -27,6 +27,11 @@ contact_dtype = np.dtype(
     [("key", np.uint64), ("normal", np.float64, 3), ("world_a", np.float64, 3), ("world_b", np.float64, 3), ("depth", np.float64)]
 )
 assert contact_dtype.itemsize == 88
+solver_row_dtype = np.dtype([("J_v", "<f8", (3,)), ("J_w_a", "<f8", (3,)), ("J_w_b", "<f8", (3,)), ("M_eff", "<f8"), ("bias", "<f8")])
+solver_point_dtype = np.dtype([("key", "<u8"), ("manifold", "<u4"), ("point", "<u4"), ("normal", solver_row_dtype),
+                               ("tangent1", solver_row_dtype), ("tangent2", solver_row_dtype), ("friction_coeff", "<f8"),
+                               ("inv_m_11", "<f8"), ("inv_m_12", "<f8"), ("inv_m_22", "<f8"), ("accumulated", "<f8", (3,))])
+assert solver_point_dtype.itemsize == 336
 ray_hit_dtype = np.dtype([("ray", np.uint32), ("body", np.uint32), ("distance", np.float64)])
 assert ray_hit_dtype.itemsize == 16
 RAY_ALL, RAY_CLOSEST = 0, 1
@@ -95,6 +100,7 @@ EXPORTS = [
     "pk_gjk_epa_batch", "pk_gjk_epa_batch_device", "pk_raycast", "pk_raycast_device_ms",
     "pk_dynamics_enable", "pk_dynamics_upload", "pk_dynamics_set_velocities", "pk_dynamics_set_forces",
     "pk_integrate_velocities", "pk_integrate_positions", "pk_dynamics_download", "pk_displacements",
+    "pk_material_upload", "pk_contact_rows_setup", "pk_contact_rows", "pk_contact_rows_device",
     "pk_device_alloc", "pk_device_free", "pk_memcpy_h2d", "pk_memcpy_d2h", "pk_memcpy_d2d", "pk_host_alloc", "pk_host_free",
 ]
 
@@ -129,6 +135,10 @@ def load_library():
     L.pk_integrate_positions.argtypes = [vp, C.c_double]
     L.pk_dynamics_download.argtypes = [vp, vp, vp, vp, vp, u32, u32]
     L.pk_displacements.argtypes = [vp, vp, u32, u32]
+    L.pk_material_upload.argtypes = [vp, vp, vp, u32, u32]
+    L.pk_contact_rows_setup.argtypes = [vp, C.c_double, C.c_double, vp]
+    L.pk_contact_rows.argtypes = [vp, vp, vp]
+    L.pk_contact_rows_device.argtypes = [vp, vp, vp, vp]
     L.pk_manifolds_enable.argtypes = [vp, C.c_uint64]
     L.pk_manifolds_update.argtypes = [vp, vp]
     L.pk_manifolds.argtypes = [vp, vp, vp]
@@ -394,6 +404,30 @@ class Context:
         d = np.empty((count, 3))
         self._check(self.L.pk_displacements(self.h, _p(d), int(first), int(count)))
         return d
+
+    # -- contact rows: constraint_solver::setup_contacts on the device (constraint.h:1052-1104)
+    def material_upload(self, restitution, friction, first=0):
+        r = _arr(restitution, np.float64).reshape(-1)
+        f = _arr(friction, np.float64).reshape(-1)
+        self._check(self.L.pk_material_upload(self.h, _p(r), _p(f), int(first), len(r)))
+
+    def contact_rows_setup(self, dt, gravity_norm=9.81):
+        n = C.c_uint64()
+        self._check(self.L.pk_contact_rows_setup(self.h, float(dt), float(gravity_norm), C.byref(n)))
+        return int(n.value)
+
+    def contact_rows(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.L.pk_contact_rows(self.h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=solver_point_dtype)
+        buf = (C.c_char * (solver_point_dtype.itemsize * n.value)).from_address(p.value)
+        return np.frombuffer(buf, dtype=solver_point_dtype).copy()
+
+    def contact_rows_device_ms(self):
+        p, n, ms = C.c_void_p(), C.c_uint64(), C.c_float()
+        self._check(self.L.pk_contact_rows_device(self.h, C.byref(p), C.byref(n), C.byref(ms)))
+        return float(ms.value)
 
     # -- ray casts over the tree of the last step (world_base::raycast, core/world.h:260-319)
     def raycast(self, origins, directions, max_distance, world=None, mode=RAY_ALL, capacity=None):

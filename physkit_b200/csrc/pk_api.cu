@@ -13,6 +13,7 @@
 #include "pk_manifold.cuh"
 #include "pk_dynamics.cuh"
 #include "pk_ray.cuh"
+#include "pk_solver.cuh"
 #include "pk_sort.cuh"
 
 #include <algorithm>
@@ -170,6 +171,17 @@ struct pk_ctx
     DynArrays dyn{};
     cudaEvent_t ev_dyn[2]{};
     float dyn_ms = 0.f;
+    double *d_material = nullptr; // [n][2] restitution, friction (core/object.h:90-91)
+    // contact rows (pk_contact_rows_setup): allocated on first use, 4 point slots per manifold
+    uint64_t sol_cap = 0, sol_count = 0;
+    uint8_t *d_sol_valid = nullptr;
+    uint32_t *d_sol_index = nullptr, *d_sol_tiles = nullptr;
+    SolverPoint *d_sol_rows = nullptr;
+    unsigned long long *d_sol_total = nullptr;
+    pk_solver_point *h_sol_rows = nullptr;
+    size_t h_sol_cap = 0;
+    cudaEvent_t ev_sol[2]{};
+    float sol_ms = 0.f;
 
     // ray casts (pk_raycast): buffers allocated on first use
     uint32_t tree_m = 0;      // leaves of the tree the last step built (0: none, < 2 bodies alive)
@@ -513,6 +525,12 @@ int pk_destroy(pk_ctx *ctx)
                     static_cast<void *>(ctx->dyn.inertia_w)})
         if (q) cudaFree(q);
     for (auto &e : ctx->ev_dyn)
+        if (e) cudaEventDestroy(e);
+    for (void *q : {static_cast<void *>(ctx->d_material), static_cast<void *>(ctx->d_sol_valid), static_cast<void *>(ctx->d_sol_index),
+                    static_cast<void *>(ctx->d_sol_tiles), static_cast<void *>(ctx->d_sol_rows), static_cast<void *>(ctx->d_sol_total)})
+        if (q) cudaFree(q);
+    if (ctx->h_sol_rows) cudaFreeHost(ctx->h_sol_rows);
+    for (auto &e : ctx->ev_sol)
         if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -1131,6 +1149,11 @@ int pk_dynamics_enable(pk_ctx *ctx)
     PK_TRY(dev_alloc(ctx, &ctx->dyn.mass, 2 * nb));
     PK_TRY(dev_alloc(ctx, &ctx->dyn.inertia, 18 * nb));
     PK_TRY(dev_alloc(ctx, &ctx->dyn.inertia_w, 18 * nb));
+    PK_TRY(dev_alloc(ctx, &ctx->d_material, 2 * nb));
+    {
+        std::vector<double> half(2 * nb, 0.5); // object_desc defaults: restitution 0.5, friction 0.5 (core/object.h:107-108)
+        PK_CUDA(cudaMemcpy(ctx->d_material, half.data(), half.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     for (double *p : {ctx->dyn.vel, ctx->dyn.ang_vel, ctx->dyn.acc, ctx->dyn.torque})
         PK_CUDA(cudaMemsetAsync(p, 0, 3 * nb * sizeof(double), ctx->stream));
     PK_CUDA(cudaEventCreate(&ctx->ev_dyn[0]));
@@ -1256,6 +1279,109 @@ int pk_displacements(pk_ctx *ctx, double *disp, uint32_t first, uint32_t count)
     cudaSetDevice(ctx->cfg.device);
     PK_CUDA(cudaMemcpyAsync(disp, ctx->d_disp + 3ull * first, 3ull * count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ contact rows
+int pk_material_upload(pk_ctx *ctx, const double *restitution, const double *friction, uint32_t first, uint32_t count)
+{
+    if (!ctx || !restitution || !friction) return PK_E_INVALID;
+    if (!ctx->dyn_enabled) return PK_E_STATE;
+    if (static_cast<uint64_t>(first) + count > ctx->n_bodies) return PK_E_INVALID;
+    if (count == 0) return PK_OK;
+    cudaSetDevice(ctx->cfg.device);
+    std::vector<double> m(2ull * count);
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        m[2ull * i] = restitution[i];
+        m[2ull * i + 1] = friction[i];
+    }
+    PK_CUDA(cudaMemcpyAsync(ctx->d_material + 2ull * first, m.data(), m.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+
+int pk_contact_rows_setup(pk_ctx *ctx, double dt, double gravity_norm, uint64_t *nrows)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (!ctx->dyn_enabled || !ctx->man_cap)
+    {
+        ctx->last_error = "pk_contact_rows_setup needs pk_dynamics_enable and pk_manifolds_enable";
+        return PK_E_STATE;
+    }
+    static_assert(sizeof(SolverPoint) == sizeof(pk_solver_point), "solver point layouts differ");
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t s = ctx->stream;
+    if (!ctx->d_sol_rows)
+    {
+        const uint64_t cap = 4 * ctx->man_cap;
+        PK_TRY(dev_alloc(ctx, &ctx->d_sol_valid, cap + 16));
+        PK_TRY(dev_alloc(ctx, &ctx->d_sol_index, cap));
+        PK_TRY(dev_alloc(ctx, &ctx->d_sol_tiles, div_up(cap, SCAN_TILE) + 1));
+        PK_TRY(dev_alloc(ctx, &ctx->d_sol_total, 1));
+        PK_TRY(dev_alloc(ctx, &ctx->d_sol_rows, cap));
+        PK_CUDA(cudaEventCreate(&ctx->ev_sol[0]));
+        PK_CUDA(cudaEventCreate(&ctx->ev_sol[1]));
+        ctx->sol_cap = cap;
+    }
+    const uint64_t nman = ctx->man_count, slots = 4 * nman;
+    ctx->sol_count = 0;
+    cudaEventRecord(ctx->ev_sol[0], s);
+    if (slots)
+    {
+        const ManifoldRec *man = ctx->d_man[ctx->man_cur];
+        const uint32_t nt = div_up(slots, SCAN_TILE);
+        solver_valid_kernel<<<div_up(slots, 256), 256, 0, s>>>(man, nman, ctx->d_pos, ctx->d_quat, ctx->d_sol_valid);
+        flag_tile_sum_kernel<<<nt, 256, 0, s>>>(ctx->d_sol_valid, slots, ctx->d_sol_tiles);
+        tile_sum_scan_kernel<<<1, 256, 0, s>>>(ctx->d_sol_tiles, nt, ctx->d_sol_total);
+        flag_scan_apply_kernel<<<nt, 256, 0, s>>>(ctx->d_sol_valid, slots, ctx->d_sol_tiles, ctx->d_sol_index);
+        solver_rows_kernel<<<div_up(slots, 128), 128, 0, s>>>(man, nman, ctx->d_pos, ctx->d_quat, ctx->dyn, ctx->d_material, ctx->d_sol_valid,
+                                                             ctx->d_sol_index, dt, gravity_norm, ctx->d_sol_rows);
+        ctx->launches += 5;
+        PK_CUDA(cudaGetLastError());
+        unsigned long long total = 0;
+        cudaEventRecord(ctx->ev_sol[1], s);
+        PK_CUDA(cudaMemcpyAsync(&total, ctx->d_sol_total, sizeof(total), cudaMemcpyDeviceToHost, s));
+        PK_CUDA(cudaStreamSynchronize(s));
+        ctx->sol_count = total;
+        cudaEventElapsedTime(&ctx->sol_ms, ctx->ev_sol[0], ctx->ev_sol[1]);
+    }
+    if (nrows) *nrows = ctx->sol_count;
+    return PK_OK;
+}
+
+int pk_contact_rows(pk_ctx *ctx, const pk_solver_point **rows, uint64_t *n)
+{
+    if (!ctx || !rows || !n) return PK_E_INVALID;
+    if (!ctx->d_sol_rows) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    const uint64_t m = ctx->sol_count;
+    if (m > ctx->h_sol_cap)
+    {
+        if (ctx->h_sol_rows) cudaFreeHost(ctx->h_sol_rows);
+        ctx->h_sol_rows = nullptr;
+        ctx->h_sol_cap = 0;
+        const size_t cap = std::min<size_t>(ctx->sol_cap, std::max<size_t>(m * 5 / 4, 1024));
+        PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_sol_rows), cap * sizeof(pk_solver_point), cudaHostAllocDefault));
+        ctx->h_sol_cap = cap;
+    }
+    if (m)
+    {
+        PK_CUDA(cudaMemcpyAsync(ctx->h_sol_rows, ctx->d_sol_rows, m * sizeof(pk_solver_point), cudaMemcpyDeviceToHost, ctx->stream));
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *rows = ctx->h_sol_rows;
+    *n = m;
+    return PK_OK;
+}
+
+int pk_contact_rows_device(pk_ctx *ctx, const void **dptr, uint64_t *n, float *device_ms)
+{
+    if (!ctx || !dptr || !n) return PK_E_INVALID;
+    if (!ctx->d_sol_rows) return PK_E_STATE;
+    *dptr = ctx->d_sol_rows;
+    *n = ctx->sol_count;
+    if (device_ms) *device_ms = ctx->sol_ms;
     return PK_OK;
 }
 
