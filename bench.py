@@ -176,9 +176,10 @@ STAGE_BYTES_DOC = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per step of the dominant stage from the committed
-# `ncu --set full` capture of this workload at side 100 (profiles/r1_epa_scan_fullsize.md: both instances
-# of epa_scan_kernel, 5.99 GB + 1.65 GB; the thread-per-pair epa_kernel it replaced moved 31 GB); null otherwise
-NCU_TRAFFIC_BYTES = {"epa": 7_637_408_000}
+# `ncu --set full` capture of this workload at side 100 (profiles/r1b_epa_scan_fullsize.md + r1b_epa_heap_fullsize.md:
+# both instances of epa_scan_kernel at 5 blocks / SM, 8.60 GB + 2.46 GB; 4 blocks / SM moved 7.6 GB, the
+# thread-per-pair epa_kernel it replaced 31 GB); null otherwise
+NCU_TRAFFIC_BYTES = {"epa": 11_065_042_000}
 
 
 def stage_bytes(name, n, pairs, hits):
@@ -293,16 +294,44 @@ def run_ours(args, rank, world, local_rank):
     h2d = n * (3 + 4 + 3) * 8
     d2h = int(res_e.num_pairs) * 8 + int(res_e.num_contacts) * 88
 
-    # ---- optional: manifold update on top of the step, not part of the headline ----------
+    # ---- optional: the rows downstream of the stage, not part of the headline -----------------
     manifold_info = None
     if args.manifolds and world == 1:
         ctx.manifolds_enable(min(max_contacts, 4 * max(contacts, 1) + 1024))
-        ms = []
+        ctx.dynamics_enable()
+        rng = np.random.default_rng(1)
+        ctx.dynamics_upload(rng.uniform(-1, 1, (n, 3)), rng.uniform(-1, 1, (n, 3)), np.full(n, 1.0), np.tile(np.eye(3).ravel(), (n, 1)))
+        ms, rows_ms, nrows = [], [], 0
         for s in range(6):
             ctx.update_pose(h_pos[s % 2], h_quat, h_disp)
             ctx.collide_resident()
             ms.append(ctx.manifolds_update())
-        manifold_info = {"manifolds": ms[-1][0], "ms_first_step": ms[0][3], "ms_steady": float(np.median([m[3] for m in ms[2:]]))}
+            nrows = ctx.contact_rows_setup(1.0 / 60.0, 9.81)
+            rows_ms.append(ctx.contact_rows_device_ms())
+        manifold_info = {"manifolds": ms[-1][0], "ms_first_step": ms[0][3], "ms_steady": float(np.median([m[3] for m in ms[2:]])),
+                         "contact_rows": nrows, "contact_rows_ms": float(np.median(rows_ms[2:]))}
+        # integrator loops A + B (pk_integrate_*), timed with events around both launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = torch.cuda.ExternalStream(ctx.stream())
+        t_int = []
+        for _ in range(5):
+            ev0.record(st)
+            ctx.integrate_velocities(1.0 / 60.0)
+            ctx.integrate_positions(1.0 / 60.0)
+            ev1.record(st)
+            ev1.synchronize()
+            t_int.append(ev0.elapsed_time(ev1))
+        manifold_info["integrate_vel_pos_ms"] = float(np.median(t_int[1:]))
+        # 1 M rays against the tree of the last step
+        ctx.update_pose(h_pos[0], h_quat, h_disp)
+        ctx.collide_resident()
+        nr = 1_000_000
+        o = rng.uniform(0.0, args.side * 0.8, (nr, 3))
+        d = rng.uniform(-1, 1, (nr, 3))
+        ray_entries = ctx.raycast(o, d, 0.5, capacity=max_pairs)
+        manifold_info["raycast"] = {"rays": nr, "max_distance_m": 0.5, "entries": int(len(ray_entries)), "device_ms": ctx.raycast_device_ms()}
+        ctx.raycast(o, d, 0.5, mode=pk.RAY_CLOSEST, capacity=nr)
+        manifold_info["raycast"]["closest_device_ms"] = ctx.raycast_device_ms()
 
     # ---- reduce over ranks (max time, sum pairs) ---------------------------------------------------
     tot_pairs, tot_contacts, max_wall, max_e2e = pairs, contacts, wall_ms, e2e_ms
@@ -355,7 +384,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"C3: {n}-body jittered lattice (side {args.side}), analytic spheres + OBBs, world-mode fat-AABB pairs",
                        "bodies": n, "pairs_per_step": tot_pairs, "contacts_per_step": tot_contacts,
                        "epa_fallback_pairs": getattr(ctx, "epa_fallback", None),
-                       **({"manifold_update": manifold_info} if manifold_info else {}),
+                       **({"downstream_rows": manifold_info} if manifold_info else {}),
                        "sharding": "pairs by sorted-leaf range, tree rebuilt per rank, one all-gather of contacts" if world > 1 else "none",
                        "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush",
                        "timing": "wall clock around K synchronous steps bracketed by barrier+synchronize, max over ranks; "
@@ -495,7 +524,7 @@ def main():
     ap.add_argument("--cpu-side", type=int, default=50, help="lattice side of the cpu_baseline sample")
     ap.add_argument("--ref-side", type=int, default=40, help="lattice side of the --impl reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--manifolds", action="store_true", help="also time pk_manifolds_update (reported under config)")
+    ap.add_argument("--manifolds", action="store_true", help="also time the downstream rows (manifolds, contact rows, integrator, ray casts; reported under config)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"], help="c3 is the headline; c4/c5 are extra configs")
     ap.add_argument("--pairs", type=int, default=2_000_000, help="c4: number of hull pairs")
     ap.add_argument("--worlds", type=int, default=4096, help="c5: number of independent worlds")

@@ -82,6 +82,7 @@ struct pk_ctx
     cudaStream_t copy_stream = nullptr; // pk_collide: pair keys go to the host while the narrowphase runs
     cudaEvent_t ev_sorted = nullptr, ev_pairs_copied = nullptr;
     bool want_host_results = false, pairs_in_flight = false;
+    bool contacts_mirrored = false; // pk_collide: EPA stored the contact records of this step into h_contacts as well
     std::string last_error;
     int sm_count = 0;
 
@@ -293,7 +294,7 @@ int bits_for(uint64_t n) // bits needed to represent values < n
 }
 
 // LSD radix sort over the listed byte shifts; returns the index (0/1) of the buffer holding the result.
-int radix_sort(pk_ctx *ctx, uint64_t *keys[2], uint32_t *vals[2], uint64_t n, const std::vector<int> &shifts, int *result)
+int radix_sort(pk_ctx *ctx, uint64_t *keys[2], uint32_t *vals[2], uint64_t n, const std::vector<int> &shifts, int *result, int lowbits = 0)
 {
     int cur = 0;
     uint32_t ntiles = div_up(n, SORT_TILE);
@@ -304,14 +305,14 @@ int radix_sort(pk_ctx *ctx, uint64_t *keys[2], uint32_t *vals[2], uint64_t n, co
     }
     for (int shift : shifts)
     {
-        radix_hist_kernel<<<ntiles, SORT_THREADS, 0, ctx->stream>>>(keys[cur], n, shift, ctx->d_tile_hist, ntiles);
+        radix_hist_kernel<<<ntiles, SORT_THREADS, 0, ctx->stream>>>(keys[cur], n, shift, lowbits, ctx->d_tile_hist, ntiles);
         radix_scan_kernel<<<256, SORT_THREADS, 0, ctx->stream>>>(ctx->d_tile_hist, ntiles, ctx->d_digit_total);
         if (vals)
             radix_scatter_kernel<true><<<ntiles, SORT_THREADS, 0, ctx->stream>>>(
-                keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
+                keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, lowbits, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
         else
             radix_scatter_kernel<false><<<ntiles, SORT_THREADS, 0, ctx->stream>>>(
-                keys[cur], nullptr, keys[cur ^ 1], nullptr, n, shift, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
+                keys[cur], nullptr, keys[cur ^ 1], nullptr, n, shift, lowbits, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
         ctx->launches += 3;
         cur ^= 1;
     }
@@ -372,7 +373,7 @@ BodyArrays body_arrays(pk_ctx *ctx)
 // GJK → scan → EPA over npairs pairs given either as sorted keys or as explicit index arrays.
 // Leaves contacts (slot order = pair order among GJK hits) in ctx->d_contacts[0], validity in d_valid.
 int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, const uint32_t *d_b, uint64_t npairs,
-                    bool timed)
+                    bool timed, ContactRec *mirror = nullptr)
 {
     if (timed) cudaEventRecord(ctx->ev[ST_GJK], ctx->stream);
     if (npairs)
@@ -403,7 +404,7 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs, ctx->d_counters + C_EPA_CURSOR,
-            ctx->d_counters + C_VALID);
+            ctx->d_counters + C_VALID, mirror);
         ctx->launches += 2;
 #else
         // Pairs with a sphere: heap-free pop (SCAN instance).  What it hands back (exact distance ties that
@@ -419,17 +420,17 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
             ctx->d_counters + C_EPA_SCAN_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr, ctx->d_epa_init);
+            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr, ctx->d_epa_init, mirror);
         epa_scan_kernel<true><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
             ctx->d_counters + C_EPA_SCAN_CURSOR + 1, ctx->d_counters + C_VALID, ctx->d_epa_fallback2,
             ctx->d_counters + C_EPA_FALLBACK + 1, ctx->d_counters + C_CLASS_COUNT, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK, ctx->d_epa_init);
+            ctx->d_counters + C_EPA_FALLBACK, ctx->d_epa_init, mirror);
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK + 1, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_fallback2, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
-            ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID);
+            ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID, mirror);
         ctx->launches += 5;
 #endif
     }
@@ -924,11 +925,11 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         }
         if (npairs)
         {
+            // (min id, max id) fields packed to 2·idbits significant bits: ceil(2·idbits / 8) passes
             int idbits = bits_for(n);
             std::vector<int> shifts;
-            for (int b = 0; b < idbits; b += 8) shifts.push_back(b);
-            for (int b = 0; b < idbits; b += 8) shifts.push_back(32 + b);
-            PK_TRY(radix_sort(ctx, ctx->d_pkeys, nullptr, npairs, shifts, &pair_buf));
+            for (int b = 0; b < 2 * idbits; b += 8) shifts.push_back(b);
+            PK_TRY(radix_sort(ctx, ctx->d_pkeys, nullptr, npairs, shifts, &pair_buf, idbits));
         }
     }
     else
@@ -948,7 +949,26 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         cudaEventRecord(ctx->ev_pairs_copied, ctx->copy_stream);
         ctx->pairs_in_flight = true;
     }
-    PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true));
+    // pk_collide: the EPA kernels store every contact record a second time, straight into the caller-visible
+    // pinned buffer (zero-copy stores over PCIe, spread over the ≈15 ms the kernels run), so that the
+    // 88 B × contacts device→host copy does not wait for them to end.  Only when the pinned buffer for
+    // max_contacts records is affordable; a step whose contacts need compaction falls back to the copy.
+    ContactRec *mirror = nullptr;
+    ctx->contacts_mirrored = false;
+    if (ctx->want_host_results && npairs && ctx->max_contacts * sizeof(pk_contact) <= (2ull << 30) && !getenv("PK_NO_MIRROR"))
+    {
+        if (ctx->h_contacts_cap < ctx->max_contacts)
+        {
+            if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
+            ctx->h_contacts = nullptr;
+            ctx->h_contacts_cap = 0;
+            PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_contacts), ctx->max_contacts * sizeof(pk_contact), cudaHostAllocDefault));
+            ctx->h_contacts_cap = ctx->max_contacts;
+        }
+        mirror = reinterpret_cast<ContactRec *>(ctx->h_contacts);
+        ctx->contacts_mirrored = true;
+    }
+    PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true, mirror));
     PK_TRY(read_counters(ctx));
     uint64_t hits = ctx->h_counters[C_HITS];
     uint64_t valid = ctx->h_counters[C_VALID];
@@ -961,6 +981,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         hits = ctx->max_contacts;
     }
     ctx->d_contacts_final = ctx->d_contacts[0];
+    if (status != PK_OK) ctx->contacts_mirrored = false;
     if (status == PK_OK && valid != hits)
     {
         // some GJK hits ended without a value in EPA (degenerate pad / exhausted heap / overflow)
@@ -974,6 +995,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
                                                                  static_cast<int>(sizeof(ContactRec)));
         ctx->launches += 4;
         ctx->d_contacts_final = ctx->d_contacts[1];
+        ctx->contacts_mirrored = false;
         PK_CUDA(cudaGetLastError());
     }
     cudaEventRecord(ctx->ev[ST_FETCH], s);
@@ -1034,7 +1056,7 @@ int pk_fetch_results(pk_ctx *ctx)
         PK_CUDA(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs_sorted, ctx->num_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                 ctx->stream));
     ctx->pairs_in_flight = false;
-    if (ctx->num_contacts)
+    if (ctx->num_contacts && !ctx->contacts_mirrored) // (mirrored: the EPA kernels already stored them there)
         PK_CUDA(cudaMemcpyAsync(ctx->h_contacts, ctx->d_contacts_final, ctx->num_contacts * sizeof(pk_contact),
                                 cudaMemcpyDeviceToHost, ctx->stream));
     cudaEventRecord(ctx->ev[ST_COUNT], ctx->stream);
@@ -1581,15 +1603,14 @@ int pk_manifolds_update(pk_ctx *ctx, pk_manifold_result *out)
     }
     const int idbits = bits_for(std::max<uint32_t>(ctx->n_bodies, 2));
     std::vector<int> shifts;
-    for (int b = 0; b < idbits; b += 8) shifts.push_back(b);
-    for (int b = 0; b < idbits; b += 8) shifts.push_back(32 + b);
+    for (int b = 0; b < 2 * idbits; b += 8) shifts.push_back(b);
     int buf = 0;
-    if (cnt[0] > 1) PK_TRY(radix_sort(ctx, ctx->d_man_ckeys, ctx->d_man_csrc, cnt[0], shifts, &buf));
+    if (cnt[0] > 1) PK_TRY(radix_sort(ctx, ctx->d_man_ckeys, ctx->d_man_csrc, cnt[0], shifts, &buf, idbits));
     if (cnt[0])
         manifold_gather_kernel<<<div_up(cnt[0], 128), 128, 0, s>>>(ctx->d_man_csrc[buf], cnt[0], ctx->d_man_stage, next);
     ctx->man_began_buf = ctx->man_ended_buf = 0;
-    if (cnt[2] > 1) PK_TRY(radix_sort(ctx, ctx->d_man_began, nullptr, cnt[2], shifts, &ctx->man_began_buf));
-    if (cnt[3] > 1) PK_TRY(radix_sort(ctx, ctx->d_man_ended, nullptr, cnt[3], shifts, &ctx->man_ended_buf));
+    if (cnt[2] > 1) PK_TRY(radix_sort(ctx, ctx->d_man_began, nullptr, cnt[2], shifts, &ctx->man_began_buf, idbits));
+    if (cnt[3] > 1) PK_TRY(radix_sort(ctx, ctx->d_man_ended, nullptr, cnt[3], shifts, &ctx->man_ended_buf, idbits));
     PK_CUDA(cudaGetLastError());
     cudaEventRecord(ctx->ev[1], s);
     PK_CUDA(cudaStreamSynchronize(s));

@@ -5,7 +5,7 @@
 // tile counts)  →  radix_scatter_kernel (stable scatter).  Inside a tile the ranking is done per warp
 // with match.any, so keys stay in registers and the only shared memory is the 8 KB of per-warp digit
 // counters.  Only the byte positions that can be non-zero are sorted (pair keys of N bodies need
-// 2·ceil(log2 N / 8) passes, not 8).
+// ceil(2·log2 N / 8) passes, not 8: sort_digit packs the two id fields).
 #pragma once
 
 #include <cstdint>
@@ -19,6 +19,15 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 keys per block
 
+// Digit of a pass.  Pair keys are (min id << 32) | max id with ids below 2^b: their 2b significant bits sit in
+// two fields.  With lowbits = b the fields are packed next to each other before the digit is taken, so that
+// a million-body scene (b = 20) sorts its pairs in five 8-bit passes instead of six.  lowbits = 0: plain key.
+__device__ __forceinline__ uint32_t sort_digit(uint64_t key, int shift, int lowbits)
+{
+    if (lowbits) key = (key & ((1ull << lowbits) - 1ull)) | ((key >> 32) << lowbits);
+    return static_cast<uint32_t>(key >> shift) & 0xFFu;
+}
+
 // item r of warp w, lane l  ↔  tile offset w·(32·ITEMS) + r·32 + l   (warp-contiguous ⇒ stable)
 __device__ __forceinline__ uint64_t sort_index(uint64_t tile_base, int warp, int round, int lane)
 {
@@ -26,7 +35,7 @@ __device__ __forceinline__ uint64_t sort_index(uint64_t tile_base, int warp, int
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint32_t *__restrict__ tile_hist,
+radix_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift, int lowbits, uint32_t *__restrict__ tile_hist,
                   uint32_t ntiles)
 {
     __shared__ uint32_t hist[256];
@@ -37,7 +46,7 @@ radix_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint
     for (int r = 0; r < SORT_ITEMS; ++r)
     {
         uint64_t i = base + static_cast<uint64_t>(r) * SORT_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&hist[(keys[i] >> shift) & 0xFFu], 1u);
+        if (i < n) atomicAdd(&hist[sort_digit(keys[i], shift, lowbits)], 1u);
     }
     __syncthreads();
     tile_hist[static_cast<uint64_t>(threadIdx.x) * ntiles + blockIdx.x] = hist[threadIdx.x];
@@ -92,7 +101,7 @@ radix_scan_kernel(uint32_t *__restrict__ tile_hist, uint32_t ntiles, uint32_t *_
 template <bool HAS_VALS>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint64_t n, int shift,
+                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint64_t n, int shift, int lowbits,
                      const uint32_t *__restrict__ tile_hist, uint32_t ntiles, const uint32_t *__restrict__ digit_total)
 {
     __shared__ uint32_t warp_cnt[SORT_WARPS][256];
@@ -115,7 +124,7 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
         uint64_t i = sort_index(base, warp, r, lane);
         bool ok = i < n;
         key[r] = ok ? keys_in[i] : 0xFFFFFFFFFFFFFFFFull;
-        uint32_t d = static_cast<uint32_t>(key[r] >> shift) & 0xFFu;
+        uint32_t d = sort_digit(key[r], shift, lowbits);
         // out-of-range lanes take a private pseudo-digit so they match nobody real
         uint32_t md = ok ? d : (256u + lane);
         uint32_t peers = __match_any_sync(0xFFFFFFFFu, md);
@@ -144,7 +153,7 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
         uint64_t i = sort_index(base, warp, r, lane);
         if (i < n)
         {
-            uint32_t d = static_cast<uint32_t>(key[r] >> shift) & 0xFFu;
+            uint32_t d = sort_digit(key[r], shift, lowbits);
             uint32_t pos = warp_cnt[warp][d] + rank[r];
             keys_out[pos] = key[r];
             if (HAS_VALS) vals_out[pos] = vals_in[i];
