@@ -244,7 +244,7 @@ def run_ours(args, rank, world, local_rank):
         ptr, cnt = ctx.contacts_device()
         if cnt:
             ctx.d2d(send.data_ptr(), ptr, cnt * 88)
-        g, counts = allgather_records(send, cnt)
+        g, counts = allgather_records(send, cnt, concat=False)
         return g
 
     def sync_all():
@@ -291,6 +291,7 @@ def run_ours(args, rank, world, local_rank):
     sync_all()
     e1 = time.perf_counter()
     e2e_ms = 1e3 * (e1 - e0) / args.steps
+    e2e_stages = {k: round(v, 4) for k, v in ctx.stage_times()[0].items()}  # device times of the last end-to-end step
     h2d = n * (3 + 4 + 3) * 8
     d2h = int(res_e.num_pairs) * 8 + int(res_e.num_contacts) * 88
 
@@ -392,7 +393,7 @@ def run_ours(args, rank, world, local_rank):
                        "poses": "alternate P0/P1 inside the fat boxes (resting pile: no re-insertions after warm-up)"},
             "device_ms_per_step": dev_step_ms,
             "e2e": {"value": tot_pairs / (max_e2e * 1e-3), "unit": UNIT, "ms_per_step": max_e2e,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "stages_ms_last_step": e2e_stages},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,

@@ -82,7 +82,6 @@ struct pk_ctx
     cudaStream_t copy_stream = nullptr; // pk_collide: pair keys go to the host while the narrowphase runs
     cudaEvent_t ev_sorted = nullptr, ev_pairs_copied = nullptr;
     bool want_host_results = false, pairs_in_flight = false;
-    bool contacts_mirrored = false; // pk_collide: EPA stored the contact records of this step into h_contacts as well
     std::string last_error;
     int sm_count = 0;
 
@@ -373,7 +372,7 @@ BodyArrays body_arrays(pk_ctx *ctx)
 // GJK → scan → EPA over npairs pairs given either as sorted keys or as explicit index arrays.
 // Leaves contacts (slot order = pair order among GJK hits) in ctx->d_contacts[0], validity in d_valid.
 int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, const uint32_t *d_b, uint64_t npairs,
-                    bool timed, ContactRec *mirror = nullptr)
+                    bool timed)
 {
     if (timed) cudaEventRecord(ctx->ev[ST_GJK], ctx->stream);
     if (npairs)
@@ -404,7 +403,7 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs, ctx->d_counters + C_EPA_CURSOR,
-            ctx->d_counters + C_VALID, mirror);
+            ctx->d_counters + C_VALID);
         ctx->launches += 2;
 #else
         // Pairs with a sphere: heap-free pop (SCAN instance).  What it hands back (exact distance ties that
@@ -420,17 +419,17 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
             ctx->d_counters + C_EPA_SCAN_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr, ctx->d_epa_init, mirror);
+            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr, ctx->d_epa_init);
         epa_scan_kernel<true><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
             ctx->d_counters + C_EPA_SCAN_CURSOR + 1, ctx->d_counters + C_VALID, ctx->d_epa_fallback2,
             ctx->d_counters + C_EPA_FALLBACK + 1, ctx->d_counters + C_CLASS_COUNT, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK, ctx->d_epa_init, mirror);
+            ctx->d_counters + C_EPA_FALLBACK, ctx->d_epa_init);
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK + 1, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_fallback2, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
-            ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID, mirror);
+            ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID);
         ctx->launches += 5;
 #endif
     }
@@ -949,26 +948,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         cudaEventRecord(ctx->ev_pairs_copied, ctx->copy_stream);
         ctx->pairs_in_flight = true;
     }
-    // pk_collide: the EPA kernels store every contact record a second time, straight into the caller-visible
-    // pinned buffer (zero-copy stores over PCIe, spread over the ≈15 ms the kernels run), so that the
-    // 88 B × contacts device→host copy does not wait for them to end.  Only when the pinned buffer for
-    // max_contacts records is affordable; a step whose contacts need compaction falls back to the copy.
-    ContactRec *mirror = nullptr;
-    ctx->contacts_mirrored = false;
-    if (ctx->want_host_results && npairs && ctx->max_contacts * sizeof(pk_contact) <= (2ull << 30) && !getenv("PK_NO_MIRROR"))
-    {
-        if (ctx->h_contacts_cap < ctx->max_contacts)
-        {
-            if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
-            ctx->h_contacts = nullptr;
-            ctx->h_contacts_cap = 0;
-            PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_contacts), ctx->max_contacts * sizeof(pk_contact), cudaHostAllocDefault));
-            ctx->h_contacts_cap = ctx->max_contacts;
-        }
-        mirror = reinterpret_cast<ContactRec *>(ctx->h_contacts);
-        ctx->contacts_mirrored = true;
-    }
-    PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true, mirror));
+    PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true));
     PK_TRY(read_counters(ctx));
     uint64_t hits = ctx->h_counters[C_HITS];
     uint64_t valid = ctx->h_counters[C_VALID];
@@ -981,7 +961,6 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         hits = ctx->max_contacts;
     }
     ctx->d_contacts_final = ctx->d_contacts[0];
-    if (status != PK_OK) ctx->contacts_mirrored = false;
     if (status == PK_OK && valid != hits)
     {
         // some GJK hits ended without a value in EPA (degenerate pad / exhausted heap / overflow)
@@ -995,7 +974,6 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
                                                                  static_cast<int>(sizeof(ContactRec)));
         ctx->launches += 4;
         ctx->d_contacts_final = ctx->d_contacts[1];
-        ctx->contacts_mirrored = false;
         PK_CUDA(cudaGetLastError());
     }
     cudaEventRecord(ctx->ev[ST_FETCH], s);
@@ -1056,7 +1034,7 @@ int pk_fetch_results(pk_ctx *ctx)
         PK_CUDA(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs_sorted, ctx->num_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                 ctx->stream));
     ctx->pairs_in_flight = false;
-    if (ctx->num_contacts && !ctx->contacts_mirrored) // (mirrored: the EPA kernels already stored them there)
+    if (ctx->num_contacts)
         PK_CUDA(cudaMemcpyAsync(ctx->h_contacts, ctx->d_contacts_final, ctx->num_contacts * sizeof(pk_contact),
                                 cudaMemcpyDeviceToHost, ctx->stream));
     cudaEventRecord(ctx->ev[ST_COUNT], ctx->stream);

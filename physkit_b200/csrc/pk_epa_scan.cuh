@@ -207,7 +207,7 @@ __device__ __forceinline__ double4 es_face_plane(d3 pi, d3 pj, d3 pk, bool has_o
 }
 
 // collision.cpp:424-454
-__device__ __noinline__ void es_write_result(const EsSlab &sl, double4 nd, unsigned long long t, ContactRec *out, uint64_t key, ContactRec *mirror)
+__device__ __noinline__ void es_write_result(const EsSlab &sl, double4 nd, unsigned long long t, ContactRec *out, uint64_t key)
 {
     d3 n{nd.x, nd.y, nd.z};
     const double2 *q0 = reinterpret_cast<const double2 *>(sl.vab + 6 * es_v(t, 0));
@@ -238,7 +238,6 @@ __device__ __noinline__ void es_write_result(const EsSlab &sl, double4 nd, unsig
     out->world_b[1] = wb.y;
     out->world_b[2] = wb.z;
     out->depth = nd.w;
-    if (mirror) *mirror = *out; // pk_collide: the record also goes straight to the caller's pinned buffer (zero-copy store)
 }
 
 // HEAP mode: the first ES_HCAP heap entries live in the thread's shared-memory area (every sift starts
@@ -417,7 +416,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 unsigned long long *__restrict__ counters /* [0]=valid contacts */, uint32_t *__restrict__ fallback_list,
                 unsigned long long *__restrict__ fallback_count, const unsigned long long *__restrict__ class_count,
                 const uint32_t *__restrict__ leftovers, const unsigned long long *__restrict__ leftover_count,
-                const EpaInit *__restrict__ init, ContactRec *contacts_host)
+                const EpaInit *__restrict__ init)
 {
     // Work of the HEAP instance: first the pairs the SCAN instance handed back (leftovers[], complete at
     // launch: mostly sphere–sphere pairs with an exact distance tie, long ones — started first so that
@@ -802,7 +801,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         const d3 p = P(sp);
         if (finished || dot(mn, p) - mf.w < 1e-6) // converged (collision.cpp:465-466)
         {
-            es_write_result(sl, mf, mt, contacts + out_slot, key, contacts_host ? contacts_host + out_slot : nullptr);
+            es_write_result(sl, mf, mt, contacts + out_slot, key);
             valid[out_slot] = 1;
             ++n_valid;
             active = false;
