@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 from kat_cases import EPA_CASES, GJK_CASES, run_epa_case
-from scenes import random_pairs_scene, scene_c3, scene_c4
+from scenes import Scene, SplitMix64, random_pairs_scene, scene_c3, scene_c4
 
 pytestmark = pytest.mark.gpu
 
@@ -190,3 +190,36 @@ def test_epa_exact_ties_bit_exact(kinds):
     sc, pa, pb = _symmetric_scene(*kinds)
     hit, out, st = _batch_vs_oracle(sc, pa, pb)
     assert hit.sum() > 300
+
+
+def test_prefiltered_hull_support_with_exact_ties_bit_exact():
+    """Hulls above 16 vertices are scanned in float first and decided in FP64 among the candidates
+    (pk_common.cuh: hull_argmax).  mesh::support keeps the FIRST vertex among equal dots
+    (src/mesh.cpp:341-358), so hulls whose vertices tie exactly — duplicated corners, rings, grids on flat
+    faces — in axis-aligned poses check that the prefiltered scan still answers with the reference's index."""
+    from scenes import sphere_vertices
+
+    rng = SplitMix64(2024)
+    shapes = []
+    corners = np.array([[sx, sy, sz] for sx in (-0.5, 0.5) for sy in (-0.4, 0.4) for sz in (-0.3, 0.3)])
+    dup = np.repeat(corners, 5, axis=0)
+    shapes.append(("hull", dup[np.argsort(rng.u01(len(dup)))]))                      # 40 vertices, every corner five times
+    ang = 2.0 * np.pi * np.arange(32) / 32.0
+    ring = np.stack([0.5 * np.cos(ang), 0.5 * np.sin(ang), np.zeros(32)], axis=1)
+    shapes.append(("hull", np.concatenate([ring + [0, 0, 0.35], ring - [0, 0, 0.35]])))  # prism: two rings of 32
+    g = np.linspace(-0.5, 0.5, 5)
+    grid = np.array([[x, y, z] for x in g for y in g for z in g if max(abs(x), abs(y), abs(z)) == 0.5])
+    shapes.append(("hull", grid[np.argsort(rng.u01(len(grid)))]))                     # 98 points on a cube's faces
+    shapes.append(("hull", sphere_vertices(0.45)))                                       # 482-vertex mesh sphere
+    n = 3000
+    sid = rng.randint(2 * n, len(shapes)).astype(np.uint32)
+    quat = rng.quats(2 * n)
+    ident = rng.u01(2 * n) < 0.6
+    quat[ident] = [0.0, 0.0, 0.0, 1.0]
+    pos = np.zeros((2 * n, 3))
+    pos[0::2] = np.round(rng.uniform(-4.0, 4.0, n, 3) * 8.0) / 8.0
+    pos[1::2] = pos[0::2] + (rng.randint(3 * n, 13).reshape(n, 3) - 6) / 8.0  # offsets in {-0.75 … 0.75}, step 1/8
+    sc = Scene(shapes, pos, quat, sid)
+    pa, pb = np.arange(0, 2 * n, 2, dtype=np.uint32), np.arange(1, 2 * n, 2, dtype=np.uint32)
+    hit, out, st = _batch_vs_oracle(sc, pa, pb)
+    assert 0.2 < hit.mean() < 0.95
