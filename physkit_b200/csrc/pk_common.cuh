@@ -19,6 +19,11 @@ constexpr int KIND_HULL = 3;   // mesh::instance::support  src/mesh.cpp:442-448,
 
 constexpr uint32_t HULL_PREFILTER_MIN = 16; // hulls up to this size are scanned in FP64 directly
 
+#ifndef PK_HULL_UNROLL
+#define PK_HULL_UNROLL 8
+#endif
+constexpr int HULL_UNROLL = PK_HULL_UNROLL; // vertex loads in flight per lane in the float scan of a hull
+
 constexpr uint8_t FLAG_STATIC = 1;
 constexpr uint8_t FLAG_ALIVE = 2;
 
@@ -205,7 +210,7 @@ __device__ __forceinline__ uint32_t hull_argmax(const float4 *__restrict__ vf, c
     for (uint32_t i = 0; i < nverts; ++i) f1 = fmaxf(f1, pk_hull_fdot(__ldg(vf + i), lx, ly, lz));
 #else
     float f1 = -3.4e38f, f2 = -3.4e38f; // largest, second largest (equal values count twice)
-#pragma unroll 4
+#pragma unroll HULL_UNROLL
     for (uint32_t i = 0; i < nverts; ++i)
     {
         const float f = pk_hull_fdot(__ldg(vf + i), lx, ly, lz);
