@@ -175,7 +175,7 @@ struct pk_ctx
     // contact rows (pk_contact_rows_setup): allocated on first use, 4 point slots per manifold
     uint64_t sol_cap = 0, sol_count = 0;
     uint8_t *d_sol_valid = nullptr;
-    uint32_t *d_sol_index = nullptr, *d_sol_tiles = nullptr;
+    uint32_t *d_sol_index = nullptr, *d_sol_tiles = nullptr, *d_sol_slot = nullptr;
     SolverPoint *d_sol_rows = nullptr;
     unsigned long long *d_sol_total = nullptr;
     pk_solver_point *h_sol_rows = nullptr;
@@ -527,7 +527,7 @@ int pk_destroy(pk_ctx *ctx)
     for (auto &e : ctx->ev_dyn)
         if (e) cudaEventDestroy(e);
     for (void *q : {static_cast<void *>(ctx->d_material), static_cast<void *>(ctx->d_sol_valid), static_cast<void *>(ctx->d_sol_index),
-                    static_cast<void *>(ctx->d_sol_tiles), static_cast<void *>(ctx->d_sol_rows), static_cast<void *>(ctx->d_sol_total)})
+                    static_cast<void *>(ctx->d_sol_tiles), static_cast<void *>(ctx->d_sol_slot), static_cast<void *>(ctx->d_sol_rows), static_cast<void *>(ctx->d_sol_total)})
         if (q) cudaFree(q);
     if (ctx->h_sol_rows) cudaFreeHost(ctx->h_sol_rows);
     for (auto &e : ctx->ev_sol)
@@ -1317,6 +1317,7 @@ int pk_contact_rows_setup(pk_ctx *ctx, double dt, double gravity_norm, uint64_t 
         const uint64_t cap = 4 * ctx->man_cap;
         PK_TRY(dev_alloc(ctx, &ctx->d_sol_valid, cap + 16));
         PK_TRY(dev_alloc(ctx, &ctx->d_sol_index, cap));
+        PK_TRY(dev_alloc(ctx, &ctx->d_sol_slot, cap));
         PK_TRY(dev_alloc(ctx, &ctx->d_sol_tiles, div_up(cap, SCAN_TILE) + 1));
         PK_TRY(dev_alloc(ctx, &ctx->d_sol_total, 1));
         PK_TRY(dev_alloc(ctx, &ctx->d_sol_rows, cap));
@@ -1335,9 +1336,11 @@ int pk_contact_rows_setup(pk_ctx *ctx, double dt, double gravity_norm, uint64_t 
         flag_tile_sum_kernel<<<nt, 256, 0, s>>>(ctx->d_sol_valid, slots, ctx->d_sol_tiles);
         tile_sum_scan_kernel<<<1, 256, 0, s>>>(ctx->d_sol_tiles, nt, ctx->d_sol_total);
         flag_scan_apply_kernel<<<nt, 256, 0, s>>>(ctx->d_sol_valid, slots, ctx->d_sol_tiles, ctx->d_sol_index);
-        solver_rows_kernel<<<div_up(slots, 128), 128, 0, s>>>(man, nman, ctx->d_pos, ctx->d_quat, ctx->dyn, ctx->d_material, ctx->d_sol_valid,
-                                                             ctx->d_sol_index, dt, gravity_norm, ctx->d_sol_rows);
-        ctx->launches += 5;
+        solver_compact_kernel<<<div_up(slots, 256), 256, 0, s>>>(ctx->d_sol_valid, ctx->d_sol_index, slots, ctx->d_sol_slot);
+        // one thread per row; the grid covers the point count of the manifolds (≥ rows), surplus threads leave at once
+        solver_rows_kernel<<<div_up(slots, 128), 128, 0, s>>>(man, ctx->d_sol_total, ctx->d_pos, ctx->d_quat, ctx->dyn, ctx->d_material,
+                                                             ctx->d_sol_slot, dt, gravity_norm, ctx->d_sol_rows);
+        ctx->launches += 6;
         PK_CUDA(cudaGetLastError());
         unsigned long long total = 0;
         cudaEventRecord(ctx->ev_sol[1], s);

@@ -4,11 +4,11 @@
 // warm-start impulses.  The serial Gauss-Seidel sweep that consumes the rows (:1107-1201) is not on this path.
 //
 // Input: the sorted manifold array of pk_manifold.cuh, the body state of pk_dynamics.cuh (velocities, inverse
-// mass, world inverse inertia tensor) and the poses.  Two kernels over the 4·M point slots: the first only
-// decides which points yield a row (penetration > 0, constraint.h:893-894), a flag scan turns that into the
-// row index, the second computes the row and writes it in place — rows come out ordered by (pair key, point),
-// with no staging copy of the 320-byte records.  One thread per point slot; FP64, no FMA, the reference's
-// operation order: bit-identical to the oracle's restatement.
+// mass, world inverse inertia tensor) and the poses.  solver_valid_kernel (one thread per point slot, 4 per
+// manifold) only decides which points yield a row (penetration > 0, constraint.h:893-894); a flag scan turns
+// that into the row index and solver_compact_kernel into its inverse; solver_rows_kernel computes one row per
+// thread and writes it in place — rows come out ordered by (pair key, point), with no staging copy of the
+// 336-byte records.  FP64, no FMA, the reference's operation order: bit-identical to the oracle's restatement.
 #pragma once
 
 #include "pk_dynamics.cuh"
@@ -103,13 +103,25 @@ __device__ __forceinline__ void st3(double *p, d3 v)
     p[2] = v.z;
 }
 
-__global__ void __launch_bounds__(128)
-solver_rows_kernel(const ManifoldRec *__restrict__ man, uint64_t nman, const double *__restrict__ pos, const double *__restrict__ quat,
-                   DynArrays dy, const double *__restrict__ material, const uint8_t *__restrict__ valid,
-                   const uint32_t *__restrict__ row_index, double dt, double gravity_norm, SolverPoint *__restrict__ out)
+// slot of every row (the inverse of the flag scan), so that solver_rows_kernel runs one thread per ROW: most
+// manifolds hold one or two points, a thread per point slot would leave three lanes of four idle in the
+// 150-register kernel (ncu r1b: 7 of 32 lanes active).
+__global__ void __launch_bounds__(256)
+solver_compact_kernel(const uint8_t *__restrict__ valid, const uint32_t *__restrict__ row_index, uint64_t nslots,
+                      uint32_t *__restrict__ slot_of_row)
 {
     const uint64_t slot = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (slot >= 4 * nman || !valid[slot]) return;
+    if (slot < nslots && valid[slot]) slot_of_row[row_index[slot]] = static_cast<uint32_t>(slot);
+}
+
+__global__ void __launch_bounds__(128)
+solver_rows_kernel(const ManifoldRec *__restrict__ man, const unsigned long long *__restrict__ nrows_ptr, const double *__restrict__ pos,
+                   const double *__restrict__ quat, DynArrays dy, const double *__restrict__ material,
+                   const uint32_t *__restrict__ slot_of_row, double dt, double gravity_norm, SolverPoint *__restrict__ out)
+{
+    const uint64_t row = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (row >= *nrows_ptr) return;
+    const uint64_t slot = slot_of_row[row];
     const ManifoldRec *m = man + (slot >> 2);
     const uint32_t j = static_cast<uint32_t>(slot & 3u);
     const uint64_t key = m->key;
@@ -176,7 +188,7 @@ solver_rows_kernel(const ManifoldRec *__restrict__ man, uint64_t nman, const dou
     p.accumulated[0] = c.normal_impulse;
     p.accumulated[1] = c.tangent_impulses[0];
     p.accumulated[2] = c.tangent_impulses[1];
-    out[row_index[slot]] = p;
+    out[row] = p;
 }
 
 } // namespace pk
