@@ -733,6 +733,17 @@ int pk_shape_hull(pk_ctx *ctx, const double *xyz, uint32_t nverts, uint32_t *id)
             r.a[k] = std::min(r.a[k], xyz[3 * i + k]);
             r.b[k] = std::max(r.b[k], xyz[3 * i + k]);
         }
+    // mesh::box's vertex table (src/mesh.cpp:31-40), bit for bit: support() then shares the eight dots' products
+    if (nverts == 8 && r.b[0] > 0.0 && r.b[1] > 0.0 && r.b[2] > 0.0)
+    {
+        bool box = true;
+        for (uint32_t i = 0; i < 8 && box; ++i)
+        {
+            const double want[3] = {((0x66 >> i) & 1) ? r.b[0] : -r.b[0], ((0xCC >> i) & 1) ? r.b[1] : -r.b[1], i >= 4 ? r.b[2] : -r.b[2]};
+            for (int k = 0; k < 3; ++k) box = box && xyz[3 * i + k] == want[k];
+        }
+        r.mesh_box = box ? 1u : 0u;
+    }
     int s = add_shape(ctx, r, id);
     if (s != PK_OK) return s;
     ctx->h_verts.insert(ctx->h_verts.end(), xyz, xyz + 3ull * nverts);

@@ -117,7 +117,7 @@ struct alignas(16) ShapeRec
     int32_t kind;
     uint32_t vert_off;
     uint32_t nverts;
-    uint32_t _pad;
+    uint32_t mesh_box; // HULL: 1 when the vertices are exactly mesh::box's table (src/mesh.cpp:31-40) for half = b
 };
 static_assert(sizeof(ShapeRec) == 64, "ShapeRec must be one 64-byte line");
 
@@ -130,7 +130,7 @@ struct ShapeView
     const float4 *vf;    // HULL: the same vertices rounded to float (x,y,z,0) for the argmax prefilter
     d3 p;                // AABB: min | others: position / centre
     d3 h;                // AABB: max | OBB: half | SPHERE: h.x = r
-    float hull_r;        // HULL: largest |coordinate| of the local box (error bound of the prefilter)
+    float hull_r;        // HULL: largest |coordinate| of the local box (error bound of the prefilter); < 0: mesh::box
     dq q;                // OBB / HULL
 };
 
@@ -165,7 +165,7 @@ __device__ __forceinline__ ShapeView load_shape(const BodyArrays &ba, uint32_t b
     if (v.kind == KIND_HULL)
     {
         double r = fmax(fmax(fmax(fabs(s0.x), fabs(s0.y)), fmax(fabs(s1.x), fabs(s1.y))), fmax(fabs(s2.x), fabs(s2.y)));
-        v.hull_r = __double2float_ru(r);
+        v.hull_r = s3.w == 1 ? -1.f : __double2float_ru(r);
     }
     if (v.kind == KIND_AABB)
     {
@@ -255,6 +255,34 @@ __device__ __forceinline__ d3 support(const ShapeView &s, d3 d)
     // HULL: argmax of v·l over all vertices, strict '>' so the lowest index wins ties
     // (src/mesh.cpp:341-358).  The dot the reference compares is the FP64 value (x·lx + y·ly) + z·lz.
     d3 l = rotate(conjugate(s.q), d);
+    if (s.hull_r < 0.f)
+    {
+        // mesh::box (src/mesh.cpp:31-40): every body of a physkit::world demo is one.  Its eight vertices are
+        // (±hx, ±hy, ±hz) in a fixed order, so the eight dots (x·lx + y·ly) + z·lz of the reference's scan share
+        // three products and four sums — (−x)·lx = −(x·lx) and (−a) + (−b) = −(a + b) hold exactly under round
+        // to nearest — and the scan's strict '>' in index order picks among them.  s.h holds the local minimum.
+        const double hx = -s.h.x, hy = -s.h.y, hz = -s.h.z;
+        const double px = hx * l.x, py = hy * l.y, pz = hz * l.z;
+        const double pp = px + py, pm = px - py;
+        const double A = pp + pz, B = pp - pz, C = pm + pz, D = pm - pz;
+        // vertex 0 (−,−,−) … 7 (−,+,+)
+        const double t[8] = {-A, D, B, -C, -B, C, A, -D};
+        int bi = 0;
+        double bt = t[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i)
+        {
+            if (t[i] > bt)
+            {
+                bt = t[i];
+                bi = i;
+            }
+        }
+        const double sx = ((0x66 >> bi) & 1) ? hx : -hx; // + for vertices 1, 2, 5, 6
+        const double sy = ((0xCC >> bi) & 1) ? hy : -hy; // + for vertices 2, 3, 6, 7
+        const double sz = (bi >= 4) ? hz : -hz;
+        return rotate(s.q, d3{sx, sy, sz}) + s.p;
+    }
     const double *v = s.verts;
     uint32_t best = 0;
     if (s.nverts <= HULL_PREFILTER_MIN)
