@@ -21,11 +21,18 @@
 //
 // Shared memory holds keys for the first 96 face slots (46 iterations); the few polytopes that grow past
 // that scan the remaining distances from their slab.  Padded simplices, improper horizons and horizons
-// longer than 16 edges also go to epa_kernel through the fallback list.
+// longer than ES_HORIZON edges also go to epa_kernel through the fallback list.
 // Results are bit-identical to epa_kernel.
 #pragma once
 
 #include "pk_narrowphase.cuh"
+// -DPK_ES_WHY: debug build that prints why the HEAP instance hands a pair back (which `bad` site fired)
+#ifdef PK_ES_WHY
+#include <cstdio>
+#define PK_ES_WHY_TAG(b) why |= (b)
+#else
+#define PK_ES_WHY_TAG(b)
+#endif
 
 namespace pk
 {
@@ -36,7 +43,7 @@ constexpr int ES_SLOTS = 136;  // live faces = 2V − 4 ≤ 132
 #define PK_ES_KEYS 92
 #endif
 #ifndef PK_ES_HORIZON
-#define PK_ES_HORIZON 16
+#define PK_ES_HORIZON 24
 #endif
 #ifndef PK_ES_HCAP
 #define PK_ES_HCAP 30
@@ -44,7 +51,8 @@ constexpr int ES_SLOTS = 136;  // live faces = 2V − 4 ≤ 132
 constexpr int ES_KEYS = PK_ES_KEYS; // slots with a float key in shared memory (the rest is scanned from the slab);
                                // 92/4 is odd: a thread's keys are contiguous and 128-bit loads are conflict-free
 constexpr int ES_VERTS = 68;   // 4 + 64 iterations
-constexpr int ES_HORIZON = PK_ES_HORIZON; // observed max 10
+constexpr int ES_HORIZON = PK_ES_HORIZON; // longer horizons are handed back: at 16 one pair of the 1 M-body scene was, and
+                                          // epa_kernel spent 0.45 ms of every step on it alone (observed max: 17)
 constexpr int ES_STACK = 8;    // observed max 4
 constexpr int ES_HEAP_MAX = EPA_MAX_FACES; // HEAP mode: heap entries (= faces ever created), as epa_kernel
 // per-thread slab: planes, topology, vertices (+ in HEAP mode the heap entries beyond the shared-memory top)
@@ -397,7 +405,7 @@ epa_init_kernel(const SimplexRec *__restrict__ simplices, const unsigned long lo
 #define PK_ES_MIN_BLOCKS 5
 #endif
 #ifndef PK_ES_FETCH_MIN
-#define PK_ES_FETCH_MIN 6
+#define PK_ES_FETCH_MIN 12
 #endif
 
 // The hit list is grouped by cost class (order[]: sphere–sphere, sphere–polyhedron, polyhedron–polyhedron);
@@ -810,6 +818,9 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
 
         // ---- find_silhouette (collision.cpp:315-353): LIFO flood fill, edge order preserved ----
         bool bad = false;
+#ifdef PK_ES_WHY
+        unsigned why = 0;
+#endif
         int nh = 0;
         {
             kill_slot(min_face);
@@ -859,7 +870,10 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                             }
                         }
                         else
+                        {
                             bad = true;
+                            PK_ES_WHY_TAG(1);
+                        }
                     }
                     else
                     {
@@ -867,7 +881,11 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                         // edge of `a` that starts at `end` (collision.cpp:305-313): `a` is in registers now
                         const int st = es_v(cur, i), en = es_v(cur, (i + 1) % 3);
                         const int e2 = (es_v(nt[i], 0) == en) ? 0 : (es_v(nt[i], 1) == en ? 1 : 2);
-                        if (es_v(nt[i], e2) != en) bad = true; // unmatched link: slot recycling is no longer safe
+                        if (es_v(nt[i], e2) != en)
+                        {
+                            bad = true; // unmatched link: slot recycling is no longer safe
+                            PK_ES_WHY_TAG(2);
+                        }
                         if (nh < ES_HORIZON)
                         {
                             shm.hz[nh][t] = static_cast<uint32_t>(st) | (static_cast<uint32_t>(en) << 7) | (static_cast<uint32_t>(a) << 14) |
@@ -875,7 +893,10 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                             ++nh;
                         }
                         else
+                        {
                             bad = true;
+                            PK_ES_WHY_TAG(4);
+                        }
                         es_prefetch(sl.vpos + 4 * st); // operands of the face loop
                         es_prefetch(sl.vpos + 4 * en);
                     }
@@ -896,6 +917,9 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         const bool full = nfree < nh || nverts >= ES_VERTS || (HEAP && heap_size + nh > ES_HEAP_MAX);
         if (bad || nh < 3 || full)
         {
+#ifdef PK_ES_WHY
+            if (HEAP) printf("[why] early bad=%d why=%u nh=%d full=%d iter=%d nverts=%d\n", (int)bad, why, nh, (int)full, iter, nverts);
+#endif
             fb = full ? 3 : 4;
             continue;
         }
@@ -925,7 +949,11 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
             const d3 n{pl.x, pl.y, pl.z};
             const double dist = pl.w;
             sl.store_plane(slot, n, dist);
-            if (!(fabs(dist) < 1e30)) bad = true;
+            if (!(fabs(dist) < 1e30))
+            {
+                bad = true;
+                PK_ES_WHY_TAG(8);
+            }
             if constexpr (HEAP)
             {
                 es_sift_up(hp, heap_size, dist, static_cast<uint32_t>(slot) | (static_cast<uint32_t>(nfaces) << 8)); // push_face, horizon order
@@ -948,7 +976,11 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
             // proper horizon: every vertex starts at most one edge and ends at most one, no self loop
             const bool ends_twice = (en < 64) ? ((end_seen0 >> en) & 1ull) : ((end_seen1 >> (en - 64)) & 1u);
             const bool starts_twice = (st < 64) ? ((start_seen0 >> st) & 1ull) : ((start_seen1 >> (st - 64)) & 1u);
-            if (st == en || starts_twice || ends_twice) bad = true;
+            if (st == en || starts_twice || ends_twice)
+            {
+                bad = true;
+                PK_ES_WHY_TAG(16);
+            }
             if (en < 64)
                 end_seen0 |= 1ull << en;
             else
@@ -970,7 +1002,11 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
             int j = 0;
             uint32_t hj = shm.hz[0][t];
             while (hz_start(hj) != en) hj = shm.hz[++j][t];
-            if (hz_end(hj) == hz_start(he)) bad = true; // 2-cycle: the reference links it one way only
+            if (hz_end(hj) == hz_start(he))
+            {
+                bad = true; // 2-cycle: the reference links it one way only
+                PK_ES_WHY_TAG(32);
+            }
             shm.ring[e][t] = static_cast<uint16_t>((shm.ring[e][t] & 0xFF00u) | (hj >> 24));
             shm.ring[j][t] = static_cast<uint16_t>((shm.ring[j][t] & 0x00FFu) | ((he >> 24) << 8));
         }
@@ -985,6 +1021,9 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         }
         if (bad)
         {
+#ifdef PK_ES_WHY
+            if (HEAP) printf("[why] late why=%u nh=%d iter=%d nverts=%d nfaces=%d\n", why, nh, iter, nverts, nfaces);
+#endif
             fb = 4;
             continue;
         }
