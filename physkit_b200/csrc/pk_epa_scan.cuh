@@ -1030,6 +1030,14 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         batch_n = nh;
     }
     if (n_valid) atomicAdd(counters + 0, n_valid);
+#ifdef PK_ES_WHY
+    if (threadIdx.x == 0) // when does each block retire: how long is the tail of the persistent launch
+    {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        printf("[exit] %d %d %llu\n", HEAP ? 1 : 0, static_cast<int>(blockIdx.x), now);
+    }
+#endif
 }
 
 } // namespace pk
