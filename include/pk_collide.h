@@ -75,6 +75,7 @@ typedef struct pk_config
 } pk_config;
 
 typedef struct pk_ctx pk_ctx;
+typedef struct pk_multi pk_multi; /* one world sharded over several GPUs from one host process */
 
 /* 88-byte contact record = collision_info (collision.h:52-59) + its pair key.
  * normal points from B to A; depth = EPA face distance (src/collision.cpp:448-453). */
@@ -230,6 +231,27 @@ int pk_contacts(pk_ctx *ctx, const pk_contact **recs, uint64_t *n);
  * (narrow_phase::calculate → contact_point, collision_phases.h:257-263).  Computed on the device on request
  * from the poses of that step; the host pointer stays valid until the next pk_collide*. */
 int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n);
+/* ---- one world on several GPUs from one host process ------------------------------------
+ * pk_create_multi creates one context per listed device (a device may be listed more than once), context i with
+ * cfg.shard_rank = i, cfg.shard_count = n: every context holds all bodies and rebuilds the whole tree, context i
+ * traverses only its slice of the sorted leaves, so the contexts' pair sets are disjoint and their union is the
+ * world's pair set (the sharding bench.py runs with one process per GPU; here the host threads of
+ * pk_multi_collide play the ranks).  Shapes are registered on every context through pk_multi_ctx (same calls in
+ * the same order give the same ids); the pk_multi_bodies_* calls fan a body upload out to all contexts.
+ * pk_multi_collide runs pk_collide on all contexts concurrently, one host thread per context; `total` holds the
+ * summed counts and the slowest context's times.  Results are read per context (pk_pairs / pk_contacts on
+ * pk_multi_ctx(i)): each is sorted by key, the shards' key ranges interleave.  The first failing context's
+ * status is returned. */
+int pk_create_multi(const pk_config *cfg, const int *devices, int n, pk_multi **out);
+int pk_destroy_multi(pk_multi *m);
+int pk_multi_size(pk_multi *m, int *n);
+int pk_multi_ctx(pk_multi *m, int i, pk_ctx **ctx);
+int pk_multi_bodies_resize(pk_multi *m, uint32_t n);
+int pk_multi_bodies_upload(pk_multi *m, const double *pos_xyz, const double *quat_xyzw, const double *disp_xyz,
+                           const uint32_t *shape_id, const uint8_t *flags, const uint32_t *world_id, uint32_t first, uint32_t count);
+int pk_multi_bodies_update_pose(pk_multi *m, const double *pos_xyz, const double *quat_xyzw, const double *disp_xyz, uint32_t first,
+                                uint32_t count);
+int pk_multi_collide(pk_multi *m, pk_step_result *total);
 /* ---- integrator (optional) ---------------------------------------------------------------
  * The two per-body loops of world::step_impl on the device, so that poses need not travel every step:
  *   loop A (src/world.cpp:22-34): apply_force(gravity · mass), semi_implicit_euler::integrate_vel

@@ -11,6 +11,7 @@ from .api import (  # noqa: F401
     RAY_CLOSEST,
     CollisionWorld,
     Context,
+    MultiContext,
     PkError,
     contact_dtype,
     ray_hit_dtype,

@@ -101,6 +101,8 @@ EXPORTS = [
     "pk_dynamics_enable", "pk_dynamics_upload", "pk_dynamics_set_velocities", "pk_dynamics_set_forces",
     "pk_integrate_velocities", "pk_integrate_positions", "pk_dynamics_download", "pk_displacements",
     "pk_material_upload", "pk_contact_rows_setup", "pk_contact_rows", "pk_contact_rows_device",
+    "pk_create_multi", "pk_destroy_multi", "pk_multi_size", "pk_multi_ctx", "pk_multi_bodies_resize",
+    "pk_multi_bodies_upload", "pk_multi_bodies_update_pose", "pk_multi_collide",
     "pk_device_alloc", "pk_device_free", "pk_memcpy_h2d", "pk_memcpy_d2h", "pk_memcpy_d2d", "pk_host_alloc", "pk_host_free",
 ]
 
@@ -136,6 +138,14 @@ def load_library():
     L.pk_dynamics_download.argtypes = [vp, vp, vp, vp, vp, u32, u32]
     L.pk_displacements.argtypes = [vp, vp, u32, u32]
     L.pk_material_upload.argtypes = [vp, vp, vp, u32, u32]
+    L.pk_create_multi.argtypes = [vp, vp, i32, vp]
+    L.pk_destroy_multi.argtypes = [vp]
+    L.pk_multi_size.argtypes = [vp, vp]
+    L.pk_multi_ctx.argtypes = [vp, i32, vp]
+    L.pk_multi_bodies_resize.argtypes = [vp, u32]
+    L.pk_multi_bodies_upload.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, u32]
+    L.pk_multi_bodies_update_pose.argtypes = [vp, vp, vp, vp, u32, u32]
+    L.pk_multi_collide.argtypes = [vp, vp]
     L.pk_contact_rows_setup.argtypes = [vp, C.c_double, C.c_double, vp]
     L.pk_contact_rows.argtypes = [vp, vp, vp]
     L.pk_contact_rows_device.argtypes = [vp, vp, vp, vp]
@@ -192,8 +202,15 @@ class Context:
     """One pk_ctx (one device, one stream)."""
 
     def __init__(self, max_bodies, max_pairs, mode=MODE_WORLD, device=0, max_shapes=None, max_contacts=0,
-                 max_hull_vertices=0, num_worlds=1, shard_rank=0, shard_count=1):
+                 max_hull_vertices=0, num_worlds=1, shard_rank=0, shard_count=1, _borrow=None):
         self.L = load_library()
+        self._owned = _borrow is None
+        if _borrow is not None:  # a context owned by a pk_multi
+            self.h = C.c_void_p(_borrow)
+            self.mode = mode
+            self.result = StepResult()
+            self._pinned = []
+            return
         cfg = _Config(
             int(device), int(mode), int(max_bodies), int(max_shapes if max_shapes is not None else max(16, max_bodies)),
             int(max_pairs), int(max_contacts), int(max_hull_vertices), int(num_worlds), int(shard_rank), int(shard_count), 0,
@@ -218,7 +235,8 @@ class Context:
             for ptr in self._pinned:
                 self.L.pk_host_free(self.h, ptr)
             self._pinned = []
-            self.L.pk_destroy(self.h)
+            if self._owned:
+                self.L.pk_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -540,6 +558,68 @@ class Context:
             allow,
         )
         return float(ms.value)
+
+
+class MultiContext:
+    """pk_multi: one world sharded over several devices from this process (pk_create_multi).  `ctx[i]` are
+    Context views of the per-device contexts; shapes go to every one of them, bodies through upload()."""
+
+    def __init__(self, devices, max_bodies, max_pairs, mode=MODE_WORLD, max_shapes=None, max_contacts=0, max_hull_vertices=0, num_worlds=1):
+        self.L = load_library()
+        cfg = _Config(0, int(mode), int(max_bodies), int(max_shapes if max_shapes is not None else max(16, max_bodies)), int(max_pairs),
+                      int(max_contacts), int(max_hull_vertices), int(num_worlds), 0, 1, 0)
+        dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self.h = C.c_void_p()
+        st = self.L.pk_create_multi(C.byref(cfg), dev, len(devices), C.byref(self.h))
+        if st != PK_OK:
+            self.h = None
+            raise PkError(st, self.L.pk_strerror(st).decode())
+        n = C.c_int()
+        self.L.pk_multi_size(self.h, C.byref(n))
+        self.ctx = []
+        for i in range(n.value):
+            p = C.c_void_p()
+            self.L.pk_multi_ctx(self.h, i, C.byref(p))
+            self.ctx.append(Context(max_bodies, max_pairs, mode=mode, _borrow=p.value))
+        self.result = StepResult()
+
+    def _check(self, st):
+        if st != PK_OK:
+            raise PkError(st, self.L.pk_strerror(st).decode())
+
+    def add_shapes(self, specs):
+        ids = [c.add_shapes(specs) for c in self.ctx]
+        assert all(i == ids[0] for i in ids)
+        return ids[0]
+
+    def resize(self, n):
+        self._check(self.L.pk_multi_bodies_resize(self.h, int(n)))
+
+    def upload(self, pos, quat, disp, shape_id, flags, world_id=None, first=0):
+        pos = _arr(pos, np.float64).reshape(-1, 3)
+        quat = _arr(quat, np.float64).reshape(-1, 4)
+        disp = None if disp is None else _arr(disp, np.float64).reshape(-1, 3)
+        sid = _arr(shape_id, np.uint32)
+        fl = _arr(flags, np.uint8)
+        wid = _arr(world_id, np.uint32)
+        self._check(self.L.pk_multi_bodies_upload(self.h, _p(pos), _p(quat), _p(disp), _p(sid), _p(fl), _p(wid), int(first), len(pos)))
+
+    def collide(self):
+        self._check(self.L.pk_multi_collide(self.h, C.byref(self.result)))
+        return self.result
+
+    def close(self):
+        if getattr(self, "h", None):
+            for c in self.ctx:
+                c.close()
+            self.L.pk_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class CollisionWorld:

@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "--shared", "-Xcompiler", "-fPIC",
     "-Xcompiler", "-O3",
+    "-Xcompiler", "-pthread",
     "-Xptxas", "-v",
     "-cudart", "static",
 ]

@@ -23,6 +23,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace pk;
@@ -1121,6 +1122,118 @@ int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n)
     }
     *pts = ctx->h_points;
     *n = m;
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ several GPUs, one process
+struct pk_multi
+{
+    std::vector<pk_ctx *> ctx;
+};
+
+int pk_create_multi(const pk_config *cfg, const int *devices, int n, pk_multi **out)
+{
+    if (!cfg || !devices || n < 1 || !out) return PK_E_INVALID;
+    pk_multi *m = new (std::nothrow) pk_multi();
+    if (!m) return PK_E_OOM;
+    for (int i = 0; i < n; ++i)
+    {
+        pk_config c = *cfg;
+        c.device = devices[i];
+        c.shard_rank = static_cast<uint32_t>(i);
+        c.shard_count = static_cast<uint32_t>(n);
+        pk_ctx *x = nullptr;
+        const int s = pk_create(&c, &x);
+        if (s != PK_OK)
+        {
+            for (pk_ctx *y : m->ctx) pk_destroy(y);
+            delete m;
+            return s;
+        }
+        m->ctx.push_back(x);
+    }
+    *out = m;
+    return PK_OK;
+}
+
+int pk_destroy_multi(pk_multi *m)
+{
+    if (!m) return PK_E_INVALID;
+    int s = PK_OK;
+    for (pk_ctx *x : m->ctx)
+    {
+        const int r = pk_destroy(x);
+        if (s == PK_OK) s = r;
+    }
+    delete m;
+    return s;
+}
+
+int pk_multi_size(pk_multi *m, int *n)
+{
+    if (!m || !n) return PK_E_INVALID;
+    *n = static_cast<int>(m->ctx.size());
+    return PK_OK;
+}
+
+int pk_multi_ctx(pk_multi *m, int i, pk_ctx **ctx)
+{
+    if (!m || !ctx || i < 0 || i >= static_cast<int>(m->ctx.size())) return PK_E_INVALID;
+    *ctx = m->ctx[static_cast<size_t>(i)];
+    return PK_OK;
+}
+
+int pk_multi_bodies_resize(pk_multi *m, uint32_t n)
+{
+    if (!m) return PK_E_INVALID;
+    for (pk_ctx *x : m->ctx) PK_TRY(pk_bodies_resize(x, n));
+    return PK_OK;
+}
+
+int pk_multi_bodies_upload(pk_multi *m, const double *pos, const double *quat, const double *disp, const uint32_t *shape_id,
+                           const uint8_t *flags, const uint32_t *world_id, uint32_t first, uint32_t count)
+{
+    if (!m) return PK_E_INVALID;
+    for (pk_ctx *x : m->ctx) PK_TRY(pk_bodies_upload(x, pos, quat, disp, shape_id, flags, world_id, first, count)); // async copies, one stream per device
+    return PK_OK;
+}
+
+int pk_multi_bodies_update_pose(pk_multi *m, const double *pos, const double *quat, const double *disp, uint32_t first, uint32_t count)
+{
+    if (!m) return PK_E_INVALID;
+    for (pk_ctx *x : m->ctx) PK_TRY(pk_bodies_update_pose(x, pos, quat, disp, first, count));
+    return PK_OK;
+}
+
+int pk_multi_collide(pk_multi *m, pk_step_result *total)
+{
+    if (!m) return PK_E_INVALID;
+    const size_t n = m->ctx.size();
+    std::vector<pk_step_result> res(n);
+    std::vector<int> status(n, PK_OK);
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (size_t i = 0; i < n; ++i) th.emplace_back([&, i] { status[i] = pk_collide(m->ctx[i], &res[i]); });
+    for (std::thread &t : th) t.join();
+    if (total)
+    {
+        std::memset(total, 0, sizeof(*total));
+        for (size_t i = 0; i < n; ++i)
+        {
+            total->num_pairs += res[i].num_pairs;
+            total->num_contacts += res[i].num_contacts;
+            total->gjk_hits += res[i].gjk_hits;
+            total->epa_overflow += res[i].epa_overflow;
+            total->pairs_required = std::max(total->pairs_required, res[i].pairs_required);
+            total->num_moved = std::max(total->num_moved, res[i].num_moved); // every context updates all bodies
+            total->ms_broadphase = std::max(total->ms_broadphase, res[i].ms_broadphase);
+            total->ms_narrowphase = std::max(total->ms_narrowphase, res[i].ms_narrowphase);
+            total->ms_total = std::max(total->ms_total, res[i].ms_total);
+            total->step_index = res[i].step_index;
+        }
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (status[i] != PK_OK) return status[i];
     return PK_OK;
 }
 

@@ -271,3 +271,39 @@ def test_contact_points_in_body_frames():
 
     back = Rotation.from_quat(sc.quat[pa]).apply(pts[:, :3]) + sc.pos[pa]
     assert np.allclose(back, con["world_a"], atol=1e-12)
+
+
+def test_pk_create_multi_shards_one_world_over_contexts():
+    """pk_create_multi / pk_multi_collide: n contexts from one process, context i traversing its
+    slice of the sorted leaves.  Run with the same device listed three times: the shards' pair and contact sets are
+    disjoint and their union is what one context produces, bit for bit."""
+    from gpu_util import make_context
+
+    sc = scene_c3(side=20)
+    w = oracle.World(sc.shapes)
+    one = make_context(sc, max_pairs=400_000, mode=pk.MODE_WORLD)
+    m = pk.MultiContext([0, 0, 0], sc.n, 400_000, mode=pk.MODE_WORLD, max_shapes=len(sc.shapes))
+    m.add_shapes(sc.shapes)
+    m.resize(sc.n)
+    pos = sc.pos.copy()
+    for step in range(3):
+        disp = np.full_like(pos, 0.01 * step)
+        w.step(pos, sc.quat, disp, sc.shape_id, sc.flags)
+        one.upload(pos, sc.quat, disp, sc.shape_id, sc.flags)
+        one.collide()
+        m.upload(pos, sc.quat, disp, sc.shape_id, sc.flags)
+        tot = m.collide()
+        keys = [c.pairs() for c in m.ctx]
+        cons = [c.contacts() for c in m.ctx]
+        allk = np.concatenate(keys)
+        assert tot.num_pairs == len(allk) == len(np.unique(allk))
+        assert np.array_equal(np.sort(allk), w.pairs())
+        assert np.array_equal(np.sort(allk), one.pairs())
+        allc = np.concatenate(cons)
+        assert tot.num_contacts == len(allc)
+        order = np.argsort(allc["key"], kind="stable")
+        assert np.array_equal(allc[order].view(np.uint8), one.contacts().view(np.uint8))
+        pos = pos + 0.03
+    assert tot.num_pairs > 10_000 and min(len(k) for k in keys) > 0
+    one.close()
+    m.close()
