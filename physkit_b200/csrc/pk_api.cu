@@ -591,8 +591,8 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     if ((s = dev_alloc(ctx, &(ptr), (count))) != PK_OK) \
     return fail(s)
     A(ctx->d_shapes, cfg->max_shapes);
-    A(ctx->d_verts, cfg->max_hull_vertices * 3 + 2);
-    A(ctx->d_verts_f, cfg->max_hull_vertices + 1);
+    A(ctx->d_verts, (cfg->max_hull_vertices + cfg->max_shapes) * 3 + 2); // + one padding vertex per hull at most
+    A(ctx->d_verts_f, cfg->max_hull_vertices + cfg->max_shapes + 2);
     A(ctx->d_pos, nb * 3);
     A(ctx->d_quat, nb * 4);
     A(ctx->d_disp, nb * 3);
@@ -717,7 +717,12 @@ int pk_shape_hull(pk_ctx *ctx, const double *xyz, uint32_t nverts, uint32_t *id)
 {
     if (!ctx || !xyz || nverts == 0) return PK_E_INVALID;
     size_t off = ctx->h_verts.size() / 3;
-    if (off + nverts > ctx->cfg.max_hull_vertices)
+    if (off & 1u) // hulls start at even vertex offsets: the float scan loads vertex pairs with 32-byte loads
+    {
+        ctx->h_verts.insert(ctx->h_verts.end(), 3, 0.0);
+        ++off;
+    }
+    if (off + nverts > ctx->cfg.max_hull_vertices + ctx->cfg.max_shapes)
     {
         ctx->last_error = "hull vertex pool full (pk_config.max_hull_vertices)";
         return PK_E_INVALID;

@@ -20,9 +20,9 @@ constexpr int KIND_HULL = 3;   // mesh::instance::support  src/mesh.cpp:442-448,
 constexpr uint32_t HULL_PREFILTER_MIN = 16; // hulls up to this size are scanned in FP64 directly
 
 #ifndef PK_HULL_UNROLL
-#define PK_HULL_UNROLL 8
+#define PK_HULL_UNROLL 4
 #endif
-constexpr int HULL_UNROLL = PK_HULL_UNROLL; // vertex loads in flight per lane in the float scan of a hull
+constexpr int HULL_UNROLL = PK_HULL_UNROLL; // 32-byte vertex-pair loads in flight per lane in the float scan of a hull
 
 constexpr uint8_t FLAG_STATIC = 1;
 constexpr uint8_t FLAG_ALIVE = 2;
@@ -210,15 +210,29 @@ __device__ __forceinline__ uint32_t hull_argmax(const float4 *__restrict__ vf, c
     for (uint32_t i = 0; i < nverts; ++i) f1 = fmaxf(f1, pk_hull_fdot(__ldg(vf + i), lx, ly, lz));
 #else
     float f1 = -3.4e38f, f2 = -3.4e38f; // largest, second largest (equal values count twice)
-#pragma unroll HULL_UNROLL
-    for (uint32_t i = 0; i < nverts; ++i)
+    // ncu (C4): the scan saturates the L1 data stage (72–89 % of its peak) — every lane walks its own hull, so
+    // a 16-byte load is one wavefront per lane.  Two vertices per 32-byte load (LDG.256, sm_100) halve the
+    // wavefronts; hulls start at even vertex offsets (pk_shape_hull) so that the pairs are aligned.
+    auto track = [&](const float4 w, uint32_t i)
     {
-        const float f = pk_hull_fdot(__ldg(vf + i), lx, ly, lz);
+        const float f = pk_hull_fdot(w, lx, ly, lz);
         const bool gt = f > f1;
         f2 = gt ? f1 : fmaxf(f2, f);
         best = gt ? i : best;
         f1 = gt ? f : f1;
+    };
+    const uint32_t npairs = nverts >> 1;
+#pragma unroll HULL_UNROLL
+    for (uint32_t k = 0; k < npairs; ++k)
+    {
+        float4 a, b;
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                     : "l"(vf + 2 * k));
+        track(a, 2 * k);
+        track(b, 2 * k + 1);
     }
+    if (nverts & 1u) track(__ldg(vf + nverts - 1), nverts - 1);
     if (f2 < f1 - 2.0f * E) return best; // a single candidate
     best = 0;
 #endif
