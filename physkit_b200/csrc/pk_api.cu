@@ -83,6 +83,7 @@ struct pk_ctx
     cudaStream_t copy_stream = nullptr; // pk_collide: pair keys go to the host while the narrowphase runs
     cudaEvent_t ev_sorted = nullptr, ev_pairs_copied = nullptr;
     bool want_host_results = false, pairs_in_flight = false;
+    bool contacts_mirrored = false; // pk_collide: the EPA kernels stored this step's contact records into h_contacts as well
     std::string last_error;
     int sm_count = 0;
 
@@ -373,7 +374,7 @@ BodyArrays body_arrays(pk_ctx *ctx)
 // GJK → scan → EPA over npairs pairs given either as sorted keys or as explicit index arrays.
 // Leaves contacts (slot order = pair order among GJK hits) in ctx->d_contacts[0], validity in d_valid.
 int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, const uint32_t *d_b, uint64_t npairs,
-                    bool timed)
+                    bool timed, ContactRec *mirror = nullptr)
 {
     if (timed) cudaEventRecord(ctx->ev[ST_GJK], ctx->stream);
     if (npairs)
@@ -404,7 +405,7 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs, ctx->d_counters + C_EPA_CURSOR,
-            ctx->d_counters + C_VALID);
+            ctx->d_counters + C_VALID, mirror);
         ctx->launches += 2;
 #else
         // Pairs with a sphere: heap-free pop (SCAN instance).  What it hands back (exact distance ties that
@@ -416,21 +417,23 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
             epa_init_kernel<<<div_up(most, 128), 128, 0, ctx->stream>>>(ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
                                                                        ctx->d_epa_init);
         }
-        epa_scan_kernel<false><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
+        auto scan = mirror ? epa_scan_kernel<false, true> : epa_scan_kernel<false, false>;
+        auto heap = mirror ? epa_scan_kernel<true, true> : epa_scan_kernel<true, false>;
+        scan<<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
             ctx->d_counters + C_EPA_SCAN_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr, ctx->d_epa_init);
-        epa_scan_kernel<true><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
+            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr, ctx->d_epa_init, mirror);
+        heap<<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
             ctx->d_counters + C_EPA_SCAN_CURSOR + 1, ctx->d_counters + C_VALID, ctx->d_epa_fallback2,
             ctx->d_counters + C_EPA_FALLBACK + 1, ctx->d_counters + C_CLASS_COUNT, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK, ctx->d_epa_init);
+            ctx->d_counters + C_EPA_FALLBACK, ctx->d_epa_init, mirror);
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK + 1, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_fallback2, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
-            ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID);
+            ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID, mirror);
         ctx->launches += 5;
 #endif
     }
@@ -649,10 +652,12 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
         A(ctx->d_slabs, threads * EPA_SLAB_BYTES);
 #ifndef PK_EPA_LEGACY_ONLY
         // epa_scan_kernel: 41 KB of shared memory per 64-thread block, as many blocks per SM as fit
-        cudaFuncSetAttribute(epa_scan_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(epa_scan_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_scan_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_scan_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_scan_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_scan_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int es_per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_scan_kernel<false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_scan_kernel<false, false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
             es_per_sm = 1;
 #ifdef PK_ES_BLOCKS_PER_SM
         es_per_sm = std::min(es_per_sm, PK_ES_BLOCKS_PER_SM);
@@ -965,7 +970,26 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         cudaEventRecord(ctx->ev_pairs_copied, ctx->copy_stream);
         ctx->pairs_in_flight = true;
     }
-    PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true));
+    // pk_collide: the EPA kernels also deliver every finished contact record to the caller-visible pinned buffer
+    // (one coalesced 88-byte store per record, spread over the time the kernels run), so that the device→host
+    // copy of the contacts does not have to wait for them.  Only when a pinned buffer for max_contacts records
+    // is affordable; a step whose contacts need compaction (a GJK hit without an EPA result) falls back to the copy.
+    ContactRec *mirror = nullptr;
+    ctx->contacts_mirrored = false;
+    if (ctx->want_host_results && npairs && ctx->max_contacts * sizeof(pk_contact) <= (2ull << 30) && !getenv("PK_NO_MIRROR"))
+    {
+        if (ctx->h_contacts_cap < ctx->max_contacts)
+        {
+            if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
+            ctx->h_contacts = nullptr;
+            ctx->h_contacts_cap = 0;
+            PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_contacts), ctx->max_contacts * sizeof(pk_contact), cudaHostAllocDefault));
+            ctx->h_contacts_cap = ctx->max_contacts;
+        }
+        mirror = reinterpret_cast<ContactRec *>(ctx->h_contacts);
+        ctx->contacts_mirrored = true;
+    }
+    PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true, mirror));
     PK_TRY(read_counters(ctx));
     uint64_t hits = ctx->h_counters[C_HITS];
     uint64_t valid = ctx->h_counters[C_VALID];
@@ -978,6 +1002,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         hits = ctx->max_contacts;
     }
     ctx->d_contacts_final = ctx->d_contacts[0];
+    if (status != PK_OK) ctx->contacts_mirrored = false;
     if (status == PK_OK && valid != hits)
     {
         // some GJK hits ended without a value in EPA (degenerate pad / exhausted heap / overflow)
@@ -991,6 +1016,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
                                                                  static_cast<int>(sizeof(ContactRec)));
         ctx->launches += 4;
         ctx->d_contacts_final = ctx->d_contacts[1];
+        ctx->contacts_mirrored = false;
         PK_CUDA(cudaGetLastError());
     }
     cudaEventRecord(ctx->ev[ST_FETCH], s);
@@ -1051,7 +1077,7 @@ int pk_fetch_results(pk_ctx *ctx)
         PK_CUDA(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs_sorted, ctx->num_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                 ctx->stream));
     ctx->pairs_in_flight = false;
-    if (ctx->num_contacts)
+    if (ctx->num_contacts && !ctx->contacts_mirrored) // (mirrored: the EPA kernels already delivered them)
         PK_CUDA(cudaMemcpyAsync(ctx->h_contacts, ctx->d_contacts_final, ctx->num_contacts * sizeof(pk_contact),
                                 cudaMemcpyDeviceToHost, ctx->stream));
     cudaEventRecord(ctx->ev[ST_COUNT], ctx->stream);

@@ -215,7 +215,7 @@ __device__ __forceinline__ double4 es_face_plane(d3 pi, d3 pj, d3 pk, bool has_o
 }
 
 // collision.cpp:424-454
-__device__ __noinline__ void es_write_result(const EsSlab &sl, double4 nd, unsigned long long t, ContactRec *out, uint64_t key)
+__device__ __noinline__ void es_write_result(const EsSlab &sl, double4 nd, unsigned long long t, ContactRec *out, uint64_t key, ContactRec *stage)
 {
     d3 n{nd.x, nd.y, nd.z};
     const double2 *q0 = reinterpret_cast<const double2 *>(sl.vab + 6 * es_v(t, 0));
@@ -246,6 +246,7 @@ __device__ __noinline__ void es_write_result(const EsSlab &sl, double4 nd, unsig
     out->world_b[1] = wb.y;
     out->world_b[2] = wb.z;
     out->depth = nd.w;
+    if (stage) *stage = *out; // a second copy in the thread's (now dead) shared-memory area, flushed to the host by the warp
 }
 
 // HEAP mode: the first ES_HCAP heap entries live in the thread's shared-memory area (every sift starts
@@ -414,7 +415,8 @@ epa_init_kernel(const SimplexRec *__restrict__ simplices, const unsigned long lo
 // mode per pair was measured slower: more registers, and both pop paths in every warp's instruction
 // stream).  Pairs handed back are published in fallback_list[] (entries start as EPA_LIST_EMPTY), where a
 // small epa_kernel launch running next to these kernels picks them up (pk_api.cu).
-template <bool HEAP>
+// MIRROR: the pk_collide instance, which also delivers finished records to the caller's pinned buffer.
+template <bool HEAP, bool MIRROR>
 __global__ void __launch_bounds__(ES_THREADS, PK_ES_MIN_BLOCKS)
 epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
                 const uint32_t *__restrict__ pair_b, const SimplexRec *__restrict__ simplices,
@@ -424,7 +426,7 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
                 unsigned long long *__restrict__ counters /* [0]=valid contacts */, uint32_t *__restrict__ fallback_list,
                 unsigned long long *__restrict__ fallback_count, const unsigned long long *__restrict__ class_count,
                 const uint32_t *__restrict__ leftovers, const unsigned long long *__restrict__ leftover_count,
-                const EpaInit *__restrict__ init)
+                const EpaInit *__restrict__ init, ContactRec *contacts_host)
 {
     // Work of the HEAP instance: first the pairs the SCAN instance handed back (leftovers[], complete at
     // launch: mostly sphere–sphere pairs with an exact distance tie, long ones — started first so that
@@ -468,6 +470,8 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
     int fb = 0; // reason + 1 when the current pair has to go to epa_kernel (one atomic site for all of them)
+    bool flush_pending = false; // a finished record waits in this lane's shared-memory area (pk_collide)
+    uint32_t flush_slot = 0;
     auto is_free = [&](int f) -> bool
     {
         const unsigned long long w = (f < 64) ? fm0 : (f < 128 ? fm1 : fm2);
@@ -530,6 +534,31 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         }
         const unsigned m_active = __ballot_sync(FULL, active);
         const unsigned m_idle = __ballot_sync(FULL, !active && !done);
+        if constexpr (MIRROR)
+        {
+            // pk_collide: finished records go to the caller's pinned buffer from here, so that no device→host
+            // copy of the contacts has to wait for the kernels to end.  The lane that finished a pair left the
+            // record in its shared-memory area; eleven lanes store it with ONE 8-byte store each (88
+            // contiguous bytes).  Letting the finishing lane store to host memory itself — eleven dependent
+            // stores from one lane of a divergent warp — slowed the kernel by more than the copy costs.
+            unsigned m_flush = __ballot_sync(FULL, flush_pending);
+            if (m_flush)
+            {
+                __syncwarp();
+                const int lane = t & 31;
+                while (m_flush)
+                {
+                    const int L = __ffs(static_cast<int>(m_flush)) - 1;
+                    m_flush &= m_flush - 1u;
+                    const uint32_t slot_l = __shfl_sync(FULL, flush_slot, L);
+                    if (lane < 11)
+                        reinterpret_cast<unsigned long long *>(contacts_host + slot_l)[lane] =
+                            reinterpret_cast<const unsigned long long *>(&shm.pop.th[(t & ~31) + L])[lane];
+                }
+                __syncwarp();
+                flush_pending = false;
+            }
+        }
         if (m_active == 0 && m_idle == 0) break;
         if (!active && !done && (__popc(m_idle) >= PK_ES_FETCH_MIN || m_active == 0))
         {
@@ -809,7 +838,13 @@ epa_scan_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint
         const d3 p = P(sp);
         if (finished || dot(mn, p) - mf.w < 1e-6) // converged (collision.cpp:465-466)
         {
-            es_write_result(sl, mf, mt, contacts + out_slot, key);
+            es_write_result(sl, mf, mt, contacts + out_slot, key, MIRROR ? reinterpret_cast<ContactRec *>(&shm.pop.th[t]) : nullptr);
+            if constexpr (MIRROR)
+            {
+                flush_pending = true;
+                flush_slot = out_slot;
+                if (hi < 22) hi = 22; // the staged record covers the first 22 key slots: the next fetch must reset them
+            }
             valid[out_slot] = 1;
             ++n_valid;
             active = false;

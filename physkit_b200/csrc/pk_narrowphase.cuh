@@ -598,7 +598,7 @@ __device__ __forceinline__ bool epa_face_plane(d3 pi, d3 pj, d3 pk, bool has_opp
 }
 
 // collision.cpp:424-454
-__device__ __forceinline__ void epa_write_result(const EpaSlab &sl, double4 nd, const FaceTopo &t, ContactRec *out, uint64_t key)
+__device__ __forceinline__ void epa_write_result(const EpaSlab &sl, double4 nd, const FaceTopo &t, ContactRec *out, uint64_t key, ContactRec *mirror = nullptr)
 {
     d3 n{nd.x, nd.y, nd.z};
     const double2 *q0 = reinterpret_cast<const double2 *>(sl.vab + 6 * t.v[0]);
@@ -629,6 +629,7 @@ __device__ __forceinline__ void epa_write_result(const EpaSlab &sl, double4 nd, 
     out->world_b[1] = wb.y;
     out->world_b[2] = wb.z;
     out->depth = nd.w;
+    if (mirror) *mirror = *out; // pk_collide: the caller's pinned copy (this kernel only sees the rare hand-backs)
 }
 
 __device__ __forceinline__ void smem_put_shape(EpaSmem &sm, int which, const ShapeView &v)
@@ -718,7 +719,7 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
            const unsigned long long *__restrict__ hit_count_ptr, uint64_t hit_capacity,
            const uint32_t *__restrict__ out_index, const uint32_t *__restrict__ order, ContactRec *__restrict__ contacts,
            uint8_t *__restrict__ valid, unsigned char *__restrict__ slabs, unsigned long long *__restrict__ cursor,
-           unsigned long long *__restrict__ counters /* [0]=valid contacts, [1]=overflow */)
+           unsigned long long *__restrict__ counters /* [0]=valid contacts, [1]=overflow */, ContactRec *contacts_host = nullptr)
 {
     __shared__ EpaSmem shm;
     const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
@@ -858,7 +859,7 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
         const FaceTopo mt = sl.load_topo(min_face);
         if (iter >= 64)
         {
-            epa_write_result(sl, mf, mt, contacts + out_slot, key); // best guess (collision.cpp:500-503)
+            epa_write_result(sl, mf, mt, contacts + out_slot, key, contacts_host ? contacts_host + out_slot : nullptr); // best guess (collision.cpp:500-503)
             valid[out_slot] = 1;
             ++n_valid;
             active = false;
@@ -870,7 +871,7 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
         d3 p = P(sp);
         if (dot(mn, p) - mf.w < 1e-6)
         {
-            epa_write_result(sl, mf, mt, contacts + out_slot, key); // converged (collision.cpp:465-466)
+            epa_write_result(sl, mf, mt, contacts + out_slot, key, contacts_host ? contacts_host + out_slot : nullptr); // converged (collision.cpp:465-466)
             valid[out_slot] = 1;
             ++n_valid;
             active = false;
