@@ -88,3 +88,76 @@ def test_gpu_reproduces_golden_pairs():
         contacts_equal_bitwise(rec, hit, g["hit"], g["contacts"])
     finally:
         ctx.close()
+
+
+# ------------------------------------------------------------------ rows around the stage
+def _rows_replay(g):
+    import sys
+
+    sys.path.insert(0, GOLD)
+    from make_golden import downstream_state
+
+    sc = scene_c3(side=int(g["side"]))
+    return sc, downstream_state(sc.n)
+
+
+def test_oracle_reproduces_golden_rows():
+    g = np.load(os.path.join(GOLD, "rows_c3_side8.npz"))
+    import sys
+
+    sys.path.insert(0, GOLD)
+    from make_golden import rows_c3
+
+    got = rows_c3(int(g["side"]), int(g["steps"]))
+    for k in ("man_keys", "man_counts", "row_keys", "row_points"):
+        assert np.array_equal(got[k], g[k]), k
+    assert np.array_equal(_bits(got["rows"]), _bits(g["rows"]))
+    assert np.array_equal(got["rays"]["ray"], g["rays"]["ray"]) and np.array_equal(got["rays"]["body"], g["rays"]["body"])
+    assert np.array_equal(_bits(got["rays"]["distance"]), _bits(g["rays"]["distance"]))
+    assert np.array_equal(_bits(got["dyn_vel"]), _bits(g["dyn_vel"])) and np.array_equal(_bits(got["dyn_pos"]), _bits(g["dyn_pos"]))
+    assert np.abs(got["dyn_quat"] - g["dyn_quat"]).max() < 1e-13  # sin / cos of the libm at hand
+    assert len(g["rows"]) > 300 and len(g["rays"]) > 300
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_rows():
+    import physkit_b200 as pk
+    from gpu_util import make_context
+
+    g = np.load(os.path.join(GOLD, "rows_c3_side8.npz"))
+    sc, (vel, w, mass, inertia, rest, fric, origins, dirs) = _rows_replay(g)
+    ctx = make_context(sc, max_pairs=100_000, mode=pk.MODE_WORLD)
+    ctx.manifolds_enable(10_000)
+    ctx.dynamics_enable()
+    ctx.dynamics_upload(vel, w, mass, inertia)
+    ctx.material_upload(rest, fric)
+    pos = sc.pos.copy()
+    for step in range(int(g["steps"])):
+        disp = np.full_like(pos, 0.01 * step)
+        ctx.upload(pos, sc.quat, disp, sc.shape_id, sc.flags)
+        ctx.collide()
+        ctx.manifolds_update()
+        pos = pos + 0.03
+    man = ctx.manifolds()
+    assert np.array_equal(man["key"], g["man_keys"]) and np.array_equal(man["count"], g["man_counts"])
+    n = ctx.contact_rows_setup(1.0 / 60.0, 9.81)
+    rows = ctx.contact_rows()
+    assert n == len(g["rows"]) and np.array_equal(rows["key"], g["row_keys"]) and np.array_equal(rows["point"], g["row_points"])
+    flat = np.concatenate([np.concatenate([rows[r]["J_v"], rows[r]["J_w_a"], rows[r]["J_w_b"], rows[r]["M_eff"][:, None], rows[r]["bias"][:, None]], axis=1)
+                           for r in ("normal", "tangent1", "tangent2")] +
+                          [rows["friction_coeff"][:, None], rows["inv_m_11"][:, None], rows["inv_m_12"][:, None], rows["inv_m_22"][:, None],
+                           rows["accumulated"]], axis=1)
+    assert np.array_equal(_bits(flat), _bits(g["rows"]))
+    hits = ctx.raycast(origins, dirs, 6.0)
+    assert np.array_equal(hits["ray"], g["rays"]["ray"]) and np.array_equal(hits["body"], g["rays"]["body"])
+    assert np.array_equal(_bits(hits["distance"]), _bits(g["rays"]["distance"]))
+    # integrator from the initial poses
+    ctx.upload(sc.pos, sc.quat, np.zeros_like(sc.pos), sc.shape_id, sc.flags)
+    ctx.dynamics_upload(vel, w, mass, inertia)
+    for _ in range(3):
+        ctx.integrate_velocities(1.0 / 60.0, (0.0, -9.81, 0.0))
+        ctx.integrate_positions(1.0 / 60.0)
+    p, q, v, om = ctx.dynamics_download(sc.n)
+    assert np.array_equal(_bits(v), _bits(g["dyn_vel"])) and np.array_equal(_bits(p), _bits(g["dyn_pos"]))
+    assert np.abs(q - g["dyn_quat"]).max() < 1e-13
+    ctx.close()
