@@ -219,7 +219,11 @@ int pk_bodies_update_pose(pk_ctx *ctx, const double *pos_xyz, const double *quat
  * pk_collide_resident: run broadphase + narrowphase on the state already in HBM; only the counters
  *   come back to the host.  Results stay on the device.
  * pk_fetch_results:    D2H of pair keys and contact records into ctx-owned pinned memory.
- * pk_collide:          both (what gpu_world::step_impl calls).
+ * pk_collide:          both (what gpu_world::step_impl calls).  The sorted pair keys travel to the host while the
+ *                      narrowphase runs and the contact records are stored into the pinned result buffer by the
+ *                      EPA kernels themselves, so no copy waits for the end of the step (the buffer holds
+ *                      max_contacts records, up to 2 GB; above that, or with PK_NO_MIRROR=1 in the environment,
+ *                      the records are copied after the kernels).
  * Pairs are sorted ascending by key; contacts are sorted by key as well. */
 int pk_collide_resident(pk_ctx *ctx, pk_step_result *out);
 int pk_fetch_results(pk_ctx *ctx);
