@@ -1244,7 +1244,17 @@ int pk_multi_collide(pk_multi *m, pk_step_result *total)
     std::vector<int> status(n, PK_OK);
     std::vector<std::thread> th;
     th.reserve(n);
-    for (size_t i = 0; i < n; ++i) th.emplace_back([&, i] { status[i] = pk_collide(m->ctx[i], &res[i]); });
+    for (size_t i = 0; i < n; ++i)
+    {
+        try
+        {
+            th.emplace_back([&, i] { status[i] = pk_collide(m->ctx[i], &res[i]); });
+        }
+        catch (...) // no thread to be had: nothing may cross the C boundary, the context is stepped here instead
+        {
+            status[i] = pk_collide(m->ctx[i], &res[i]);
+        }
+    }
     for (std::thread &t : th) t.join();
     if (total)
     {
