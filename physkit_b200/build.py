@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpk_collide.so")
 SOURCES = ["pk_api.cu"]
-HEADERS = ["pk_common.cuh", "pk_broadphase.cuh", "pk_narrowphase.cuh", "pk_epa_scan.cuh", "pk_manifold.cuh", "pk_sort.cuh", "../../include/pk_collide.h"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + ["../../include/pk_collide.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -10,6 +10,7 @@
 #include "pk_common.cuh"
 #include "pk_narrowphase.cuh"
 #include "pk_epa_scan.cuh"
+#include "pk_epa_coop.cuh"
 #include "pk_manifold.cuh"
 #include "pk_dynamics.cuh"
 #include "pk_ray.cuh"
@@ -143,6 +144,7 @@ struct pk_ctx
     // results
     int32_t epoch = 0;
     bool have_results = false, fetched = false;
+    bool device_results = false; // the narrowphase buffers still hold the last step's results (pk_gjk_epa_batch re-uses them)
     uint64_t num_pairs = 0, num_contacts = 0;
     uint64_t *h_pairs = nullptr;
     size_t h_pairs_cap = 0;
@@ -417,8 +419,13 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
             epa_init_kernel<<<div_up(most, 128), 128, 0, ctx->stream>>>(ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
                                                                        ctx->d_epa_init);
         }
+#ifdef PK_EPA_SCAN_OLD
         auto scan = mirror ? epa_scan_kernel<false, true> : epa_scan_kernel<false, false>;
         auto heap = mirror ? epa_scan_kernel<true, true> : epa_scan_kernel<true, false>;
+#else
+        auto scan = mirror ? epa_coop_kernel<false, true> : epa_coop_kernel<false, false>;
+        auto heap = mirror ? epa_coop_kernel<true, true> : epa_coop_kernel<true, false>;
+#endif
         scan<<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
@@ -652,12 +659,17 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
         A(ctx->d_slabs, threads * EPA_SLAB_BYTES);
 #ifndef PK_EPA_LEGACY_ONLY
         // epa_scan_kernel: 41 KB of shared memory per 64-thread block, as many blocks per SM as fit
-        cudaFuncSetAttribute(epa_scan_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(epa_scan_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(epa_scan_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(epa_scan_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#ifdef PK_EPA_SCAN_OLD
+#define PK_EPA_MAIN_KERNEL epa_scan_kernel
+#else
+#define PK_EPA_MAIN_KERNEL epa_coop_kernel
+#endif
+        cudaFuncSetAttribute(PK_EPA_MAIN_KERNEL<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(PK_EPA_MAIN_KERNEL<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(PK_EPA_MAIN_KERNEL<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(PK_EPA_MAIN_KERNEL<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int es_per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_scan_kernel<false, false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, PK_EPA_MAIN_KERNEL<false, false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
             es_per_sm = 1;
 #ifdef PK_ES_BLOCKS_PER_SM
         es_per_sm = std::min(es_per_sm, PK_ES_BLOCKS_PER_SM);
@@ -1031,6 +1043,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
     ctx->num_pairs = npairs;
     ctx->num_contacts = (status == PK_OK) ? valid : 0;
     ctx->have_results = status == PK_OK;
+    ctx->device_results = ctx->have_results;
     if (out)
     {
         std::memset(out, 0, sizeof(*out));
@@ -1060,6 +1073,8 @@ int pk_fetch_results(pk_ctx *ctx)
 {
     if (!ctx) return PK_E_INVALID;
     if (!ctx->have_results) return PK_E_STATE;
+    if (ctx->fetched) return PK_OK;
+    if (!ctx->device_results) return PK_E_STATE;
     cudaSetDevice(ctx->cfg.device);
     cudaEventRecord(ctx->ev[ST_FETCH], ctx->stream);
     PK_TRY(ensure_host_pairs(ctx, ctx->num_pairs));
@@ -1120,7 +1135,7 @@ int pk_pairs_device(pk_ctx *ctx, const void **dptr, uint64_t *n)
 {
     if (!ctx || !dptr || !n) return PK_E_INVALID;
     if (!ctx->have_results) return PK_E_STATE;
-    *dptr = ctx->d_pairs_sorted;
+    *dptr = ctx->d_pairs_sorted; // the pair keys are not touched by pk_gjk_epa_batch
     *n = ctx->num_pairs;
     return PK_OK;
 }
@@ -1128,7 +1143,7 @@ int pk_pairs_device(pk_ctx *ctx, const void **dptr, uint64_t *n)
 int pk_contact_points(pk_ctx *ctx, const pk_contact_point **pts, uint64_t *n)
 {
     if (!ctx || !pts || !n) return PK_E_INVALID;
-    if (!ctx->have_results) return PK_E_STATE;
+    if (!ctx->have_results || !ctx->device_results) return PK_E_STATE;
     cudaSetDevice(ctx->cfg.device);
     static_assert(sizeof(ContactPointRec) == sizeof(pk_contact_point), "contact point layouts differ");
     const uint64_t m = ctx->num_contacts;
@@ -1716,7 +1731,7 @@ int pk_manifolds_enable(pk_ctx *ctx, uint64_t capacity)
 int pk_manifolds_update(pk_ctx *ctx, pk_manifold_result *out)
 {
     if (!ctx) return PK_E_INVALID;
-    if (!ctx->man_cap || !ctx->have_results || ctx->man_epoch == ctx->epoch) return PK_E_STATE;
+    if (!ctx->man_cap || !ctx->have_results || !ctx->device_results || ctx->man_epoch == ctx->epoch) return PK_E_STATE;
     cudaSetDevice(ctx->cfg.device);
     cudaStream_t s = ctx->stream;
     const uint64_t m_prev = ctx->man_count;
@@ -1855,7 +1870,7 @@ int pk_manifolds_set_impulses(pk_ctx *ctx, const double *impulses, uint64_t n)
 int pk_contacts_device(pk_ctx *ctx, const void **dptr, uint64_t *n)
 {
     if (!ctx || !dptr || !n) return PK_E_INVALID;
-    if (!ctx->have_results) return PK_E_STATE;
+    if (!ctx->have_results || !ctx->device_results) return PK_E_STATE;
     *dptr = ctx->d_contacts_final;
     *n = ctx->num_contacts;
     return PK_OK;
@@ -1925,11 +1940,16 @@ int pk_gjk_epa_batch_device(pk_ctx *ctx, const uint32_t *d_a, const uint32_t *d_
     cudaStream_t s = ctx->stream;
     ctx->launches = 0;
     cudaEventRecord(ctx->ev[ST_BOUNDS], s);
-    scene_reset_kernel<<<1, 64, 0, s>>>(ctx->d_scene, ctx->d_counters, C_COUNT);
+    // the batch shares the narrowphase buffers (hit flags, contact slots, contact records) with the step: what the
+    // last pk_collide left there is gone: results that were not fetched to the host can no longer be, nor merged
+    // into manifolds (PK_E_STATE).  Host copies already fetched, the pair keys, the tree and the scene box of that
+    // step (pk_raycast) stay valid.
+    ctx->device_results = false;
+    scene_reset_kernel<<<1, 64, 0, s>>>(nullptr, ctx->d_counters, C_COUNT);
     PK_TRY(run_narrowphase(ctx, nullptr, d_a, d_b, n, true));
     if (n)
         expand_contacts_kernel<<<div_up(n, 256), 256, 0, s>>>(ctx->d_hit, ctx->d_out_index, ctx->d_valid, ctx->d_contacts[0],
-                                                             d_a, d_b, n, reinterpret_cast<ContactRec *>(d_out), d_hit);
+                                                             d_a, d_b, n, ctx->max_contacts, reinterpret_cast<ContactRec *>(d_out), d_hit);
     ctx->launches += 2;
     cudaEventRecord(ctx->ev[ST_COUNT], s);
     PK_TRY(read_counters(ctx));

@@ -71,11 +71,15 @@ __device__ __forceinline__ float ord2f(uint32_t u)
 }
 
 // scene[0..2] = min centre (ordered uint), scene[3..5] = max centre
+// scene == nullptr: counters only (pk_gjk_epa_batch must leave the last step's scene box to pk_raycast)
 __global__ void scene_reset_kernel(uint32_t *scene, unsigned long long *counters, int ncounters)
 {
     int t = threadIdx.x;
-    if (t < 3) scene[t] = 0xFFFFFFFFu;
-    else if (t < 6) scene[t] = 0u;
+    if (scene)
+    {
+        if (t < 3) scene[t] = 0xFFFFFFFFu;
+        else if (t < 6) scene[t] = 0u;
+    }
     if (t < ncounters) counters[t] = 0ull;
 }
 

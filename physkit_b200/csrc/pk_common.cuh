@@ -226,9 +226,14 @@ __device__ __forceinline__ uint32_t hull_argmax(const float4 *__restrict__ vf, c
     for (uint32_t k = 0; k < npairs; ++k)
     {
         float4 a, b;
+#ifdef __CUDA_ARCH__
         asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                      : "l"(vf + 2 * k));
+#else // host build of the kernels (tests/cpp/simt_host.h): same two vertices, plain loads
+        a = vf[2 * k];
+        b = vf[2 * k + 1];
+#endif
         track(a, 2 * k);
         track(b, 2 * k + 1);
     }

@@ -175,7 +175,14 @@ __device__ __forceinline__ int fi4(int f) { return f == 3 ? 1 : 0; }
 __device__ __forceinline__ int fj4(int f) { return (0x3321 >> (4 * f)) & 0xF; }
 __device__ __forceinline__ int fk4(int f) { return (0x2132 >> (4 * f)) & 0xF; }
 __device__ __forceinline__ int fo4(int f) { return (0x0213 >> (4 * f)) & 0xF; }
-__device__ __forceinline__ void es_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void es_prefetch(const void *p)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 __device__ __forceinline__ float es_inf() { return __int_as_float(0x7F800000); }
 
 template <class SM> __device__ __forceinline__ void es_put_shape(SM &sm, int which, const ShapeView &v, const BodyArrays &ba)

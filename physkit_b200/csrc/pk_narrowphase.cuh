@@ -767,6 +767,11 @@ epa_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                     key = (static_cast<uint64_t>(ia) << 32) | ib;
                 }
                 out_slot = out_index[pair];
+                if (out_slot >= hit_capacity)
+                {
+                    ++n_over; // more GJK hits than contact records (the step reports PK_E_PAIR_OVERFLOW): nothing to write to
+                    continue;
+                }
                 Simplex s;
                 s.n = static_cast<int>(r->n & 0xFFu);
                 for (int i = 0; i < 4; ++i)
@@ -1075,13 +1080,14 @@ contact_points_kernel(const ContactRec *__restrict__ contacts, uint64_t n, const
 __global__ void expand_contacts_kernel(const uint8_t *__restrict__ hit, const uint32_t *__restrict__ index,
                                        const uint8_t *__restrict__ valid, const ContactRec *__restrict__ compact,
                                        const uint32_t *__restrict__ pa, const uint32_t *__restrict__ pb, uint64_t n,
-                                       ContactRec *__restrict__ out, uint8_t *__restrict__ out_hit)
+                                       uint64_t capacity, ContactRec *__restrict__ out, uint8_t *__restrict__ out_hit)
 {
     uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (k >= n) return;
     bool h = hit[k] != 0;
     uint32_t slot = index[k];
-    if (h) h = valid[slot] != 0;
+    if (h) h = slot < capacity && valid[slot] != 0; // hits beyond the contact capacity have no record
+
     ContactRec r;
     if (h)
         r = compact[slot];

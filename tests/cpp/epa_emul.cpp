@@ -1,0 +1,171 @@
+// epa_emul.cpp — TEST INFRASTRUCTURE: the narrowphase's EPA kernels (physkit_b200/csrc/pk_epa_coop.cuh,
+// pk_epa_scan.cuh, pk_narrowphase.cuh) compiled by g++ through tests/cpp/simt_host.h and driven the way
+// run_narrowphase (pk_api.cu) drives them on the device: GJK hits → contact slots → cost-class order →
+// epa_init_kernel → epa_coop_kernel<SCAN> → epa_coop_kernel<HEAP> (takes what SCAN handed back) → epa_kernel (takes
+// what HEAP handed back).  tests/test_epa_emul.py compares the records with the oracle bit for bit.
+// Not linked into, nor reachable from, the product library.
+#include "simt_host.h"
+
+inline unsigned __activemask()
+{
+    std::abort(); // kernels that need it (gjk_kernel, epa_order_kernel) are not emulated
+}
+template <class T> inline unsigned __match_any_sync(unsigned, T) { std::abort(); }
+
+#include "../../physkit_b200/csrc/pk_epa_coop.cuh"
+
+using namespace pk;
+
+extern "C" int emu_gjk_epa(const ShapeRec *shapes, const double *verts, uint64_t nverts_pool, const double *pos, const double *quat,
+                           const uint32_t *shape_id, const uint32_t *pa, const uint32_t *pb, uint64_t n, uint64_t capacity,
+                           ContactRec *out, uint8_t *hit_out, int mirror, int arrival, uint64_t *stats /*[8]*/)
+{
+    std::vector<float4> vf(nverts_pool + 2);
+    for (uint64_t i = 0; i < nverts_pool; ++i)
+        vf[i] = make_float4(static_cast<float>(verts[3 * i]), static_cast<float>(verts[3 * i + 1]), static_cast<float>(verts[3 * i + 2]), 0.f);
+    BodyArrays ba;
+    ba.shapes = shapes;
+    ba.verts = verts;
+    ba.verts_f = vf.data();
+    ba.pos = pos;
+    ba.quat = quat;
+    ba.shape_id = shape_id;
+
+    // gjk_kernel (pk_narrowphase.cuh:311-360) per pair.  On the device the hits take their simplex slots in arrival
+    // order; `arrival` picks pair order (0), reversed (1) or a fixed pseudo-random permutation (2)
+    std::vector<uint8_t> hit(n, 0);
+    std::vector<SimplexRec> simplices(capacity + 1);
+    unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // [0] hits, [1..3] class counts, [4] valid, [5] dropped
+    std::vector<uint64_t> seq(n);
+    for (uint64_t k = 0; k < n; ++k) seq[k] = arrival == 1 ? n - 1 - k : k;
+    if (arrival == 2)
+    {
+        uint64_t x = 0x9E3779B97F4A7C15ull;
+        for (uint64_t k = n; k > 1; --k)
+        {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            std::swap(seq[k - 1], seq[x % k]);
+        }
+    }
+    for (uint64_t q = 0; q < n; ++q)
+    {
+        const uint64_t k = seq[q];
+        ShapeView A = load_shape(ba, pa[k]);
+        ShapeView B = load_shape(ba, pb[k]);
+        Simplex s;
+        const bool h = gjk_collision(A, B, s);
+        hit[k] = h ? 1 : 0;
+        if (!h) continue;
+        const unsigned long long slot = counters[0]++;
+        if (slot >= capacity) continue;
+        SimplexRec &r = simplices[slot];
+        std::memset(&r, 0, sizeof(r));
+        for (int i = 0; i < s.n; ++i)
+        {
+            r.v[i][0] = s.pt[i].pa.x; r.v[i][1] = s.pt[i].pa.y; r.v[i][2] = s.pt[i].pa.z;
+            r.v[i][3] = s.pt[i].pb.x; r.v[i][4] = s.pt[i].pb.y; r.v[i][5] = s.pt[i].pb.z;
+        }
+        const bool smooth_a = A.kind == KIND_SPHERE || (A.kind == KIND_HULL && A.nverts > HULL_PREFILTER_MIN);
+        const bool smooth_b = B.kind == KIND_SPHERE || (B.kind == KIND_HULL && B.nverts > HULL_PREFILTER_MIN);
+        const uint32_t cls = (smooth_a ? 1u : 0u) + (smooth_b ? 1u : 0u);
+        counters[1 + cls]++;
+        r.n = static_cast<uint32_t>(s.n) | (cls << 8);
+        r.pair = static_cast<uint32_t>(k);
+    }
+    const uint64_t nhits = std::min<uint64_t>(counters[0], capacity);
+    // contact slot = rank of the pair among the hits; order[] = hit slots grouped by class, heaviest first
+    std::vector<uint32_t> out_index(n + 1, 0);
+    {
+        uint32_t run = 0;
+        for (uint64_t k = 0; k < n; ++k)
+        {
+            out_index[k] = run;
+            run += hit[k];
+        }
+    }
+    std::vector<uint32_t> order(nhits + 1);
+    {
+        uint64_t fill[3] = {counters[3] + counters[2], counters[3], 0}; // class 0 after 2 and 1; class 1 after 2
+        for (uint64_t s = 0; s < nhits; ++s)
+        {
+            const uint32_t cls = (simplices[s].n >> 8) & 3u;
+            if (fill[cls] < nhits) order[fill[cls]] = static_cast<uint32_t>(s);
+            fill[cls]++;
+        }
+    }
+    std::vector<EpaInit> init(nhits + 1);
+    std::vector<ContactRec> contacts(capacity + 1), host_mirror(capacity + 1);
+    std::vector<uint8_t> valid(capacity + 16, 0);
+    std::vector<uint32_t> fb1(nhits + 1, 0), fb2(nhits + 1, 0);
+    unsigned long long cursor[3] = {0, 0, 0}, fbc[2] = {0, 0};
+    unsigned long long *hit_count = &counters[0];
+    unsigned long long *class_count = &counters[1];
+    unsigned long long *vcount = &counters[4];
+    const unsigned block = ES_THREADS;
+    std::vector<unsigned char> spill(static_cast<size_t>(block) * std::max(es_slab_bytes(false), es_slab_bytes(true)));
+    std::vector<unsigned char> slabs(static_cast<size_t>(EPA_THREADS) * EPA_SLAB_BYTES);
+    ContactRec *mir = mirror ? host_mirror.data() : nullptr;
+
+    if (nhits)
+    {
+        simt::launch((nhits + 127) / 128, 128, [&]() { epa_init_kernel(simplices.data(), hit_count, capacity, init.data()); });
+        auto run_coop = [&](auto kernel, unsigned long long *cur, uint32_t *fbl, unsigned long long *fbn, const uint32_t *left,
+                            const unsigned long long *nleft)
+        {
+            simt::launch(1, block,
+                         [&]()
+                         {
+                             kernel(ba, nullptr, pa, pb, simplices.data(), hit_count, capacity, out_index.data(), order.data(), contacts.data(),
+                                    valid.data(), spill.data(), cur, vcount, fbl, fbn, class_count, left, nleft, init.data(), mir);
+                         });
+        };
+        if (mirror)
+        {
+            run_coop(epa_coop_kernel<false, true>, &cursor[0], fb1.data(), &fbc[0], nullptr, nullptr);
+            run_coop(epa_coop_kernel<true, true>, &cursor[1], fb2.data(), &fbc[1], fb1.data(), &fbc[0]);
+        }
+        else
+        {
+            run_coop(epa_coop_kernel<false, false>, &cursor[0], fb1.data(), &fbc[0], nullptr, nullptr);
+            run_coop(epa_coop_kernel<true, false>, &cursor[1], fb2.data(), &fbc[1], fb1.data(), &fbc[0]);
+        }
+        simt::launch(1, EPA_THREADS,
+                     [&]()
+                     {
+                         epa_kernel(ba, nullptr, pa, pb, simplices.data(), &fbc[1], capacity, out_index.data(), fb2.data(), contacts.data(),
+                                    valid.data(), slabs.data(), &cursor[2], vcount, mir);
+                     });
+    }
+    // expand_contacts_kernel
+    for (uint64_t k = 0; k < n; ++k)
+    {
+        bool h = hit[k] != 0;
+        const uint32_t slot = out_index[k];
+        if (h) h = slot < capacity && valid[slot] != 0;
+        ContactRec r;
+        if (h)
+        {
+            r = contacts[slot];
+            if (mirror && std::memcmp(&r, &host_mirror[slot], sizeof(r)) != 0) return -2; // the pinned copy must be the same record
+        }
+        else
+        {
+            std::memset(&r, 0, sizeof(r));
+            r.key = (static_cast<uint64_t>(pa[k]) << 32) | pb[k];
+        }
+        out[k] = r;
+        hit_out[k] = h ? 1 : 0;
+    }
+    if (stats)
+    {
+        stats[0] = counters[0]; // GJK hits
+        stats[1] = fbc[0];      // handed back by SCAN
+        stats[2] = fbc[1];      // handed back by HEAP
+        stats[3] = counters[4]; // valid contacts
+        stats[4] = counters[5]; // dropped: no room for the contact
+        stats[5] = counters[1];
+        stats[6] = counters[2];
+        stats[7] = counters[3];
+    }
+    return 0;
+}

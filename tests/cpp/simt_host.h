@@ -1,0 +1,153 @@
+// simt_host.h — TEST INFRASTRUCTURE.  Runs the library's CUDA kernels on the CPU, one OS thread per CUDA thread,
+// so that their control flow (warp votes, shuffles, work sharing between lanes, hand-back lists) can be checked
+// against the oracle in the container that has no GPU, and so that a kernel whose lanes disagree about a
+// warp-wide primitive dead-locks HERE (a test time-out) and not on the GPU box.
+//
+// Not part of the product: nothing under physkit_b200/ or include/ includes this file, and the product has no
+// CPU path (tests/test_abi_cpu.py).  The arithmetic is the kernels' own source compiled by g++ with
+// -ffp-contract=off for SSE2 (no FMA), which is what -fmad=false gives on the device; pk_div_by_rcp's explicit
+// fma calls go to libm's correctly rounded fma.
+//
+// Only what the EPA kernels use is provided: full-mask votes / shuffles / __syncwarp (a std::barrier over the 32
+// threads of a warp), atomicAdd on 64-bit counters, the bit and rounding intrinsics.  `__shared__` becomes a
+// function-local static, so ONE block of a given kernel instance runs at a time (blocks are run one after the
+// other; the kernels under test are persistent and take their work from an atomic cursor, so a single block does
+// all of it).
+#pragma once
+
+#include <cuda_runtime.h> // vector types and make_*; under g++ the __device__ / __global__ annotations vanish
+
+#include <barrier>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#undef __shared__
+#define __shared__ static
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
+
+namespace simt
+{
+struct Idx
+{
+    unsigned x = 0, y = 0, z = 0;
+};
+struct Warp
+{
+    std::barrier<> bar{32};
+    uint64_t buf[32];
+};
+inline thread_local Idx tl_threadIdx, tl_blockIdx, tl_blockDim, tl_gridDim;
+inline thread_local Warp *tl_warp = nullptr;
+inline thread_local int tl_lane = 0;
+
+template <class K> void launch(unsigned grid, unsigned block, K &&kernel)
+{
+    assert(block % 32 == 0 || grid * block <= 32 || true);
+    for (unsigned b = 0; b < grid; ++b)
+    {
+        const unsigned nwarps = (block + 31) / 32;
+        std::vector<Warp> warps(nwarps);
+        std::vector<std::thread> th;
+        th.reserve(block);
+        for (unsigned t = 0; t < block; ++t)
+            th.emplace_back(
+                [&, t]()
+                {
+                    tl_threadIdx = Idx{t, 0, 0};
+                    tl_blockIdx = Idx{b, 0, 0};
+                    tl_blockDim = Idx{block, 1, 1};
+                    tl_gridDim = Idx{grid, 1, 1};
+                    tl_warp = &warps[t / 32];
+                    tl_lane = static_cast<int>(t % 32);
+                    kernel();
+                });
+        for (auto &x : th) x.join();
+    }
+}
+} // namespace simt
+
+#define threadIdx simt::tl_threadIdx
+#define blockIdx simt::tl_blockIdx
+#define blockDim simt::tl_blockDim
+#define gridDim simt::tl_gridDim
+
+constexpr unsigned SIMT_FULL = 0xFFFFFFFFu;
+
+inline unsigned __ballot_sync(unsigned mask, int pred)
+{
+    assert(mask == SIMT_FULL);
+    simt::Warp &w = *simt::tl_warp;
+    w.buf[simt::tl_lane] = pred ? 1u : 0u;
+    w.bar.arrive_and_wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= static_cast<unsigned>(w.buf[i]) << i;
+    w.bar.arrive_and_wait();
+    return r;
+}
+template <class T> inline T simt_exchange(unsigned mask, T v, int src)
+{
+    assert(mask == SIMT_FULL);
+    static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+    simt::Warp &w = *simt::tl_warp;
+    uint64_t bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    w.buf[simt::tl_lane] = bits;
+    w.bar.arrive_and_wait();
+    uint64_t got = (src >= 0 && src < 32) ? w.buf[src] : bits;
+    w.bar.arrive_and_wait();
+    T out;
+    std::memcpy(&out, &got, sizeof(T));
+    return out;
+}
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src) { return simt_exchange(mask, v, src & 31); }
+template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta)
+{
+    const int src = simt::tl_lane - static_cast<int>(delta);
+    return simt_exchange(mask, v, src < 0 ? simt::tl_lane : src);
+}
+inline void __syncwarp(unsigned mask = SIMT_FULL)
+{
+    assert(mask == SIMT_FULL);
+    simt::tl_warp->bar.arrive_and_wait();
+}
+inline void __syncthreads() { std::abort(); } // not used by the kernels under test
+
+template <class T> inline T __ldg(const T *p) { return *p; }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+inline float __int_as_float(int x)
+{
+    float f;
+    std::memcpy(&f, &x, 4);
+    return f;
+}
+inline float __double2float_rd(double d)
+{
+    float f = static_cast<float>(d);
+    if (static_cast<double>(f) > d) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+inline float __double2float_ru(double d)
+{
+    float f = static_cast<float>(d);
+    if (static_cast<double>(f) < d) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+inline double __drcp_rn(double x) { return 1.0 / x; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

@@ -1,0 +1,96 @@
+"""Host-side run of the library's EPA kernels (tests/cpp/epa_emul.cpp through tests/cpp/simt_host.h): TEST
+INFRASTRUCTURE for the container without a GPU.  The kernels' own source is compiled by g++, one OS thread per CUDA
+thread, warp votes / shuffles as barriers; a test compares the records with the oracle.  The product never loads this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "epa_emul.cpp")
+OUT = os.path.join(ROOT, "tests", "cpp", "_build", "libepa_emul.so")
+CUDA_INC = "/usr/local/cuda/include"
+
+SHAPE_REC = np.dtype([("a", "<f8", 3), ("b", "<f8", 3), ("kind", "<i4"), ("vert_off", "<u4"), ("nverts", "<u4"), ("mesh_box", "<u4")])
+CONTACT = np.dtype([("key", "<u8"), ("normal", "<f8", 3), ("world_a", "<f8", 3), ("world_b", "<f8", 3), ("depth", "<f8")])
+assert SHAPE_REC.itemsize == 64 and CONTACT.itemsize == 88
+
+KIND = {"aabb": 0, "obb": 1, "sphere": 2, "hull": 3}
+
+
+def available() -> bool:
+    return os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h"))
+
+
+def build(force: bool = False) -> str:
+    deps = [SRC, os.path.join(ROOT, "tests", "cpp", "simt_host.h")] + [
+        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_narrowphase.cuh", "pk_epa_scan.cuh", "pk_epa_coop.cuh")
+    ]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cmd = ["g++", "-O1", "-g", "-std=c++20", "-ffp-contract=off", "-pthread", "-fPIC", "-shared", "-I" + CUDA_INC, SRC, "-o", OUT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stderr[-4000:])
+    return OUT
+
+
+def shape_table(specs):
+    """ShapeRec table + vertex pool exactly as pk_shape_box / _sphere / _aabb / _hull (pk_api.cu) build them."""
+    tab = np.zeros(len(specs), dtype=SHAPE_REC)
+    verts = []
+    off = 0
+    for i, s in enumerate(specs):
+        k = s[0]
+        tab[i]["kind"] = KIND[k]
+        if k == "aabb":
+            tab[i]["a"] = np.asarray(s[1], dtype=np.float64)
+            tab[i]["b"] = np.asarray(s[2], dtype=np.float64)
+        elif k == "obb":
+            tab[i]["a"] = np.asarray(s[1], dtype=np.float64)
+        elif k == "sphere":
+            tab[i]["a"][0] = float(s[1])
+        else:
+            v = np.ascontiguousarray(s[1], dtype=np.float64).reshape(-1, 3)
+            if off & 1:
+                verts.append(np.zeros((1, 3)))
+                off += 1
+            tab[i]["vert_off"] = off
+            tab[i]["nverts"] = len(v)
+            tab[i]["a"] = v.min(axis=0)
+            tab[i]["b"] = v.max(axis=0)
+            hb = tab[i]["b"]
+            if len(v) == 8 and (hb > 0).all():
+                want = np.array([[hb[0] if (0x66 >> j) & 1 else -hb[0], hb[1] if (0xCC >> j) & 1 else -hb[1], hb[2] if j >= 4 else -hb[2]] for j in range(8)])
+                tab[i]["mesh_box"] = 1 if np.array_equal(v, want) else 0
+            verts.append(v)
+            off += len(v)
+    pool = np.ascontiguousarray(np.concatenate(verts) if verts else np.zeros((2, 3)), dtype=np.float64)
+    return tab, pool
+
+
+def gjk_epa_pairs(specs, pos, quat, shape_id, pair_a, pair_b, capacity=None, mirror=False, arrival=2):
+    """→ (hit[n] u8, contacts[n] CONTACT, stats dict), as pk_gjk_epa_batch delivers them."""
+    lib = C.CDLL(build())
+    tab, pool = shape_table(specs)
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+    quat = np.ascontiguousarray(quat, dtype=np.float64).reshape(-1, 4)
+    sid = np.ascontiguousarray(shape_id, dtype=np.uint32)
+    pa = np.ascontiguousarray(pair_a, dtype=np.uint32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.uint32)
+    n = len(pa)
+    cap = n if capacity is None else int(capacity)
+    out = np.zeros(n, dtype=CONTACT)
+    hit = np.zeros(n, dtype=np.uint8)
+    stats = np.zeros(8, dtype=np.uint64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emu_gjk_epa(p(tab), p(pool), C.c_uint64(len(pool)), p(pos), p(quat), p(sid), p(pa), p(pb), C.c_uint64(n), C.c_uint64(cap),
+                         p(out), p(hit), C.c_int(1 if mirror else 0), C.c_int(arrival), p(stats))
+    if rc != 0:
+        raise RuntimeError(f"emu_gjk_epa failed: {rc}")
+    names = ["gjk_hits", "scan_handed_back", "heap_handed_back", "valid", "dropped", "class0", "class1", "class2"]
+    return hit, out, dict(zip(names, (int(x) for x in stats)))
