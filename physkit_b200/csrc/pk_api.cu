@@ -9,7 +9,6 @@
 #include "pk_broadphase.cuh"
 #include "pk_common.cuh"
 #include "pk_narrowphase.cuh"
-#include "pk_epa_scan.cuh"
 #include "pk_epa_coop.cuh"
 #include "pk_manifold.cuh"
 #include "pk_dynamics.cuh"
@@ -29,8 +28,7 @@
 
 using namespace pk;
 
-// EPA implementation: epa_scan_kernel (pk_epa_scan.cuh) + epa_kernel for what it hands back (default);
-// -DPK_EPA_LEGACY_ONLY builds the thread-per-pair epa_kernel alone (the r1 baseline, kept for A/B runs)
+// EPA implementation: epa_coop_kernel (pk_epa_coop.cuh) + epa_kernel (pk_narrowphase.cuh) for what it hands back
 namespace
 {
 
@@ -67,8 +65,8 @@ enum Counter
     C_GJK_CURSOR,
     C_CLASS_COUNT, // [3]
     C_CLASS_FILL = C_CLASS_COUNT + 3, // [3]
-    C_EPA_FALLBACK = C_CLASS_FILL + 3, // [2] pairs handed back by the SCAN / by the HEAP instance of epa_scan_kernel
-    C_EPA_SCAN_CURSOR = C_EPA_FALLBACK + 3, // [2] work cursors of those two launches
+    C_EPA_FALLBACK = C_CLASS_FILL + 3, // [0] SCAN pairs started again in HEAP mode, [1] pairs epa_coop_kernel handed to epa_kernel
+    C_EPA_SCAN_CURSOR = C_EPA_FALLBACK + 3, // work cursor of epa_coop_kernel
     C_EPA_FB_CURSOR = C_EPA_SCAN_CURSOR + 3, // work cursor of epa_kernel on the second fallback list
     C_EPA_REASONS = C_EPA_FALLBACK + 10, // [6] debug builds (PK_ES_REASONS)
     C_GJK_CLASS = 32, // [4] GJK prefilter survivors per shape-kind class
@@ -135,7 +133,7 @@ struct pk_ctx
     uint32_t *d_gjk_work = nullptr;
     unsigned char *d_slabs = nullptr;
     unsigned char *d_epa_spill = nullptr;
-    uint32_t *d_epa_fallback = nullptr, *d_epa_fallback2 = nullptr;
+    uint32_t *d_epa_fallback2 = nullptr; // hit slots epa_coop_kernel handed to epa_kernel
     EpaInit *d_epa_init = nullptr;
     uint32_t epa_scan_blocks = 0;
     uint32_t epa_blocks = 0;
@@ -403,46 +401,38 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
         epa_order_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
                                                                      ctx->d_counters + C_CLASS_COUNT, ctx->d_counters + C_CLASS_FILL,
                                                                      ctx->d_epa_order);
-#ifdef PK_EPA_LEGACY_ONLY
-        epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
-            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
-            ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs, ctx->d_counters + C_EPA_CURSOR,
-            ctx->d_counters + C_VALID, mirror);
-        ctx->launches += 2;
-#else
-        // Pairs with a sphere: heap-free pop (SCAN instance).  What it hands back (exact distance ties that
-        // only the heap's history can break) goes first into the HEAP instance, which restates the heap and
-        // then does the polyhedron pairs; what that one hands back (padded simplices, improper horizons,
-        // polytopes past 768 faces: a handful) is left to epa_kernel.
+        // One persistent launch for all hits (pk_epa_coop.cuh); what it hands back (padded simplices, improper
+        // horizons, polytopes past the slab: a handful) is left to epa_kernel.
         {
             const uint64_t most = std::min<uint64_t>(npairs, ctx->max_contacts);
-            epa_init_kernel<<<div_up(most, 128), 128, 0, ctx->stream>>>(ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
-                                                                       ctx->d_epa_init);
+            epa_init_kernel<<<div_up(most, 128), 128, 0, ctx->stream>>>(ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts, d_keys,
+                                                                       d_a, d_b, ctx->d_out_index, ctx->d_epa_init);
         }
-#ifdef PK_EPA_SCAN_OLD
-        auto scan = mirror ? epa_scan_kernel<false, true> : epa_scan_kernel<false, false>;
-        auto heap = mirror ? epa_scan_kernel<true, true> : epa_scan_kernel<true, false>;
-#else
-        auto scan = mirror ? epa_coop_kernel<false, true> : epa_coop_kernel<false, false>;
-        auto heap = mirror ? epa_coop_kernel<true, true> : epa_coop_kernel<true, false>;
-#endif
-        scan<<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
-            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
-            ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
-            ctx->d_counters + C_EPA_SCAN_CURSOR, ctx->d_counters + C_VALID, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK, ctx->d_counters + C_CLASS_COUNT, nullptr, nullptr, ctx->d_epa_init, mirror);
-        heap<<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(
-            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_HITS, ctx->max_contacts,
-            ctx->d_out_index, ctx->d_epa_order, ctx->d_contacts[0], ctx->d_valid, ctx->d_epa_spill,
-            ctx->d_counters + C_EPA_SCAN_CURSOR + 1, ctx->d_counters + C_VALID, ctx->d_epa_fallback2,
-            ctx->d_counters + C_EPA_FALLBACK + 1, ctx->d_counters + C_CLASS_COUNT, ctx->d_epa_fallback,
-            ctx->d_counters + C_EPA_FALLBACK, ctx->d_epa_init, mirror);
+        EcParams ep;
+        ep.bodies = body_arrays(ctx);
+        ep.simplices = ctx->d_simplices;
+        ep.hit_count_ptr = ctx->d_counters + C_HITS;
+        ep.hit_capacity = ctx->max_contacts;
+        ep.order = ctx->d_epa_order;
+        ep.contacts = ctx->d_contacts[0];
+        ep.valid = ctx->d_valid;
+        ep.slabs = ctx->d_epa_spill;
+        ep.cursor = ctx->d_counters + C_EPA_SCAN_CURSOR;
+        ep.counters = ctx->d_counters + C_VALID;
+        ep.fallback = ctx->d_epa_fallback2;
+        ep.fallback_count = ctx->d_counters + C_EPA_FALLBACK + 1;
+        ep.restart_count = ctx->d_counters + C_EPA_FALLBACK;
+        ep.init = ctx->d_epa_init;
+        ep.contacts_host = mirror;
+        if (mirror)
+            epa_coop_kernel<true><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(ep);
+        else
+            epa_coop_kernel<false><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(ep);
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK + 1, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_fallback2, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
             ctx->d_counters + C_EPA_FB_CURSOR, ctx->d_counters + C_VALID, mirror);
-        ctx->launches += 5;
-#endif
+        ctx->launches += 4;
     }
     if (timed) cudaEventRecord(ctx->ev[ST_COMPACT], ctx->stream);
     PK_CUDA(cudaGetLastError());
@@ -507,7 +497,7 @@ int pk_destroy(pk_ctx *ctx)
                    ctx->d_merge_flag,  ctx->d_pkeys[0],     ctx->d_pkeys[1],    ctx->d_hit,          ctx->d_out_index,
                    ctx->d_scan_tiles,  ctx->d_simplices,    ctx->d_contacts[0], ctx->d_contacts[1],  ctx->d_valid,
                    ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order,    ctx->d_gjk_work,
-                   ctx->d_epa_spill,   ctx->d_epa_fallback, ctx->d_epa_fallback2, ctx->d_epa_init};
+                   ctx->d_epa_spill,   ctx->d_epa_fallback2, ctx->d_epa_init};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -657,19 +647,11 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
         uint64_t threads = std::min(want_threads, std::max<uint64_t>(need_threads, EPA_THREADS));
         ctx->epa_blocks = static_cast<uint32_t>(threads / EPA_THREADS);
         A(ctx->d_slabs, threads * EPA_SLAB_BYTES);
-#ifndef PK_EPA_LEGACY_ONLY
-        // epa_scan_kernel: 41 KB of shared memory per 64-thread block, as many blocks per SM as fit
-#ifdef PK_EPA_SCAN_OLD
-#define PK_EPA_MAIN_KERNEL epa_scan_kernel
-#else
-#define PK_EPA_MAIN_KERNEL epa_coop_kernel
-#endif
-        cudaFuncSetAttribute(PK_EPA_MAIN_KERNEL<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(PK_EPA_MAIN_KERNEL<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(PK_EPA_MAIN_KERNEL<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(PK_EPA_MAIN_KERNEL<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        // epa_coop_kernel: 43 KB of shared memory per 64-thread block, as many blocks per SM as fit
+        cudaFuncSetAttribute(epa_coop_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_coop_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int es_per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, PK_EPA_MAIN_KERNEL<false, false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_coop_kernel<false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
             es_per_sm = 1;
 #ifdef PK_ES_BLOCKS_PER_SM
         es_per_sm = std::min(es_per_sm, PK_ES_BLOCKS_PER_SM);
@@ -677,15 +659,12 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
 #ifdef PK_ES_FORCE_BLOCKS
         es_per_sm = PK_ES_FORCE_BLOCKS;
 #endif
-        if (getenv("PK_DEBUG")) fprintf(stderr, "[pk] epa_scan_kernel: %d blocks per SM\n", es_per_sm);
+        if (getenv("PK_DEBUG")) fprintf(stderr, "[pk] epa_coop_kernel: %d blocks per SM\n", es_per_sm);
         const uint64_t es_need = (nc + ES_THREADS - 1) / ES_THREADS;
         ctx->epa_scan_blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(ctx->sm_count) * es_per_sm, es_need)));
-        // the two instances run one after the other and share the slab area
-        A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_scan_blocks) * ES_THREADS * std::max(es_slab_bytes(false), es_slab_bytes(true)));
+        A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_scan_blocks) * ES_THREADS * es_slab_bytes());
         A(ctx->d_epa_fallback2, nc);
         A(ctx->d_epa_init, nc);
-#endif
-        A(ctx->d_epa_fallback, nc);
     }
 #undef A
     if (cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_counters), C_COUNT * sizeof(unsigned long long),

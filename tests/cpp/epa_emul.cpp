@@ -1,8 +1,7 @@
 // epa_emul.cpp — TEST INFRASTRUCTURE: the narrowphase's EPA kernels (physkit_b200/csrc/pk_epa_coop.cuh,
-// pk_epa_scan.cuh, pk_narrowphase.cuh) compiled by g++ through tests/cpp/simt_host.h and driven the way
+// pk_narrowphase.cuh) compiled by g++ through tests/cpp/simt_host.h and driven the way
 // run_narrowphase (pk_api.cu) drives them on the device: GJK hits → contact slots → cost-class order →
-// epa_init_kernel → epa_coop_kernel<SCAN> → epa_coop_kernel<HEAP> (takes what SCAN handed back) → epa_kernel (takes
-// what HEAP handed back).  tests/test_epa_emul.py compares the records with the oracle bit for bit.
+// epa_init_kernel → epa_coop_kernel → epa_kernel (takes what that one handed back).  tests/test_epa_emul.py compares the records with the oracle bit for bit.
 // Not linked into, nor reachable from, the product library.
 #include "simt_host.h"
 
@@ -12,13 +11,27 @@ inline unsigned __activemask()
 }
 template <class T> inline unsigned __match_any_sync(unsigned, T) { std::abort(); }
 
+#define PK_EC_STATS
+namespace pk
+{
+unsigned long long g_ec_stats[16];
+}
 #include "../../physkit_b200/csrc/pk_epa_coop.cuh"
 
 using namespace pk;
 
+extern "C" void emu_stats(unsigned long long *out, int reset)
+{
+    for (int i = 0; i < 16; ++i)
+    {
+        out[i] = pk::g_ec_stats[i];
+        if (reset) pk::g_ec_stats[i] = 0;
+    }
+}
+
 extern "C" int emu_gjk_epa(const ShapeRec *shapes, const double *verts, uint64_t nverts_pool, const double *pos, const double *quat,
                            const uint32_t *shape_id, const uint32_t *pa, const uint32_t *pb, uint64_t n, uint64_t capacity,
-                           ContactRec *out, uint8_t *hit_out, int mirror, int arrival, uint64_t *stats /*[8]*/)
+                           ContactRec *out, uint8_t *hit_out, int mirror, int arrival, int nblocks, uint64_t *stats /*[8]*/)
 {
     std::vector<float4> vf(nverts_pool + 2);
     for (uint64_t i = 0; i < nverts_pool; ++i)
@@ -96,44 +109,44 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, const double *verts, uint64_t
     std::vector<EpaInit> init(nhits + 1);
     std::vector<ContactRec> contacts(capacity + 1), host_mirror(capacity + 1);
     std::vector<uint8_t> valid(capacity + 16, 0);
-    std::vector<uint32_t> fb1(nhits + 1, 0), fb2(nhits + 1, 0);
-    unsigned long long cursor[3] = {0, 0, 0}, fbc[2] = {0, 0};
+    std::vector<uint32_t> fb2(nhits + 1, 0);
+    unsigned long long cursors[4] = {0, 0, 0, 0}, fbc[3] = {0, 0, 0};
     unsigned long long *hit_count = &counters[0];
-    unsigned long long *class_count = &counters[1];
-    unsigned long long *vcount = &counters[4];
     const unsigned block = ES_THREADS;
-    std::vector<unsigned char> spill(static_cast<size_t>(block) * std::max(es_slab_bytes(false), es_slab_bytes(true)));
+    std::vector<unsigned char> spill(static_cast<size_t>(block) * nblocks * es_slab_bytes());
     std::vector<unsigned char> slabs(static_cast<size_t>(EPA_THREADS) * EPA_SLAB_BYTES);
     ContactRec *mir = mirror ? host_mirror.data() : nullptr;
 
     if (nhits)
     {
-        simt::launch((nhits + 127) / 128, 128, [&]() { epa_init_kernel(simplices.data(), hit_count, capacity, init.data()); });
-        auto run_coop = [&](auto kernel, unsigned long long *cur, uint32_t *fbl, unsigned long long *fbn, const uint32_t *left,
-                            const unsigned long long *nleft)
-        {
-            simt::launch(1, block,
-                         [&]()
-                         {
-                             kernel(ba, nullptr, pa, pb, simplices.data(), hit_count, capacity, out_index.data(), order.data(), contacts.data(),
-                                    valid.data(), spill.data(), cur, vcount, fbl, fbn, class_count, left, nleft, init.data(), mir);
-                         });
-        };
+        simt::launch((nhits + 127) / 128, 128,
+                     [&]() { epa_init_kernel(simplices.data(), hit_count, capacity, nullptr, pa, pb, out_index.data(), init.data()); });
+        EcParams ep;
+        ep.bodies = ba;
+        ep.simplices = simplices.data();
+        ep.hit_count_ptr = hit_count;
+        ep.hit_capacity = capacity;
+        ep.order = order.data();
+        ep.contacts = contacts.data();
+        ep.valid = valid.data();
+        ep.slabs = spill.data();
+        ep.cursor = &cursors[0];
+        ep.counters = &counters[4];
+        ep.fallback = fb2.data();
+        ep.fallback_count = &fbc[1];
+        ep.restart_count = &fbc[0];
+        ep.init = init.data();
+        ep.contacts_host = mir;
+        // blocks run one after the other (see simt_host.h): the first takes the whole list, later blocks find it drained
         if (mirror)
-        {
-            run_coop(epa_coop_kernel<false, true>, &cursor[0], fb1.data(), &fbc[0], nullptr, nullptr);
-            run_coop(epa_coop_kernel<true, true>, &cursor[1], fb2.data(), &fbc[1], fb1.data(), &fbc[0]);
-        }
+            simt::launch(nblocks, block, [&]() { epa_coop_kernel<true>(ep); });
         else
-        {
-            run_coop(epa_coop_kernel<false, false>, &cursor[0], fb1.data(), &fbc[0], nullptr, nullptr);
-            run_coop(epa_coop_kernel<true, false>, &cursor[1], fb2.data(), &fbc[1], fb1.data(), &fbc[0]);
-        }
+            simt::launch(nblocks, block, [&]() { epa_coop_kernel<false>(ep); });
         simt::launch(1, EPA_THREADS,
                      [&]()
                      {
                          epa_kernel(ba, nullptr, pa, pb, simplices.data(), &fbc[1], capacity, out_index.data(), fb2.data(), contacts.data(),
-                                    valid.data(), slabs.data(), &cursor[2], vcount, mir);
+                                    valid.data(), slabs.data(), &cursors[3], &counters[4], mir);
                      });
     }
     // expand_contacts_kernel
@@ -159,8 +172,8 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, const double *verts, uint64_t
     if (stats)
     {
         stats[0] = counters[0]; // GJK hits
-        stats[1] = fbc[0];      // handed back by SCAN
-        stats[2] = fbc[1];      // handed back by HEAP
+        stats[1] = fbc[0];      // SCAN pairs started again in HEAP mode
+        stats[2] = fbc[1];      // handed to epa_kernel
         stats[3] = counters[4]; // valid contacts
         stats[4] = counters[5]; // dropped: no room for the contact
         stats[5] = counters[1];

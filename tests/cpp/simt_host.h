@@ -36,6 +36,9 @@
 #ifndef __noinline__
 #define __noinline__ __attribute__((noinline))
 #endif
+#ifndef __maxnreg__
+#define __maxnreg__(...)
+#endif
 
 namespace simt
 {
@@ -151,3 +154,9 @@ inline double __drcp_rn(double x) { return 1.0 / x; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long expected, unsigned long long desired)
+{
+    __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return expected; // the old value, as the device intrinsic returns it
+}

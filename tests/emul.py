@@ -27,7 +27,7 @@ def available() -> bool:
 
 def build(force: bool = False) -> str:
     deps = [SRC, os.path.join(ROOT, "tests", "cpp", "simt_host.h")] + [
-        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_narrowphase.cuh", "pk_epa_scan.cuh", "pk_epa_coop.cuh")
+        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_narrowphase.cuh", "pk_epa_coop.cuh")
     ]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
@@ -73,7 +73,7 @@ def shape_table(specs):
     return tab, pool
 
 
-def gjk_epa_pairs(specs, pos, quat, shape_id, pair_a, pair_b, capacity=None, mirror=False, arrival=2):
+def gjk_epa_pairs(specs, pos, quat, shape_id, pair_a, pair_b, capacity=None, mirror=False, arrival=2, nblocks=1):
     """→ (hit[n] u8, contacts[n] CONTACT, stats dict), as pk_gjk_epa_batch delivers them."""
     lib = C.CDLL(build())
     tab, pool = shape_table(specs)
@@ -89,8 +89,8 @@ def gjk_epa_pairs(specs, pos, quat, shape_id, pair_a, pair_b, capacity=None, mir
     stats = np.zeros(8, dtype=np.uint64)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib.emu_gjk_epa(p(tab), p(pool), C.c_uint64(len(pool)), p(pos), p(quat), p(sid), p(pa), p(pb), C.c_uint64(n), C.c_uint64(cap),
-                         p(out), p(hit), C.c_int(1 if mirror else 0), C.c_int(arrival), p(stats))
+                         p(out), p(hit), C.c_int(1 if mirror else 0), C.c_int(arrival), C.c_int(nblocks), p(stats))
     if rc != 0:
         raise RuntimeError(f"emu_gjk_epa failed: {rc}")
-    names = ["gjk_hits", "scan_handed_back", "heap_handed_back", "valid", "dropped", "class0", "class1", "class2"]
+    names = ["gjk_hits", "restarted_in_heap_mode", "handed_to_epa_kernel", "valid", "dropped", "class0", "class1", "class2"]
     return hit, out, dict(zip(names, (int(x) for x in stats)))

@@ -2,7 +2,7 @@
 
 tests/emul.py compiles the kernels' own source (pk_epa_coop.cuh and what it builds on) with g++ and runs one OS thread
 per CUDA thread (tests/cpp/simt_host.h).  What this pins down before any GPU time is spent: the split of an iteration
-into the per-pair part and the per-edge part dealt out over the warp, the hand-back chain SCAN → HEAP → epa_kernel, the
+into the per-pair part and the per-edge part dealt out over the warp, the restart of tied pairs in HEAP mode, the hand-back to epa_kernel, the
 parked results / refill protocol, the pinned-buffer copy — all bit for bit against the oracle.  A kernel whose lanes
 disagree about a warp-wide vote dead-locks here (pytest time-out) instead of on the GPU box.  The same scenes run through
 the real kernels in tests/test_gpu_narrowphase.py."""
@@ -11,7 +11,7 @@ import pytest
 
 import emul
 import oracle
-from scenes import Scene, SplitMix64, random_pairs_scene, scene_c3, scene_c4, box_vertices, sphere_vertices
+from scenes import IDENT, Scene, SplitMix64, random_pairs_scene, scene_c3, scene_c4, box_vertices, sphere_vertices
 
 pytestmark = [pytest.mark.skipif(not emul.available(), reason="CUDA headers not installed"), pytest.mark.timeout(600)]
 
@@ -93,3 +93,44 @@ def test_more_hits_than_contact_records():
     got = np.concatenate([out["normal"], out["world_a"], out["world_b"], out["depth"][:, None]], axis=1)
     m = hit.astype(bool)
     assert np.array_equal(got[m].view(np.uint64), np.ascontiguousarray(out_ref[m]).view(np.uint64))
+
+
+def test_reference_kat_cases_in_one_batch():
+    """All GJK / EPA cases of the reference's tests (tests/kat_cases.py) as one batch: same-box and containment cases
+    reach pad_simplex, i.e. the second hand-back (HEAP → epa_kernel)."""
+    from kat_cases import EPA_CASES, GJK_CASES
+
+    shapes, pos, quat = [], [], []
+    for c in list(GJK_CASES) + list(EPA_CASES):
+        for spec, p, q in (c[1], c[2]):
+            shapes.append(spec)
+            pos.append(p)
+            quat.append(q)
+    # the first support point is the origin (collision.cpp:174): GJK returns a one-point simplex, EPA pads it
+    for r, gap in ((1.0, 2.0), (0.5, 1.0), (0.25, 0.5)):
+        shapes += [("sphere", r), ("sphere", r)]
+        pos += [(0.0, 0.0, 0.0), (gap, 0.0, 0.0)]
+        quat += [IDENT, IDENT]
+    n = len(shapes) // 2
+    sc = Scene(shapes, np.array(pos), np.array(quat), np.arange(2 * n))
+    pa = np.arange(0, 2 * n, 2, dtype=np.uint32)
+    hit, stats = _check(sc, pa, pa + 1)
+    assert stats["handed_to_epa_kernel"] > 0
+
+
+def test_sphere_pairs_with_exact_ties_restart_in_heap_mode():
+    """Axis-aligned equal spheres: mirror-symmetric polytopes whose equidistant faces only the heap's history can order.
+    Most pairs are started again in HEAP mode by their lane; two blocks: the second finds the list drained."""
+    rng = SplitMix64(5)
+    n = 600
+    shapes = [("sphere", 0.5), ("sphere", 0.3)]
+    pos = np.zeros((2 * n, 3))
+    pos[0::2] = rng.uniform(-3, 3, n, 3)
+    pos[1::2] = pos[0::2] + rng.uniform(-0.4, 0.4, n, 3)
+    quat = np.tile([0, 0, 0, 1.0], (2 * n, 1))
+    sid = rng.randint(2 * n, 2).astype(np.uint32)
+    sc = Scene(shapes, pos, quat, sid)
+    pa = np.arange(0, 2 * n, 2, dtype=np.uint32)
+    hit, out, stats = emul.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pa + 1, nblocks=2)
+    assert stats["restarted_in_heap_mode"] > 100 and stats["valid"] == hit.sum()
+    _check(sc, pa, pa + 1)
