@@ -763,14 +763,17 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
         }
 
         // ---------------- S1: the sequential part of one iteration, one lane per pair ----------------
+        // Written as a sequence of stages, each under `go` and each closed before the next begins: a lane that leaves
+        // the iteration (converged, handed back, restarted) clears `go`, and the lanes that go on meet again at the
+        // next stage.  (With early exits out of nested blocks the compiler can only let them meet at the end of S1:
+        // ncu showed the plane load after the pop at 14 of 32 lanes instead of 27.)
         int emit = 0; // horizon edges this lane hands to S2
-        if (active && !fb)
+        bool go = active && !fb;
+        int min_face = -1;
         {
-            do
             {
                 // ---- pop_face (collision.cpp:397-408) ----
-                int min_face = -1;
-                if (heap)
+                if (go && heap)
                 {
                     while (heap_size > 0) // skip obsolete entries: slot free, or re-used by a younger face
                     {
@@ -782,7 +785,7 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                         break;
                     }
                 }
-                else
+                else if (go)
                 {
                     // minimal key: per 16-byte chunk the minimum of its four keys against the running minimum (no
                     // per-key index bookkeeping), then the winning chunk alone is looked at key by key.  Free slots
@@ -931,20 +934,27 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                             {
                                 restart = true; // same lane, same slab, from the simplex again, with the heap
                                 active = false;
+                                go = false;
                                 atomicAdd(P_.restart_count, 1ull);
-                                break;
                             }
                         }
                     }
                 }
-                if (min_face < 0)
+                if (go && min_face < 0)
                 {
                     P_.valid[out_slot] = 0; // heap exhausted → nullopt (collision.cpp:459,502)
                     active = false;
-                    break;
+                    go = false;
                 }
-                const double4 mf = sl.load_plane(min_face);
-                const unsigned long long mt = sl.topo[min_face];
+            }
+            double4 mf = make_double4(0.0, 0.0, 0.0, 0.0);
+            unsigned long long mt = 0;
+            SupportPt sp{}; // minkowski_support (collision.h:41-49): pa = A.support(n), pb = B.support(−n)
+            d3 p{0.0, 0.0, 0.0};
+            if (go)
+            {
+                mf = sl.load_plane(min_face);
+                mt = sl.topo[min_face];
                 if (mf.w > stale_lb) stale_lb = mf.w; // entries closer than the popped face have left the heap
                 const bool finished = iter >= 64;     // best guess after the loop (collision.cpp:500-503)
                 if (!finished) ++iter;
@@ -959,10 +969,13 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                     }
                 }
                 const d3 mn{mf.x, mf.y, mf.z};
-                SupportPt sp{}; // minkowski_support (collision.h:41-49): pa = A.support(n), pb = B.support(−n)
                 if (!finished)
                 {
+#ifdef PK_EC_SUPPORT_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
                     for (int w = 0; w < 2; ++w) // one copy of the support code (instruction cache)
                     {
                         const bool is_b = (w == 1) != swapped; // view w holds body b
@@ -974,15 +987,17 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                             sp.pa = q;
                     }
                 }
-                const d3 p = P(sp);
+                p = P(sp);
                 if (finished || dot(mn, p) - mf.w < 1e-6) // converged (collision.cpp:465-466)
                 {
                     pending = true;
                     pend_face = min_face;
                     active = false;
-                    break;
+                    go = false;
                 }
-
+            }
+            if (go)
+            {
                 // ---- find_silhouette (collision.cpp:315-353): LIFO flood fill, edge order preserved ----
                 bool bad = false;
                 int nh = 0;
@@ -1060,18 +1075,24 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                     }
                 }
                 batch_n = 0;
+                const int nfree = __popcll(fm0) + __popcll(fm1) + __popcll(fm2);
+                const bool full = nfree < nh || nverts >= ES_VERTS || (heap && heap_size + nh > ES_HEAP_MAX);
                 if (nh == 0 && !bad)
                 {
                     iter = 64; // empty horizon → best remaining face (collision.cpp:469,500-503)
-                    break;
+                    go = false;
                 }
-                const int nfree = __popcll(fm0) + __popcll(fm1) + __popcll(fm2);
-                const bool full = nfree < nh || nverts >= ES_VERTS || (heap && heap_size + nh > ES_HEAP_MAX);
-                if (bad || nh < 3 || full)
+                else if (bad || nh < 3 || full)
                 {
                     fb = full ? 3 : 4;
-                    break;
+                    go = false;
                 }
+                else
+                    emit = nh;
+            }
+            if (go)
+            {
+                const int nh = emit;
                 sl.set_vert(nverts, sp, p);
                 shm.pnew[0][t] = p.x;
                 shm.pnew[1][t] = p.y;
@@ -1088,11 +1109,10 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                     ++nfaces;
                     shm.hz[e][t] |= static_cast<uint32_t>(slot) << 24;
                 }
-                emit = nh;
                 EC_STAT(5, nh);
                 EC_STAT(6, 1);
                 EC_STAT(7 + (heap ? 1 : 0), 1);
-            } while (false);
+            }
         }
 
         // ---------------- S2: the new faces of all pairs of the warp, dealt out evenly over its lanes ----------------

@@ -55,6 +55,11 @@ def test_c3_one_million_bodies_world_mode():
         want = np.sort((lo << np.uint64(32)) | hi)
         got = keys[(a == i) | (b == i)]
         assert np.array_equal(np.sort(got), want)
+    # (4b) the WHOLE pair set, key for key: every body has just been re-inserted (num_moved == n), so the reference's
+    # set is every intersecting pair of stored boxes; the oracle finds them with the faithful dynamic_bvh (SAH
+    # insertion of the 1 M fat boxes, one query_aabb per leaf: ≈30 s of CPU)
+    want_all = oracle.query_pairs(stored)
+    assert len(want_all) == len(keys) and np.array_equal(keys, np.sort(want_all))
     # (5) contacts: sorted subset of the pair keys, unit (or reference-degenerate zero) normals
     assert r1.num_contacts == len(con) and len(con) > 1_000_000
     assert np.all(con["key"][1:] > con["key"][:-1])
