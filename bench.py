@@ -175,11 +175,35 @@ STAGE_BYTES_DOC = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per step of the dominant stage from the committed
-# `ncu --set full` capture of this workload at side 100 (profiles/r1b_epa_scan_fullsize.md + r1b_epa_heap_fullsize.md:
-# both instances of epa_scan_kernel at 5 blocks / SM, 8.60 GB + 2.46 GB; 4 blocks / SM moved 7.6 GB, the
-# thread-per-pair epa_kernel it replaced 31 GB); null otherwise
-NCU_TRAFFIC_BYTES = {"epa": 11_065_042_000}
+def source_hash():
+    """Hash of the CUDA sources the library is built from: ties a committed ncu capture to the code it measured."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "physkit_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(stage, workload, n_gpus):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture summarised in profiles/ncu_traffic.json (scripts/ncu_summary.py traffic ...).
+    None when there is no capture of this stage / workload, when the sources have changed since it was taken, or
+    on more than one GPU (the capture is a single-GPU launch)."""
+    if n_gpus != 1:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            recs = json.load(f)
+    except Exception:
+        return None
+    for r in recs:
+        if r.get("stage") == stage and r.get("workload") == workload and r.get("source_hash") == source_hash():
+            return int(r["dram_bytes_read"] + r["dram_bytes_write"])
+    return None
 
 
 def stage_bytes(name, n, pairs, hits):
@@ -362,7 +386,7 @@ def run_ours(args, rank, world, local_rank):
         dev_step_ms = dev_ms / args.steps
         roofline = {
             "bound": "hbm", "kernel": dom[0], "achieved": dom[3], "peak": peak, "unit": "GB/s", "frac": dom[3] / peak,
-            "traffic": NCU_TRAFFIC_BYTES.get(dom[0]) if n == 1_000_000 else None, "peak_source": peak_src,
+            "traffic": ncu_traffic(dom[0], f"c3-side{args.side}", world), "peak_source": peak_src,
             "kernel_ms": dom[1], "kernel_share_of_step": dom[1] / max(dev_step_ms, 1e-9),
             "whole_step": {"alg_bytes": total_bytes, "device_ms": dev_step_ms,
                            "achieved": total_bytes / (dev_step_ms * 1e-3) / 1e9, "frac": total_bytes / (dev_step_ms * 1e-3) / 1e9 / peak},
@@ -453,62 +477,180 @@ def run_c4(args, rank, world, local_rank):
     ctx.close()
 
 
+def c5_worlds(first, count):
+    """Worlds [first, first+count) of BASELINE C5: a C1-style 8x8x8 pile of 8-vertex box hulls + ground per world,
+    jitter seeded per world (0x5EED0005 + k), so a rank's worlds do not depend on how many ranks there are."""
+    from scenes import SplitMix64, scene_c1
+
+    base = scene_c1(side=8, spacing=0.97)
+    per = base.n
+    pos = np.concatenate([base.pos + SplitMix64(0x5EED0005 + first + k).uniform(-0.03, 0.03, per, 3) for k in range(count)])
+    quat = np.tile(base.quat, (count, 1))
+    sid = np.tile(base.shape_id, count)
+    flags = np.tile(base.flags, count)
+    wid = np.repeat(np.arange(count, dtype=np.uint32), per)
+    return base, pos, quat, sid, flags, wid
+
+
+def c5_partition(worlds, world_size):
+    """Block partition of the worlds over the ranks: [(first, count)] per rank, a partition of range(worlds)."""
+    q, r = divmod(worlds, world_size)
+    out, first = [], 0
+    for k in range(world_size):
+        c = q + (1 if k < r else 0)
+        out.append((first, c))
+        first += c
+    return out
+
+
+def cpu_sample_c5(nworlds):
+    """Oracle port (1 thread, as the reference) on the first `nworlds` C5 worlds, one steady-state step each."""
+    import oracle
+
+    base, pos, quat, sid, flags, wid = c5_worlds(0, nworlds)
+    per = base.n
+    tot_pairs, tb, tn = 0, 0.0, 0.0
+    for k in range(nworlds):
+        sl = slice(k * per, (k + 1) * per)
+        w = oracle.World(base.shapes)
+        p0 = pos[sl]
+        p1 = p0.copy()
+        p1[:, 1] -= 0.04
+        zero = np.zeros_like(p0)
+        w.step(p0, quat[sl], zero, base.shape_id, base.flags)
+        w.step(p1, quat[sl], zero, base.shape_id, base.flags)
+        t0 = time.perf_counter()
+        w.step(p0, quat[sl], zero, base.shape_id, base.flags)
+        keys = w.pairs()
+        pa = (keys >> np.uint64(32)).astype(np.uint32)
+        pb = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        t1 = time.perf_counter()
+        oracle.gjk_epa_pairs(base.shapes, p0, quat[sl], base.shape_id, pa, pb, nthreads=1)
+        t2 = time.perf_counter()
+        tot_pairs += len(keys)
+        tb += t1 - t0
+        tn += t2 - t1
+    return dict(worlds=nworlds, pairs=tot_pairs, s_broad=tb, s_narrow=tn, pairs_per_s=tot_pairs / (tb + tn))
+
+
 def run_c5(args, rank, world, local_rank):
-    """BASELINE C5: independent 513-body worlds batched in one context per rank (no collective)."""
+    """BASELINE C5: independent 513-body worlds batched in one context per rank; the worlds are block-partitioned
+    over the ranks (replicas of the pipeline, no collective on the data path)."""
     import torch
 
     import physkit_b200 as pk
-    from scenes import SplitMix64, scene_c1
 
     torch.cuda.set_device(local_rank)
+    dist = None
     if world > 1:
-        import torch.distributed as dist
+        import torch.distributed as dist  # noqa: F811
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    nw = args.worlds // world
-    base = scene_c1(side=8, spacing=0.97)
+    first, nw = c5_partition(args.worlds, world)[rank]
+    base, pos, quat, sid, flags, wid = c5_worlds(first, nw)
     per = base.n
-    pos = np.concatenate([base.pos + SplitMix64(0x5EED0005 + rank * nw + k).uniform(-0.03, 0.03, per, 3) for k in range(nw)])
-    quat = np.tile(base.quat, (nw, 1))
-    sid = np.tile(base.shape_id, nw)
-    flags = np.tile(base.flags, nw)
-    wid = np.repeat(np.arange(nw, dtype=np.uint32), per)
     n = len(pos)
-    ctx = pk.Context(n, int(14 * n), mode=pk.MODE_WORLD, device=local_rank, max_shapes=8, max_contacts=int(7 * n),
+    max_pairs, max_contacts = int(14 * n), int(7 * n)
+    ctx = pk.Context(n, max_pairs, mode=pk.MODE_WORLD, device=local_rank, max_shapes=8, max_contacts=max_contacts,
                      max_hull_vertices=64, num_worlds=nw)
     ctx.add_shapes(base.shapes)
     ctx.resize(n)
-    ctx.upload(pos, quat, None, sid, flags, wid)
+    h_pos = [ctx.pinned_empty((n, 3), np.float64) for _ in range(2)]
+    h_quat = ctx.pinned_empty((n, 4), np.float64)
+    h_disp = ctx.pinned_empty((n, 3), np.float64)
+    h_pos[0][:] = pos
+    h_pos[1][:] = pos
+    h_pos[1][:, 1] -= 0.04
+    h_quat[:] = quat
+    h_disp[:] = 0.0
+    ctx.upload(h_pos[0], h_quat, h_disp, sid, flags, wid)
     ctx.collide_resident()
-    p1 = pos.copy()
-    p1[:, 1] -= 0.04
-    ctx.update_pose(p1)
+    ctx.update_pose(h_pos[1], None, None)
     r = ctx.collide_resident()
+    log(f"[rank {rank}] worlds {first}..{first + nw - 1}  bodies {n}  pairs {r.num_pairs}  contacts {r.num_contacts}")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     for _ in range(args.warmup):
         ctx.collide_resident()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    stage_acc, launches, dev_ms = {}, 0, 0.0
+    sync_all()
+    sampler.start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = ctx.collide_resident()
-    torch.cuda.synchronize()
+        st, ln = ctx.stage_times()
+        for k, v in st.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        launches += ln
+        dev_ms += r.ms_total
+    sync_all()
     ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    pairs = int(r.num_pairs)
+    clocks = sampler.stop()
+    pairs, hits, contacts = int(r.num_pairs), int(r.gjk_hits), int(r.num_contacts)
+    # end to end: every rank uploads the poses of ITS worlds from pinned host memory and reads its pair keys and
+    # contact records back
+    for s in range(3):
+        ctx.update_pose(h_pos[s % 2], None, h_disp)
+        ctx.collide()
+    sync_all()
+    e0 = time.perf_counter()
+    for s in range(args.steps):
+        ctx.update_pose(h_pos[s % 2], h_quat, h_disp)
+        re_ = ctx.collide()
+    sync_all()
+    e2e_ms = 1e3 * (time.perf_counter() - e0) / args.steps
+    h2d = n * (3 + 4 + 3) * 8
+    d2h = int(re_.num_pairs) * 8 + int(re_.num_contacts) * 88
+    tot = [float(pairs), float(contacts), float(h2d), float(d2h)]
+    mx = [ms, e2e_ms]
     if world > 1:
-        t = torch.tensor([float(pairs), ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        tp = t.clone()
-        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pairs, ms = int(tp[0].item()), float(t[1].item())
-    st, launches = ctx.stage_times()
+        t = torch.tensor(tot, dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot = [float(x) for x in t.tolist()]
+        m = torch.tensor(mx, dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        mx = [float(x) for x in m.tolist()]
     if rank == 0:
-        line = {"metric": "colliding-pair tests/sec (batched independent worlds)", "value": pairs / (ms * 1e-3), "unit": UNIT,
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        peak, peak_src = measured_peak()
+        stages = {k: v / args.steps for k, v in stage_acc.items()}
+        table = sorted(((k, v, stage_bytes(k, n, pairs, hits)) for k, v in stages.items() if k != "fetch_d2h" and v > 0), key=lambda x: -x[1])
+        dom = table[0]
+        total_bytes = sum(t[2] for t in table)
+        dev_step = dev_ms / args.steps
+        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": dom[2] / (dom[1] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": dom[2] / (dom[1] * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(dom[0], f"c5-{nw}worlds", world),
+                    "peak_source": peak_src, "kernel_ms": dom[1], "kernel_share_of_step": dom[1] / max(dev_step, 1e-9),
+                    "whole_step": {"alg_bytes": total_bytes, "device_ms": dev_step, "achieved": total_bytes / (dev_step * 1e-3) / 1e9,
+                                   "frac": total_bytes / (dev_step * 1e-3) / 1e9 / peak},
+                    "stages_ms": {k: round(v, 4) for k, v in stages.items()},
+                    "note": "rank 0's launches; algorithmic bytes as for C3 (SURVEY 8d) with this rank's bodies / pairs / hits"}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            import oracle
+
+            oracle.build()
+            c = cpu_sample_c5(64)
+            cpu = {"value": c["pairs_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": (f"the first {c['worlds']} C5 worlds ({c['pairs']} pairs), one steady-state world step each of the oracle port: "
+                              f"dynamic_bvh broadphase {1e3 * c['s_broad']:.1f} ms + gjk_epa {1e3 * c['s_narrow']:.1f} ms, single thread like the reference")}
+        line = {"metric": "colliding-pair tests/sec (batched independent worlds)", "value": tot[0] / (mx[0] * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mx[0], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C5: {nw * world} worlds x {per} bodies (8-vertex box hulls + ground), worlds split across ranks",
-                           "pairs_per_step": pairs, "worlds_per_s": nw * world / (ms * 1e-3)},
-                "gpu_launches": launches * args.steps, "stages_ms": {k: round(v, 4) for k, v in st.items() if v > 0}}
+                "config": {"workload": f"C5: {args.worlds} worlds x {per} bodies (8-vertex box hulls + ground), worlds block-partitioned over the ranks, no collective",
+                           "worlds_per_rank": [c for _, c in c5_partition(args.worlds, world)], "pairs_per_step": int(tot[0]),
+                           "contacts_per_step": int(tot[1]), "worlds_per_s": args.worlds / (mx[0] * 1e-3),
+                           "l2": "per-step working set of a rank exceeds L2 at <= 4 ranks (no explicit flush); 512 worlds per rank: 0.3 GB",
+                           "timing": "wall clock around K synchronous steps bracketed by barrier+synchronize, max over ranks"},
+                "device_ms_per_step": dev_step,
+                "e2e": {"value": tot[0] / (mx[1] * 1e-3), "unit": UNIT, "ms_per_step": mx[1], "h2d_bytes_per_step": int(tot[2]),
+                        "d2h_bytes_per_step": int(tot[3])},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -42,7 +42,8 @@ typedef enum pk_status
     PK_E_NO_DEVICE = -2,     /* no usable CUDA device (never falls back to the CPU) */
     PK_E_CUDA = -3,          /* CUDA runtime error; pk_last_error() has the text */
     PK_E_OOM = -4,           /* device or pinned allocation failed */
-    PK_E_PAIR_OVERFLOW = -5, /* candidate pairs exceed pk_config.max_pairs; result.pairs_required set */
+    PK_E_PAIR_OVERFLOW = -5, /* candidate pairs exceed pk_config.max_pairs (result.pairs_required set) or GJK hits exceed
+                              * max_contacts: pk_reserve_pairs, then repeat the step */
     PK_E_EPA_OVERFLOW = -6,  /* an EPA polytope exceeded the per-pair scratch (result.epa_overflow) */
     PK_E_STATE = -7          /* call order violated (e.g. results requested before pk_collide) */
 } pk_status;
@@ -182,7 +183,7 @@ typedef struct pk_stage_times
     float ms[PK_NUM_STAGES];
     const char *name[PK_NUM_STAGES];
     uint32_t launches; /* kernels launched by the last pk_collide */
-    uint32_t epa_fallback; /* GJK hits the group EPA kernel handed to the thread-per-pair EPA kernel */
+    uint32_t epa_fallback; /* GJK hits epa_coop_kernel handed to epa_kernel (padded simplices, improper horizons) */
 } pk_stage_times;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -201,6 +202,13 @@ int pk_shape_aabb(pk_ctx *ctx, const double min[3], const double max[3], uint32_
 /* Bulk variant: n boxes / spheres in one H2D copy. kind: 1 = box (par = half xyz), 2 = sphere (par[0] = r). */
 int pk_shapes_bulk(pk_ctx *ctx, const int32_t *kind, const double *par3, uint32_t n, uint32_t *first_id);
 
+/* Grow the capacities of a live context (never shrinks; 0 for max_contacts = max_pairs).  After PK_E_PAIR_OVERFLOW:
+ * pk_reserve_pairs(ctx, result.pairs_required · margin, …) and call pk_collide* again with the same poses — the
+ * failed attempt does not advance the context's epoch, and the fat boxes it already updated are left as they are
+ * by the second pass, so the repeated step yields the pair set the first would have (only num_moved differs).
+ * Results of an earlier step that were not fetched are gone (PK_E_STATE). */
+int pk_reserve_pairs(pk_ctx *ctx, uint64_t max_pairs, uint64_t max_contacts);
+
 /* ---- bodies ---------------------------------------------------------------------------------
  * flags bit0 = static (never updated, never queries: src/world.cpp:24), bit1 = alive.
  * A body whose alive bit rises is create_rigid()'d (exact box, not marked moved: core/world.h:202-208,
@@ -211,7 +219,12 @@ int pk_bodies_resize(pk_ctx *ctx, uint32_t n);
 int pk_bodies_upload(pk_ctx *ctx, const double *pos_xyz, const double *quat_xyzw, const double *disp_xyz,
                      const uint32_t *shape_id, const uint8_t *flags, const uint32_t *world_id,
                      uint32_t first, uint32_t count);
-/* Pose-only refresh (the per-step H2D of a running world). Any pointer may be NULL = unchanged. */
+/* Pose-only refresh (the per-step H2D of a running world). Any pointer may be NULL = unchanged.
+ * Both calls only ENQUEUE the copies on the context's stream.  Pageable source buffers may be reused when the call
+ * returns; page-locked ones (pk_host_alloc) are read by the DMA engine later: leave them untouched until the next
+ * call that synchronises the context (pk_collide*, pk_fetch_results, pk_gjk_epa_batch, pk_memcpy_*).
+ * With pk_dynamics_enable, a new orientation also refreshes the body's world-frame inertia tensors, as
+ * particle::orientation(q) does (core/particle.h:40-44). */
 int pk_bodies_update_pose(pk_ctx *ctx, const double *pos_xyz, const double *quat_xyzw, const double *disp_xyz,
                           uint32_t first, uint32_t count);
 
@@ -339,7 +352,10 @@ int pk_selftest_division(pk_ctx *ctx, uint64_t seed, uint64_t samples, uint64_t 
  * out[k].key = make_pair_key as given (a<<32|b, NOT min/max: argument order is the caller's). */
 int pk_gjk_epa_batch(pk_ctx *ctx, const uint32_t *pair_a, const uint32_t *pair_b, uint64_t n,
                      pk_contact *out, uint8_t *hit);
-/* Same with the pair list and outputs resident in HBM (device pointers); returns device ms. */
+/* Same with the pair list and outputs resident in HBM (device pointers); returns device ms.
+ * Both batch calls share the narrowphase buffers with the step: device-side results of the last pk_collide* that were
+ * not fetched can no longer be (pk_fetch_results, pk_contacts_device, pk_manifolds_update, pk_contact_points return
+ * PK_E_STATE); host copies already fetched, the pair keys and the tree (pk_raycast) stay valid. */
 int pk_gjk_epa_batch_device(pk_ctx *ctx, const uint32_t *d_pair_a, const uint32_t *d_pair_b, uint64_t n,
                             pk_contact *d_out, uint8_t *d_hit, float *ms);
 

@@ -6,6 +6,8 @@ no CPU implementation of anything and raises if the library or a CUDA device is 
 """
 from .api import (  # noqa: F401
     MODE_QUERY,
+    PK_E_EPA_OVERFLOW,
+    PK_E_PAIR_OVERFLOW,
     MODE_WORLD,
     RAY_ALL,
     RAY_CLOSEST,

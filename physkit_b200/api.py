@@ -94,7 +94,7 @@ EXPORTS = [
     "pk_abi_version", "pk_selftest_division", "pk_contact_points", "pk_manifolds_enable", "pk_manifolds_update",
     "pk_manifolds", "pk_manifolds_device", "pk_manifold_events", "pk_manifolds_set_impulses", "pk_create", "pk_destroy", "pk_strerror", "pk_last_error",
     "pk_shape_box", "pk_shape_sphere", "pk_shape_hull", "pk_shape_aabb", "pk_shapes_bulk",
-    "pk_bodies_resize", "pk_bodies_upload", "pk_bodies_update_pose",
+    "pk_bodies_resize", "pk_bodies_upload", "pk_bodies_update_pose", "pk_reserve_pairs",
     "pk_collide_resident", "pk_fetch_results", "pk_collide", "pk_pairs", "pk_contacts",
     "pk_pairs_device", "pk_contacts_device", "pk_stored_bounds", "pk_stage_times_get", "pk_stream",
     "pk_gjk_epa_batch", "pk_gjk_epa_batch_device", "pk_raycast", "pk_raycast_device_ms",
@@ -164,6 +164,7 @@ def load_library():
     L.pk_bodies_resize.argtypes = [vp, u32]
     L.pk_bodies_upload.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, u32]
     L.pk_bodies_update_pose.argtypes = [vp, vp, vp, vp, u32, u32]
+    L.pk_reserve_pairs.argtypes = [vp, C.c_uint64, C.c_uint64]
     L.pk_collide_resident.argtypes = [vp, vp]
     L.pk_fetch_results.argtypes = [vp]
     L.pk_collide.argtypes = [vp, vp]
@@ -331,6 +332,10 @@ class Context:
         allow = (PK_E_EPA_OVERFLOW,) if allow_epa_overflow else ()
         self._check(self.L.pk_collide(self.h, C.byref(self.result)), allow)
         return self.result
+
+    def reserve_pairs(self, max_pairs, max_contacts=0):
+        """Grow the pair / contact capacities (after PK_E_PAIR_OVERFLOW: reserve, then repeat the step)."""
+        self._check(self.L.pk_reserve_pairs(self.h, int(max_pairs), int(max_contacts)))
 
     def pairs(self):
         ptr, n = C.c_void_p(), C.c_uint64()

@@ -484,6 +484,91 @@ const char *pk_strerror(int status)
 
 const char *pk_last_error(pk_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 
+// Everything sized by pk_config.max_pairs / max_contacts (pk_create, pk_reserve_pairs).
+static int alloc_pair_buffers(pk_ctx *ctx)
+{
+    const size_t nb = ctx->cfg.max_bodies;
+    const size_t np = ctx->cfg.max_pairs;
+    const size_t nc = ctx->max_contacts;
+    int s;
+#define A(ptr, count)                                   \
+    if ((s = dev_alloc(ctx, &(ptr), (count))) != PK_OK) \
+    return s
+    ctx->tile_hist_entries = static_cast<size_t>(div_up(std::max(nb, np), SORT_TILE)) * 256;
+    A(ctx->d_tile_hist, ctx->tile_hist_entries);
+    A(ctx->d_digit_total, 256);
+    A(ctx->d_pkeys[0], np);
+    A(ctx->d_pkeys[1], np);
+    A(ctx->d_hit, np + 16);
+    A(ctx->d_out_index, np);
+    A(ctx->d_scan_tiles, div_up(np, SCAN_TILE) + 1);
+    A(ctx->d_simplices, nc);
+    A(ctx->d_contacts[0], nc);
+    A(ctx->d_contacts[1], nc);
+    A(ctx->d_valid, nc + 16);
+    A(ctx->d_valid_index, nc);
+    A(ctx->d_epa_order, nc);
+    A(ctx->d_gjk_work, 4 * np); // one survivor list per shape-kind class
+    // persistent EPA grid: enough resident threads to fill the machine, never more than the work
+    {
+        int gjk_per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm, gjk_kernel, PK_GJK_THREADS, 0) != cudaSuccess || gjk_per_sm < 1)
+            gjk_per_sm = 2;
+        ctx->gjk_blocks = static_cast<uint32_t>(ctx->sm_count * gjk_per_sm);
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_kernel, EPA_THREADS, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+#ifdef PK_EPA_BLOCKS_PER_SM
+        per_sm = std::min(per_sm, PK_EPA_BLOCKS_PER_SM);
+#endif
+        uint64_t want_threads = static_cast<uint64_t>(ctx->sm_count) * per_sm * EPA_THREADS;
+        uint64_t need_threads = ((nc + EPA_THREADS - 1) / EPA_THREADS) * EPA_THREADS;
+        uint64_t threads = std::min(want_threads, std::max<uint64_t>(need_threads, EPA_THREADS));
+        ctx->epa_blocks = static_cast<uint32_t>(threads / EPA_THREADS);
+        A(ctx->d_slabs, threads * EPA_SLAB_BYTES);
+        // epa_coop_kernel: 43 KB of shared memory per 64-thread block, as many blocks per SM as fit
+        cudaFuncSetAttribute(epa_coop_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_coop_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int es_per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_coop_kernel<false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
+            es_per_sm = 1;
+#ifdef PK_ES_BLOCKS_PER_SM
+        es_per_sm = std::min(es_per_sm, PK_ES_BLOCKS_PER_SM);
+#endif
+#ifdef PK_ES_FORCE_BLOCKS
+        es_per_sm = PK_ES_FORCE_BLOCKS;
+#endif
+        if (getenv("PK_DEBUG")) fprintf(stderr, "[pk] epa_coop_kernel: %d blocks per SM\n", es_per_sm);
+        const uint64_t es_need = (nc + ES_THREADS - 1) / ES_THREADS;
+        ctx->epa_scan_blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(ctx->sm_count) * es_per_sm, es_need)));
+        A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_scan_blocks) * ES_THREADS * es_slab_bytes());
+        A(ctx->d_epa_fallback2, nc);
+        A(ctx->d_epa_init, nc);
+    }
+#undef A
+    cudaMemsetAsync(ctx->d_hit, 0, np + 16, ctx->stream);
+    return PK_OK;
+}
+
+static void free_pair_buffers(pk_ctx *ctx)
+{
+    for (void **q : {reinterpret_cast<void **>(&ctx->d_tile_hist), reinterpret_cast<void **>(&ctx->d_digit_total),
+                     reinterpret_cast<void **>(&ctx->d_pkeys[0]), reinterpret_cast<void **>(&ctx->d_pkeys[1]),
+                     reinterpret_cast<void **>(&ctx->d_hit), reinterpret_cast<void **>(&ctx->d_out_index),
+                     reinterpret_cast<void **>(&ctx->d_scan_tiles), reinterpret_cast<void **>(&ctx->d_simplices),
+                     reinterpret_cast<void **>(&ctx->d_contacts[0]), reinterpret_cast<void **>(&ctx->d_contacts[1]),
+                     reinterpret_cast<void **>(&ctx->d_valid), reinterpret_cast<void **>(&ctx->d_valid_index),
+                     reinterpret_cast<void **>(&ctx->d_epa_order), reinterpret_cast<void **>(&ctx->d_gjk_work),
+                     reinterpret_cast<void **>(&ctx->d_slabs), reinterpret_cast<void **>(&ctx->d_epa_spill),
+                     reinterpret_cast<void **>(&ctx->d_epa_fallback2), reinterpret_cast<void **>(&ctx->d_epa_init)})
+    {
+        if (*q) cudaFree(*q);
+        *q = nullptr;
+    }
+    ctx->d_pairs_sorted = nullptr;
+    ctx->d_contacts_final = nullptr;
+}
+
 int pk_destroy(pk_ctx *ctx)
 {
     if (!ctx) return PK_E_INVALID;
@@ -585,7 +670,6 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
 
     const size_t nb = cfg->max_bodies;
     const size_t np = cfg->max_pairs;
-    const size_t nc = ctx->max_contacts;
     int s;
 #define A(ptr, count)                                   \
     if ((s = dev_alloc(ctx, &(ptr), (count))) != PK_OK) \
@@ -609,63 +693,13 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     A(ctx->d_bkeys[1], nb);
     A(ctx->d_bvals[0], nb);
     A(ctx->d_bvals[1], nb);
-    ctx->tile_hist_entries = static_cast<size_t>(div_up(std::max(nb, np), SORT_TILE)) * 256;
-    A(ctx->d_tile_hist, ctx->tile_hist_entries);
-    A(ctx->d_digit_total, 256);
     A(ctx->d_leaves, nb);
     A(ctx->d_nodes, 2 * nb);
     A(ctx->d_right, nb);
     A(ctx->d_range_last, nb);
     A(ctx->d_root, 1);
     A(ctx->d_merge_flag, nb);
-    A(ctx->d_pkeys[0], np);
-    A(ctx->d_pkeys[1], np);
-    A(ctx->d_hit, np + 16);
-    A(ctx->d_out_index, np);
-    A(ctx->d_scan_tiles, div_up(np, SCAN_TILE) + 1);
-    A(ctx->d_simplices, nc);
-    A(ctx->d_contacts[0], nc);
-    A(ctx->d_contacts[1], nc);
-    A(ctx->d_valid, nc + 16);
-    A(ctx->d_valid_index, nc);
-    A(ctx->d_epa_order, nc);
-    A(ctx->d_gjk_work, 4 * np); // one survivor list per shape-kind class
-    // persistent EPA grid: enough resident threads to fill the machine, never more than the work
-    {
-        int gjk_per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm, gjk_kernel, PK_GJK_THREADS, 0) != cudaSuccess || gjk_per_sm < 1)
-            gjk_per_sm = 2;
-        ctx->gjk_blocks = static_cast<uint32_t>(ctx->sm_count * gjk_per_sm);
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_kernel, EPA_THREADS, 0) != cudaSuccess || per_sm < 1)
-            per_sm = 4;
-#ifdef PK_EPA_BLOCKS_PER_SM
-        per_sm = std::min(per_sm, PK_EPA_BLOCKS_PER_SM);
-#endif
-        uint64_t want_threads = static_cast<uint64_t>(ctx->sm_count) * per_sm * EPA_THREADS;
-        uint64_t need_threads = ((nc + EPA_THREADS - 1) / EPA_THREADS) * EPA_THREADS;
-        uint64_t threads = std::min(want_threads, std::max<uint64_t>(need_threads, EPA_THREADS));
-        ctx->epa_blocks = static_cast<uint32_t>(threads / EPA_THREADS);
-        A(ctx->d_slabs, threads * EPA_SLAB_BYTES);
-        // epa_coop_kernel: 43 KB of shared memory per 64-thread block, as many blocks per SM as fit
-        cudaFuncSetAttribute(epa_coop_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(epa_coop_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        int es_per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_coop_kernel<false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
-            es_per_sm = 1;
-#ifdef PK_ES_BLOCKS_PER_SM
-        es_per_sm = std::min(es_per_sm, PK_ES_BLOCKS_PER_SM);
-#endif
-#ifdef PK_ES_FORCE_BLOCKS
-        es_per_sm = PK_ES_FORCE_BLOCKS;
-#endif
-        if (getenv("PK_DEBUG")) fprintf(stderr, "[pk] epa_coop_kernel: %d blocks per SM\n", es_per_sm);
-        const uint64_t es_need = (nc + ES_THREADS - 1) / ES_THREADS;
-        ctx->epa_scan_blocks = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(ctx->sm_count) * es_per_sm, es_need)));
-        A(ctx->d_epa_spill, static_cast<size_t>(ctx->epa_scan_blocks) * ES_THREADS * es_slab_bytes());
-        A(ctx->d_epa_fallback2, nc);
-        A(ctx->d_epa_init, nc);
-    }
+    if ((s = alloc_pair_buffers(ctx)) != PK_OK) return fail(s);
 #undef A
     if (cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_counters), C_COUNT * sizeof(unsigned long long),
                       cudaHostAllocDefault) != cudaSuccess)
@@ -678,6 +712,35 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(PK_E_CUDA);
     ctx->h_flags.assign(nb, 0);
     *out = ctx;
+    return PK_OK;
+}
+
+int pk_reserve_pairs(pk_ctx *ctx, uint64_t max_pairs, uint64_t max_contacts)
+{
+    if (!ctx || max_pairs == 0) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    if (max_contacts == 0) max_contacts = max_pairs;
+    if (max_pairs <= ctx->cfg.max_pairs && max_contacts <= ctx->max_contacts) return PK_OK; // never shrinks
+    max_pairs = std::max<uint64_t>(max_pairs, ctx->cfg.max_pairs);
+    max_contacts = std::max<uint64_t>(max_contacts, ctx->max_contacts);
+    if (ctx->pairs_in_flight) cudaStreamSynchronize(ctx->copy_stream);
+    ctx->pairs_in_flight = false;
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_pair_buffers(ctx);
+    ctx->cfg.max_pairs = max_pairs;
+    ctx->max_contacts = max_contacts;
+    ctx->cfg.max_contacts = max_contacts;
+    ctx->have_results = false; // the last step's device results lived in the old buffers
+    ctx->device_results = false;
+    ctx->fetched = false;
+    PK_TRY(alloc_pair_buffers(ctx));
+    if (ctx->d_man_consumed)
+    {
+        cudaFree(ctx->d_man_consumed);
+        ctx->d_man_consumed = nullptr;
+        PK_TRY(dev_alloc(ctx, &ctx->d_man_consumed, ctx->max_contacts + 16));
+    }
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
 
@@ -826,6 +889,7 @@ int pk_bodies_upload(pk_ctx *ctx, const double *pos, const double *quat, const d
     }
     std::memcpy(ctx->h_flags.data() + first, flags, count);
     ctx->alive_dirty = true;
+    if (ctx->dyn_enabled) dynamics_derive_kernel<<<div_up(count, 256), 256, 0, s>>>(ctx->d_quat, ctx->dyn, first, count);
     return PK_OK;
 }
 
@@ -843,6 +907,8 @@ int pk_bodies_update_pose(pk_ctx *ctx, const double *pos, const double *quat, co
         PK_CUDA(cudaMemcpyAsync(ctx->d_quat + 4ull * first, quat, 4ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
     if (disp)
         PK_CUDA(cudaMemcpyAsync(ctx->d_disp + 3ull * first, disp, 3ull * count * sizeof(double), cudaMemcpyHostToDevice, s));
+    // particle::orientation(q) refreshes the world-frame inertia tensors (core/particle.h:40-44, 140-146)
+    if (quat && ctx->dyn_enabled) dynamics_derive_kernel<<<div_up(count, 256), 256, 0, s>>>(ctx->d_quat, ctx->dyn, first, count);
     return PK_OK;
 }
 
@@ -931,8 +997,11 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
                 out->num_moved = ctx->h_counters[C_MOVED];
                 out->step_index = static_cast<uint32_t>(ctx->epoch);
             }
-            ctx->last_error = "candidate pairs exceed pk_config.max_pairs";
-            ctx->epoch += 1; // the fat-box state has advanced; the step cannot be replayed
+            // The step can be repeated after pk_reserve_pairs: the pair set is a function of the per-body state
+            // (stored box, last_move, create), which this attempt has already brought up to date for this epoch; a
+            // second pass over the same poses in the same epoch leaves it as it is (every true box lies inside its
+            // stored box now), so only num_moved of the repeated step differs (0).
+            ctx->last_error = "candidate pairs exceed pk_config.max_pairs (pk_reserve_pairs, then repeat the step)";
             return PK_E_PAIR_OVERFLOW;
         }
         if (npairs)
@@ -1039,7 +1108,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         out->ms_total = bp + np_ms;
         out->step_index = static_cast<uint32_t>(ctx->epoch);
     }
-    ctx->epoch += 1;
+    if (status != PK_E_PAIR_OVERFLOW) ctx->epoch += 1; // an overflowed step is repeated after pk_reserve_pairs
     if (status == PK_OK && over)
     {
         ctx->last_error = "EPA polytope exceeded the per-pair scratch for some pairs";
@@ -1674,6 +1743,14 @@ int pk_raycast_device_ms(pk_ctx *ctx, float *ms)
 // ------------------------------------------------------------------------------------ manifolds
 int pk_manifolds_enable(pk_ctx *ctx, uint64_t capacity)
 {
+    // A manifold lives as long as its pair stays in the pair set (collision_phases.h:309-318), but a sharded context
+    // only sees the pairs whose lower leaf falls into its slice of the Morton order, and bodies move between slices:
+    // manifolds need the gathered pair and contact set of the whole world.
+    if (ctx && ctx->cfg.shard_count > 1)
+    {
+        ctx->last_error = "manifolds need an unsharded context (pk_config.shard_count == 1)";
+        return PK_E_STATE;
+    }
     if (!ctx || capacity == 0) return PK_E_INVALID;
     if (ctx->man_cap) return PK_E_STATE;
     if (capacity > std::max<uint64_t>(ctx->cfg.max_pairs, ctx->cfg.max_bodies))

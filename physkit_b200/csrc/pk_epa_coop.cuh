@@ -1009,7 +1009,9 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                     for (;;)
                     {
                         double4 nf[3];
+#ifdef PK_EC_FLOOD_PREFETCH
                         unsigned long long nt[3];
+#endif
                         bool live[3];
 #pragma unroll
                         for (int i = 0; i < 3; ++i)

@@ -3,6 +3,7 @@
 
   python scripts/ncu_summary.py launches <launches.csv> <out.md>
   python scripts/ncu_summary.py kernel <report.ncu-rep> <kernel-substr> <out.md> [lib.so]
+  python scripts/ncu_summary.py traffic <report.ncu-rep> <kernel-substr> <stage> <workload> [profiles/ncu_traffic.json]
 
 `kernel` needs ncu, cuobjdump and nvdisasm (all in the CUDA toolkit; no GPU).  Per-line stall
 attribution joins ncu's SASS-level source page with nvdisasm's line table of the library."""
@@ -128,8 +129,41 @@ def kernel(rep, kern, out, lib):
     print("".join(lines))
 
 
+def traffic(rep, kern, stage, workload, out):
+    """Adds / replaces the (stage, workload) record of profiles/ncu_traffic.json: DRAM bytes of one launch of `kern`
+    in an `ncu --set full` report, with the hash of the sources it was built from (bench.py only trusts a record
+    whose hash matches the current sources)."""
+    import json
+
+    sys.path.insert(0, ROOT)
+    from bench import source_hash
+
+    base = kern.split("<")[0]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "-k", "regex:" + base], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rr[0], rr[1]
+    row = next(r for r in rr[2:] if kern in re.sub(r"\((?:bool|int)\)", "", r[4]).replace("pk::", ""))
+
+    def gb(name):
+        i = hdr.index(name)
+        v = float(row[i].replace(",", ""))
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
+
+    rec = {"stage": stage, "workload": workload, "kernel": kern, "report": os.path.basename(rep), "source_hash": source_hash(),
+           "dram_bytes_read": gb("dram__bytes_read.sum"), "dram_bytes_write": gb("dram__bytes_write.sum"),
+           "duration_ms": float(row[hdr.index("gpu__time_duration.sum")].replace(",", "")) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")].replace("second", "s").replace("msecond", "ms").replace("usecond", "us").replace("nsecond", "ns"), 1.0)}
+    recs = []
+    if os.path.exists(out):
+        recs = [r for r in json.load(open(out)) if not (r["stage"] == stage and r["workload"] == workload)]
+    recs.append(rec)
+    json.dump(recs, open(out, "w"), indent=1)
+    print(json.dumps(rec))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5], sys.argv[6] if len(sys.argv) > 6 else os.path.join(ROOT, "profiles", "ncu_traffic.json"))
     else:
         kernel(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else os.path.join(ROOT, "physkit_b200", "libpk_collide.so"))

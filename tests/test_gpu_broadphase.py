@@ -307,3 +307,45 @@ def test_pk_create_multi_shards_one_world_over_contexts():
     assert tot.num_pairs > 10_000 and min(len(k) for k in keys) > 0
     one.close()
     m.close()
+
+
+def test_pair_overflow_is_recoverable():
+    """PK_E_PAIR_OVERFLOW (pairs, then GJK hits): pk_reserve_pairs and the SAME step again give what a context with enough
+    room gives — pair set, contacts, stored boxes — and later steps stay in step with the oracle (the failed attempts
+    did not advance the epoch).  Also the ADVICE r1 case: more GJK hits than contact records must not write past them."""
+    from gpu_util import make_context
+
+    sc = scene_c3(side=12)
+    big = make_context(sc, max_pairs=200_000, mode=pk.MODE_WORLD)
+    cap_pairs, cap_contacts = 3_000, 100
+    small = make_context(sc, max_pairs=cap_pairs, mode=pk.MODE_WORLD, max_contacts=cap_contacts)
+    w = oracle.World(sc.shapes)
+    pos = sc.pos.copy()
+    total_tries = 0
+    for step in range(4):
+        disp = np.full_like(pos, 0.01 * step)
+        w.step(pos, sc.quat, disp, sc.shape_id, sc.flags)
+        big.upload(pos, sc.quat, disp, sc.shape_id, sc.flags)
+        small.upload(pos, sc.quat, disp, sc.shape_id, sc.flags)
+        big.collide()
+        for attempt in range(4):
+            try:
+                small.collide()
+                break
+            except pk.PkError as e:
+                assert e.status == pk.PK_E_PAIR_OVERFLOW and attempt < 3
+                total_tries += 1
+                need = int(small.result.pairs_required)
+                if need:  # candidate pairs did not fit
+                    cap_pairs = need + 16
+                else:  # GJK hits did not fit the contact records
+                    cap_contacts = int(small.result.gjk_hits) + 16
+                small.reserve_pairs(cap_pairs, cap_contacts)
+        assert np.array_equal(small.pairs(), w.pairs())
+        assert np.array_equal(small.pairs(), big.pairs())
+        assert np.array_equal(small.contacts().view(np.uint8), big.contacts().view(np.uint8))
+        assert np.array_equal(small.stored_bounds(0, sc.n).view(np.uint64), big.stored_bounds(0, sc.n).view(np.uint64))
+        pos = pos + 0.03
+    assert total_tries >= 2  # the pairs overflowed, then the contacts
+    big.close()
+    small.close()
