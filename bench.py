@@ -256,19 +256,24 @@ def run_ours(args, rank, world, local_rank):
     log(f"[rank {rank}] bodies {n}  pairs {r1.num_pairs}  contacts {r1.num_contacts}  moved {r1.num_moved}  "
         f"device ms {r1.ms_total:.3f}")
 
-    send = None
+    # one world over several ranks: the exchange runs inside the library (pk_comm_*: NCCL all-gathers on the context's
+    # stream, straight from the contact buffer); torch.distributed only carries the communicator id and the timings
+    first, count = 0, n
     if world > 1:
-        from physkit_b200.exchange import allgather_records
+        cid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        if rank == 0:
+            cid.copy_(torch.from_numpy(pk.Context.comm_get_id()))
+        dist.broadcast(cid, 0)
+        ctx.comm_init(cid.cpu().numpy(), rank, world)
+        first, count = ctx.comm_pose_slice()
 
-        send = torch.empty(max_contacts * 88, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    gather_ms = []
 
     def exchange():
         if world == 1:
             return None
-        ptr, cnt = ctx.contacts_device()
-        if cnt:
-            ctx.d2d(send.data_ptr(), ptr, cnt * 88)
-        g, counts = allgather_records(send, cnt, concat=False)
+        g = ctx.comm_allgather_contacts()
+        gather_ms.append(g[3])
         return g
 
     def sync_all():
@@ -303,20 +308,31 @@ def run_ours(args, rank, world, local_rank):
     pairs, hits, contacts = int(res.num_pairs), int(res.gjk_hits), int(res.num_contacts)
 
     # ---- end-to-end timing: host poses in, pair keys + contacts out ------------------------------
+    # every rank uploads the poses of ITS slice of the bodies (1/N of the per-step H2D) and gets the rest over NVLink
+    sl = slice(first, first + count)
+
+    def e2e_step(s):
+        ctx.update_pose(h_pos[s % 2][sl], h_quat[sl], h_disp[sl], first=first, count=count)
+        if world > 1:
+            ctx.comm_allgather_poses()
+        r = ctx.collide()
+        exchange()
+        return r
+
     for s in range(min(args.warmup, 3)):
-        ctx.update_pose(h_pos[s % 2], None, h_disp)
-        ctx.collide()
+        e2e_step(s)
     sync_all()
+    gather_ms.clear()
     e0 = time.perf_counter()
     for s in range(args.steps):
-        ctx.update_pose(h_pos[s % 2], h_quat, h_disp)
-        res_e = ctx.collide()
-        exchange()
+        res_e = e2e_step(s)
     sync_all()
     e1 = time.perf_counter()
     e2e_ms = 1e3 * (e1 - e0) / args.steps
     e2e_stages = {k: round(v, 4) for k, v in ctx.stage_times()[0].items()}  # device times of the last end-to-end step
-    h2d = n * (3 + 4 + 3) * 8
+    if gather_ms:
+        e2e_stages["contact_allgather"] = round(float(np.mean(gather_ms)), 4)
+    h2d = count * (3 + 4 + 3) * 8
     d2h = int(res_e.num_pairs) * 8 + int(res_e.num_contacts) * 88
 
     # ---- optional: the rows downstream of the stage, not part of the headline -----------------
@@ -361,9 +377,9 @@ def run_ours(args, rank, world, local_rank):
     # ---- reduce over ranks (max time, sum pairs) ---------------------------------------------------
     tot_pairs, tot_contacts, max_wall, max_e2e = pairs, contacts, wall_ms, e2e_ms
     if world > 1:
-        t = torch.tensor([pairs, contacts], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor([pairs, contacts, h2d, d2h], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        tot_pairs, tot_contacts = int(t[0].item()), int(t[1].item())
+        tot_pairs, tot_contacts, h2d, d2h = (int(x) for x in t.tolist())
         m = torch.tensor([wall_ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
         max_wall, max_e2e = float(m[0].item()), float(m[1].item())
@@ -410,7 +426,8 @@ def run_ours(args, rank, world, local_rank):
                        "bodies": n, "pairs_per_step": tot_pairs, "contacts_per_step": tot_contacts,
                        "epa_fallback_pairs": getattr(ctx, "epa_fallback", None),
                        **({"downstream_rows": manifold_info} if manifold_info else {}),
-                       "sharding": "pairs by sorted-leaf range, tree rebuilt per rank, one all-gather of contacts" if world > 1 else "none",
+                       "sharding": ("pairs by sorted-leaf range, tree rebuilt per rank; pk_comm_*: each rank uploads 1/N of the poses + NCCL all-gather, "
+                                    "one NCCL all-gather of contact records per step, both inside the library") if world > 1 else "none",
                        "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush",
                        "timing": "wall clock around K synchronous steps bracketed by barrier+synchronize, max over ranks; "
                                  "per-kernel times from CUDA events on the library's stream",

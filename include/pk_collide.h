@@ -347,6 +347,38 @@ int pk_stream(pk_ctx *ctx, void **stream);
  * ones and ones constructed next to exact quotients — and reports how many quotients differ from `/`. */
 int pk_selftest_division(pk_ctx *ctx, uint64_t seed, uint64_t samples, uint64_t *mismatches);
 
+/* ---- one world over several PROCESSES, one GPU each -------------------------------------
+ * Every rank creates its context with pk_config.shard_rank / shard_count = its rank / the number of ranks and the
+ * same capacities, then joins a communicator: rank 0 calls pk_comm_get_id and hands the 128 bytes to the others by
+ * whatever means the host has (MPI, a file, torch.distributed), every rank calls pk_comm_init.  The collectives are
+ * NCCL all-gathers over NVLink on the context's stream; NCCL is looked up at run time (libnccl.so.2), the library
+ * does not link against it.  All ranks must make the same pk_comm_* calls in the same order.
+ * Per step: upload the poses of the bodies pk_comm_pose_slice names (1/N of the per-step H2D), pk_comm_allgather_poses,
+ * pk_collide_resident, pk_comm_allgather_contacts — the one exchange of the step: every rank then holds the contact
+ * records of the whole world, which is what constraint_solver::setup_contacts reads (collision/constraint.h:1052-1104).
+ * The single-process form of the same sharding is pk_create_multi below. */
+typedef struct pk_comm_id
+{
+    char bytes[128];
+} pk_comm_id;
+#define PK_POSE_POS 1
+#define PK_POSE_QUAT 2
+#define PK_POSE_DISP 4
+typedef struct pk_gathered_contacts
+{
+    const void *d_records;   /* DEVICE pointer: num_ranks blocks of stride_records pk_contact each; block r holds   */
+    uint64_t stride_records; /* counts[r] records sorted by key, the ranks' key ranges interleave                    */
+    const uint64_t *counts;  /* host, ctx-owned, valid until the next call                                          */
+    uint32_t num_ranks;
+    uint64_t total;          /* sum of counts */
+    float ms;                /* device time of the exchange (counts + records) */
+} pk_gathered_contacts;
+int pk_comm_get_id(pk_comm_id *id);
+int pk_comm_init(pk_ctx *ctx, const pk_comm_id *id, int rank, int nranks);
+int pk_comm_pose_slice(pk_ctx *ctx, uint32_t *first, uint32_t *count); /* bodies [n·r/N, n·(r+1)/N) of this rank */
+int pk_comm_allgather_poses(pk_ctx *ctx, int what /* PK_POSE_* bits */); /* in place, enqueued on the ctx stream */
+int pk_comm_allgather_contacts(pk_ctx *ctx, pk_gathered_contacts *out);  /* returns when the records have arrived */
+
 /* ---- narrowphase only: gjk_epa over an explicit pair list (BASELINE config C4) ----------------
  * pair_a/pair_b index the uploaded bodies; out[k] / hit[k] are written for every k (host pointers).
  * out[k].key = make_pair_key as given (a<<32|b, NOT min/max: argument order is the caller's). */

@@ -43,6 +43,11 @@ class PkError(RuntimeError):
         self.status = status
 
 
+class _Gathered(C.Structure):
+    _fields_ = [("d_records", C.c_void_p), ("stride_records", C.c_uint64), ("counts", C.POINTER(C.c_uint64)), ("num_ranks", C.c_uint32),
+                ("total", C.c_uint64), ("ms", C.c_float)]
+
+
 class _Config(C.Structure):
     _fields_ = [
         ("device", C.c_int32),
@@ -95,6 +100,7 @@ EXPORTS = [
     "pk_manifolds", "pk_manifolds_device", "pk_manifold_events", "pk_manifolds_set_impulses", "pk_create", "pk_destroy", "pk_strerror", "pk_last_error",
     "pk_shape_box", "pk_shape_sphere", "pk_shape_hull", "pk_shape_aabb", "pk_shapes_bulk",
     "pk_bodies_resize", "pk_bodies_upload", "pk_bodies_update_pose", "pk_reserve_pairs",
+    "pk_comm_get_id", "pk_comm_init", "pk_comm_pose_slice", "pk_comm_allgather_poses", "pk_comm_allgather_contacts",
     "pk_collide_resident", "pk_fetch_results", "pk_collide", "pk_pairs", "pk_contacts",
     "pk_pairs_device", "pk_contacts_device", "pk_stored_bounds", "pk_stage_times_get", "pk_stream",
     "pk_gjk_epa_batch", "pk_gjk_epa_batch_device", "pk_raycast", "pk_raycast_device_ms",
@@ -165,6 +171,11 @@ def load_library():
     L.pk_bodies_upload.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, u32]
     L.pk_bodies_update_pose.argtypes = [vp, vp, vp, vp, u32, u32]
     L.pk_reserve_pairs.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.pk_comm_get_id.argtypes = [vp]
+    L.pk_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.pk_comm_pose_slice.argtypes = [vp, vp, vp]
+    L.pk_comm_allgather_poses.argtypes = [vp, C.c_int]
+    L.pk_comm_allgather_contacts.argtypes = [vp, vp]
     L.pk_collide_resident.argtypes = [vp, vp]
     L.pk_fetch_results.argtypes = [vp]
     L.pk_collide.argtypes = [vp, vp]
@@ -332,6 +343,36 @@ class Context:
         allow = (PK_E_EPA_OVERFLOW,) if allow_epa_overflow else ()
         self._check(self.L.pk_collide(self.h, C.byref(self.result)), allow)
         return self.result
+
+    # -- one world over several processes (pk_comm_*: NCCL all-gathers inside the library)
+    @staticmethod
+    def comm_get_id():
+        """128 bytes rank 0 hands to the other ranks (numpy uint8 array)."""
+        buf = np.zeros(128, dtype=np.uint8)
+        st = load_library().pk_comm_get_id(_p(buf))
+        if st != PK_OK:
+            raise PkError(st, "pk_comm_get_id failed (NCCL not available?)")
+        return buf
+
+    def comm_init(self, comm_id, rank, nranks):
+        cid = np.ascontiguousarray(comm_id, dtype=np.uint8)
+        assert cid.size == 128
+        self._check(self.L.pk_comm_init(self.h, _p(cid), int(rank), int(nranks)))
+
+    def comm_pose_slice(self):
+        f, c = C.c_uint32(), C.c_uint32()
+        self._check(self.L.pk_comm_pose_slice(self.h, C.byref(f), C.byref(c)))
+        return int(f.value), int(c.value)
+
+    def comm_allgather_poses(self, pos=True, quat=True, disp=True):
+        self._check(self.L.pk_comm_allgather_poses(self.h, (1 if pos else 0) | (2 if quat else 0) | (4 if disp else 0)))
+
+    def comm_allgather_contacts(self):
+        """→ (device pointer, stride in records, counts per rank, device ms)."""
+        g = _Gathered()
+        self._check(self.L.pk_comm_allgather_contacts(self.h, C.byref(g)))
+        counts = np.ctypeslib.as_array(g.counts, shape=(g.num_ranks,)).copy() if g.num_ranks else np.zeros(0, np.uint64)
+        return g.d_records, int(g.stride_records), counts, float(g.ms)
 
     def reserve_pairs(self, max_pairs, max_contacts=0):
         """Grow the pair / contact capacities (after PK_E_PAIR_OVERFLOW: reserve, then repeat the step)."""

@@ -7,6 +7,7 @@
 #include "../../include/pk_collide.h"
 
 #include "pk_broadphase.cuh"
+#include "pk_comm.cuh"
 #include "pk_common.cuh"
 #include "pk_narrowphase.cuh"
 #include "pk_epa_coop.cuh"
@@ -201,6 +202,15 @@ struct pk_ctx
     cudaEvent_t ev[ST_COUNT + 1]{};
     float stage_ms[ST_COUNT]{};
     uint32_t launches = 0;
+
+    // one world over several processes (pk_comm_*): NCCL communicator on this context's stream
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    unsigned long long *d_comm_counts = nullptr; // [comm_size + 1]: every rank's contact count (+ this rank's, as sent)
+    unsigned long long *h_comm_counts = nullptr; // pinned
+    ContactRec *d_gather = nullptr;              // room for comm_size blocks of gather_stride records
+    uint64_t gather_stride = 0;
+    cudaEvent_t ev_comm[2]{};
 };
 
 namespace
@@ -625,6 +635,12 @@ int pk_destroy(pk_ctx *ctx)
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
+    if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
+    if (ctx->d_comm_counts) cudaFree(ctx->d_comm_counts);
+    if (ctx->h_comm_counts) cudaFreeHost(ctx->h_comm_counts);
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    for (auto &e : ctx->ev_comm)
+        if (e) cudaEventDestroy(e);
     if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
     if (ctx->ev_pairs_copied) cudaEventDestroy(ctx->ev_pairs_copied);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1981,6 +1997,157 @@ int pk_stream(pk_ctx *ctx, void **stream)
 {
     if (!ctx || !stream) return PK_E_INVALID;
     *stream = ctx->stream;
+    return PK_OK;
+}
+
+// ------------------------------------------------------------------------------------ one world over several processes
+// every rank holds all bodies and rebuilds the tree, traverses its own slice of the sorted leaves and
+// runs GJK / EPA on its own pairs; what the ranks exchange is (1) the poses, each rank uploading 1/N of them from the
+// host and all-gathering the rest over NVLink instead of N copies of the whole array crossing PCIe, and (2) the
+// contact records, which constraint_solver::setup_contacts reads for the whole world (collision/constraint.h:1052-1104).
+
+#define PK_NCCL(call)                                                                            \
+    do                                                                                           \
+    {                                                                                            \
+        ncclResult_t r__ = (call);                                                               \
+        if (r__ != ncclSuccess)                                                                  \
+        {                                                                                        \
+            ctx->last_error = std::string(#call) + ": " + nccl_api().GetErrorString(r__);        \
+            return PK_E_CUDA;                                                                    \
+        }                                                                                        \
+    } while (0)
+
+int pk_comm_get_id(pk_comm_id *id)
+{
+    if (!id) return PK_E_INVALID;
+    static_assert(sizeof(pk_comm_id) == sizeof(ncclUniqueId), "pk_comm_id must hold an ncclUniqueId");
+    NcclApi &api = nccl_api();
+    if (!api.error.empty()) return PK_E_STATE;
+    ncclUniqueId u;
+    if (api.GetUniqueId(&u) != ncclSuccess) return PK_E_CUDA;
+    std::memcpy(id, &u, sizeof(u));
+    return PK_OK;
+}
+
+int pk_comm_init(pk_ctx *ctx, const pk_comm_id *id, int rank, int nranks)
+{
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return PK_E_INVALID;
+    if (ctx->comm) return PK_E_STATE;
+    NcclApi &api = nccl_api();
+    if (!api.error.empty())
+    {
+        ctx->last_error = api.error;
+        return PK_E_STATE;
+    }
+    cudaSetDevice(ctx->cfg.device);
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof(u));
+    PK_NCCL(api.CommInitRank(&ctx->comm, nranks, u, rank));
+    ctx->comm_rank = rank;
+    ctx->comm_size = nranks;
+    PK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_comm_counts), (static_cast<size_t>(nranks) + 1) * sizeof(unsigned long long)));
+    PK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_comm_counts), (static_cast<size_t>(nranks) + 1) * sizeof(unsigned long long),
+                          cudaHostAllocDefault));
+    for (auto &e : ctx->ev_comm) PK_CUDA(cudaEventCreate(&e));
+    return PK_OK;
+}
+
+int pk_comm_pose_slice(pk_ctx *ctx, uint32_t *first, uint32_t *count)
+{
+    if (!ctx || !first || !count) return PK_E_INVALID;
+    const uint64_t n = ctx->n_bodies, N = static_cast<uint64_t>(ctx->comm_size), r = static_cast<uint64_t>(ctx->comm_rank);
+    *first = static_cast<uint32_t>(n * r / N);
+    *count = static_cast<uint32_t>(n * (r + 1) / N - n * r / N);
+    return PK_OK;
+}
+
+int pk_comm_allgather_poses(pk_ctx *ctx, int what)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (!ctx->comm) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    NcclApi &api = nccl_api();
+    const uint64_t n = ctx->n_bodies, N = static_cast<uint64_t>(ctx->comm_size);
+    struct Arr
+    {
+        double *p;
+        uint64_t width;
+        int bit;
+    } arrs[3] = {{ctx->d_pos, 3, PK_POSE_POS}, {ctx->d_quat, 4, PK_POSE_QUAT}, {ctx->d_disp, 3, PK_POSE_DISP}};
+    for (const Arr &a : arrs)
+    {
+        if (!(what & a.bit)) continue;
+        if (n % N == 0)
+        {
+            const uint64_t chunk = n / N * a.width; // in place: the send block is this rank's block of the receive buffer
+            PK_NCCL(api.AllGather(a.p + chunk * static_cast<uint64_t>(ctx->comm_rank), a.p, chunk, ncclDouble, ctx->comm, ctx->stream));
+        }
+        else
+        {
+            PK_NCCL(api.GroupStart());
+            for (uint64_t r = 0; r < N; ++r)
+            {
+                const uint64_t f = n * r / N, c = n * (r + 1) / N - f;
+                if (c) PK_NCCL(api.Broadcast(a.p + f * a.width, a.p + f * a.width, c * a.width, ncclDouble, static_cast<int>(r), ctx->comm, ctx->stream));
+            }
+            PK_NCCL(api.GroupEnd());
+        }
+    }
+    if ((what & PK_POSE_QUAT) && ctx->dyn_enabled)
+        dynamics_derive_kernel<<<div_up(ctx->n_bodies, 256), 256, 0, ctx->stream>>>(ctx->d_quat, ctx->dyn, 0, ctx->n_bodies);
+    return PK_OK;
+}
+
+int pk_comm_allgather_contacts(pk_ctx *ctx, pk_gathered_contacts *out)
+{
+    if (!ctx || !out) return PK_E_INVALID;
+    if (!ctx->comm) return PK_E_STATE;
+    if (!ctx->have_results || !ctx->device_results) return PK_E_STATE;
+    cudaSetDevice(ctx->cfg.device);
+    NcclApi &api = nccl_api();
+    cudaStream_t s = ctx->stream;
+    const int N = ctx->comm_size;
+    cudaEventRecord(ctx->ev_comm[0], s);
+    // (1) every rank's count.  This rank's is on the host already (the step read it); the others' come through a
+    // one-word all-gather, and the block size of (2) has to be known on the host: one small synchronisation.
+    ctx->h_comm_counts[N] = ctx->num_contacts;
+    PK_CUDA(cudaMemcpyAsync(ctx->d_comm_counts + N, ctx->h_comm_counts + N, sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    PK_NCCL(api.AllGather(ctx->d_comm_counts + N, ctx->d_comm_counts, 1, ncclUint64, ctx->comm, s));
+    PK_CUDA(cudaMemcpyAsync(ctx->h_comm_counts, ctx->d_comm_counts, static_cast<size_t>(N) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    PK_CUDA(cudaStreamSynchronize(s));
+    uint64_t stride = 0, total = 0;
+    for (int r = 0; r < N; ++r)
+    {
+        stride = std::max<uint64_t>(stride, ctx->h_comm_counts[r]);
+        total += ctx->h_comm_counts[r];
+    }
+    // (2) the records, straight from the contact buffer the EPA kernels wrote (no staging copy), in blocks of `stride`
+    // records (the largest count; what a block holds beyond its rank's count is unspecified)
+    if (stride > ctx->max_contacts)
+    {
+        ctx->last_error = "a rank holds more contacts than this context's max_contacts: ranks must be created with equal capacities";
+        return PK_E_STATE;
+    }
+    if (stride > ctx->gather_stride)
+    {
+        if (ctx->d_gather) cudaFree(ctx->d_gather);
+        ctx->d_gather = nullptr;
+        ctx->gather_stride = 0;
+        const uint64_t cap = std::min<uint64_t>(ctx->max_contacts, stride + stride / 4 + 1024);
+        PK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_gather), static_cast<size_t>(N) * cap * sizeof(ContactRec)));
+        ctx->gather_stride = cap;
+    }
+    if (stride) PK_NCCL(api.AllGather(ctx->d_contacts_final, ctx->d_gather, stride * sizeof(ContactRec), ncclChar, ctx->comm, s));
+    cudaEventRecord(ctx->ev_comm[1], s);
+    PK_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_comm[0], ctx->ev_comm[1]);
+    out->d_records = ctx->d_gather;
+    out->stride_records = stride;
+    out->counts = reinterpret_cast<const uint64_t *>(ctx->h_comm_counts);
+    out->num_ranks = static_cast<uint32_t>(N);
+    out->total = total;
+    out->ms = ms;
     return PK_OK;
 }
 
