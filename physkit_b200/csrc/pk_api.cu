@@ -91,6 +91,7 @@ struct pk_ctx
     std::vector<ShapeRec> h_shapes;
     std::vector<double> h_verts;
     bool shapes_dirty = false;
+    bool has_big_hulls = false; // a hull above HULL_PREFILTER_MIN vertices is registered
     ShapeRec *d_shapes = nullptr;
     double *d_verts = nullptr;
     float4 *d_verts_f = nullptr;
@@ -132,6 +133,7 @@ struct pk_ctx
     uint32_t *d_valid_index = nullptr;
     uint32_t *d_epa_order = nullptr;
     uint32_t *d_gjk_work = nullptr;
+    GjkCarry *d_gjk_carry = nullptr; // first two support points of the prefilter survivors, by pair index
     unsigned char *d_slabs = nullptr;
     unsigned char *d_epa_spill = nullptr;
     uint32_t *d_epa_fallback2 = nullptr; // hit slots epa_coop_kernel handed to epa_kernel
@@ -389,11 +391,23 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
     if (timed) cudaEventRecord(ctx->ev[ST_GJK], ctx->stream);
     if (npairs)
     {
-        gjk_prefilter_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit,
-                                                                          ctx->d_gjk_work, ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS);
-        gjk_kernel<<<div_up(npairs, PK_GJK_THREADS), PK_GJK_THREADS, 0, ctx->stream>>>(
-            body_arrays(ctx), d_keys, d_a, d_b, ctx->d_gjk_work, ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, ctx->d_hit, ctx->d_simplices,
-            ctx->d_counters + C_HITS, ctx->max_contacts, ctx->d_counters + C_CLASS_COUNT);
+        // contexts with many-vertex hulls carry the first two support points from the prefilter to gjk_kernel
+        if (ctx->has_big_hulls)
+        {
+            gjk_prefilter_kernel<true><<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit, ctx->d_gjk_work,
+                                                                                    ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, ctx->d_gjk_carry);
+            gjk_kernel<true><<<div_up(npairs, PK_GJK_THREADS), PK_GJK_THREADS, 0, ctx->stream>>>(
+                body_arrays(ctx), d_keys, d_a, d_b, ctx->d_gjk_work, ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, ctx->d_hit, ctx->d_simplices,
+                ctx->d_counters + C_HITS, ctx->max_contacts, ctx->d_counters + C_CLASS_COUNT, ctx->d_gjk_carry);
+        }
+        else
+        {
+            gjk_prefilter_kernel<false><<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit, ctx->d_gjk_work,
+                                                                                     ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, nullptr);
+            gjk_kernel<false><<<div_up(npairs, PK_GJK_THREADS), PK_GJK_THREADS, 0, ctx->stream>>>(
+                body_arrays(ctx), d_keys, d_a, d_b, ctx->d_gjk_work, ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, ctx->d_hit, ctx->d_simplices,
+                ctx->d_counters + C_HITS, ctx->max_contacts, ctx->d_counters + C_CLASS_COUNT, nullptr);
+        }
         ctx->launches += 2;
     }
     if (timed) cudaEventRecord(ctx->ev[ST_SCAN], ctx->stream);
@@ -519,10 +533,11 @@ static int alloc_pair_buffers(pk_ctx *ctx)
     A(ctx->d_valid_index, nc);
     A(ctx->d_epa_order, nc);
     A(ctx->d_gjk_work, 4 * np); // one survivor list per shape-kind class
+    A(ctx->d_gjk_carry, np);
     // persistent EPA grid: enough resident threads to fill the machine, never more than the work
     {
         int gjk_per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm, gjk_kernel, PK_GJK_THREADS, 0) != cudaSuccess || gjk_per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm, gjk_kernel<false>, PK_GJK_THREADS, 0) != cudaSuccess || gjk_per_sm < 1)
             gjk_per_sm = 2;
         ctx->gjk_blocks = static_cast<uint32_t>(ctx->sm_count * gjk_per_sm);
         int per_sm = 0;
@@ -569,6 +584,7 @@ static void free_pair_buffers(pk_ctx *ctx)
                      reinterpret_cast<void **>(&ctx->d_contacts[0]), reinterpret_cast<void **>(&ctx->d_contacts[1]),
                      reinterpret_cast<void **>(&ctx->d_valid), reinterpret_cast<void **>(&ctx->d_valid_index),
                      reinterpret_cast<void **>(&ctx->d_epa_order), reinterpret_cast<void **>(&ctx->d_gjk_work),
+                     reinterpret_cast<void **>(&ctx->d_gjk_carry),
                      reinterpret_cast<void **>(&ctx->d_slabs), reinterpret_cast<void **>(&ctx->d_epa_spill),
                      reinterpret_cast<void **>(&ctx->d_epa_fallback2), reinterpret_cast<void **>(&ctx->d_epa_init)})
     {
@@ -827,6 +843,7 @@ int pk_shape_hull(pk_ctx *ctx, const double *xyz, uint32_t nverts, uint32_t *id)
     }
     int s = add_shape(ctx, r, id);
     if (s != PK_OK) return s;
+    if (nverts > HULL_PREFILTER_MIN) ctx->has_big_hulls = true;
     ctx->h_verts.insert(ctx->h_verts.end(), xyz, xyz + 3ull * nverts);
     return PK_OK;
 }

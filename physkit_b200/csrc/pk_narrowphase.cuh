@@ -192,6 +192,42 @@ __device__ __forceinline__ bool gjk_collision(const ShapeView &A, const ShapeVie
     return false;
 }
 
+// What gjk_prefilter_kernel hands to gjk_kernel for a surviving pair: the first two support points, so that the
+// survivor does not evaluate them a second time (half of the supports of a typical pair).  96 bytes per candidate
+// pair, written for survivors only.
+struct alignas(16) GjkCarry
+{
+    double v[2][6]; // pa xyz, pb xyz of simplex points 0 and 1; v[1][0] = NaN: the first point hit the origin, which
+                    // gjk_collision answers with the one-point simplex (collision.cpp:174)
+};
+static_assert(sizeof(GjkCarry) == 96, "GjkCarry layout");
+
+// gjk_collision (collision.cpp:165-189) from its third support on: the simplex holds the first two points, the
+// second of which passed the separation test against direction −normalized(p0).  Written without early returns
+// (one exit flag): lanes of a warp meet again at the head of every iteration.
+__device__ __forceinline__ bool gjk_resume(const ShapeView &A, const ShapeView &B, Simplex &s)
+{
+    d3 dir{0.0, 0.0, 0.0};
+    bool hit = handle_simplex(s, dir); // the line case of iteration 0
+    bool alive = !hit;
+    for (int iter = 1; alive && iter < 100; ++iter)
+    {
+        const SupportPt np = minkowski_support(A, B, dir);
+        if (dot(P(np), dir) <= 0.0)
+            alive = false;
+        else
+        {
+            s.pt[s.n++] = np;
+            if (handle_simplex(s, dir))
+            {
+                hit = true;
+                alive = false;
+            }
+        }
+    }
+    return hit;
+}
+
 // collision.cpp:191-248
 __device__ __forceinline__ bool pad_simplex(const ShapeView &A, const ShapeView &B, Simplex &s)
 {
@@ -265,11 +301,12 @@ __device__ __forceinline__ void load_pair(const uint64_t *__restrict__ keys, con
 // Survivors are listed per shape-kind class (bit 0: A is a sphere, bit 1: B is a sphere) so that the
 // lanes of a gjk_kernel warp run the same support code: with the pair list in key order a warp held a
 // random mix of sphere and box supports and executed both paths for every call.
+template <bool CARRY>
 __global__ void __launch_bounds__(128)
 gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
                      const uint32_t *__restrict__ pair_b, uint64_t npairs, uint8_t *__restrict__ hit,
                      uint32_t *__restrict__ work /*[4][work_stride]*/, uint64_t work_stride,
-                     unsigned long long *__restrict__ work_count /*[4]*/)
+                     unsigned long long *__restrict__ work_count /*[4]*/, GjkCarry *__restrict__ carry /*[npairs]*/)
 {
     const uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     bool survive = false;
@@ -281,14 +318,34 @@ gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const
         ShapeView A = load_shape(bodies, ia);
         ShapeView B = load_shape(bodies, ib);
         cls = (A.kind == KIND_SPHERE ? 1u : 0u) | (B.kind == KIND_SPHERE ? 2u : 0u);
-        d3 p0 = P(minkowski_support(A, B, d3{1.0, 0.0, 0.0}));
+        const SupportPt s0 = minkowski_support(A, B, d3{1.0, 0.0, 0.0});
+        const d3 p0 = P(s0);
+        double2 *c = reinterpret_cast<double2 *>(carry + k);
         if (sqnorm(p0) < 1e-12)
-            survive = true; // origin hit on the first point: full path decides (collision.cpp:174)
+        {
+            survive = true; // origin hit on the first point: a hit with a one-point simplex (collision.cpp:174)
+            if constexpr (CARRY)
+            {
+                c[0] = make_double2(s0.pa.x, s0.pa.y);
+                c[1] = make_double2(s0.pa.z, s0.pb.x);
+                c[2] = make_double2(s0.pb.y, s0.pb.z);
+                c[3] = make_double2(__longlong_as_double(0x7FF8000000000000ll), 0.0);
+            }
+        }
         else
         {
-            d3 dir = -normalized(p0);
-            d3 p1 = P(minkowski_support(A, B, dir));
-            survive = !(dot(p1, dir) <= 0.0); // collision.cpp:181-182
+            const d3 dir = -normalized(p0);
+            const SupportPt s1 = minkowski_support(A, B, dir);
+            survive = !(dot(P(s1), dir) <= 0.0); // collision.cpp:181-182
+            if (CARRY && survive)
+            {
+                c[0] = make_double2(s0.pa.x, s0.pa.y);
+                c[1] = make_double2(s0.pa.z, s0.pb.x);
+                c[2] = make_double2(s0.pb.y, s0.pb.z);
+                c[3] = make_double2(s1.pa.x, s1.pa.y);
+                c[4] = make_double2(s1.pa.z, s1.pb.x);
+                c[5] = make_double2(s1.pb.y, s1.pb.z);
+            }
         }
         if (!survive) hit[k] = 0;
     }
@@ -308,12 +365,13 @@ gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const
 // One thread per surviving pair.  (A persistent-lane variant with per-lane refill was measured in r1
 // and lost: with a mean of 1.9 iterations per pair half the lanes refill every round and the set-up
 // path — two gathered body loads — then sits on the critical path of every round.)
+template <bool CARRY>
 __global__ void __launch_bounds__(PK_GJK_THREADS, PK_GJK_MIN_BLOCKS)
 gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
            const uint32_t *__restrict__ pair_b, const uint32_t *__restrict__ work, uint64_t work_stride,
            const unsigned long long *__restrict__ work_count /*[4]*/, uint8_t *__restrict__ hit,
            SimplexRec *__restrict__ simplices, unsigned long long *__restrict__ hit_count, uint64_t hit_capacity,
-           unsigned long long *__restrict__ class_count /*[3]*/)
+           unsigned long long *__restrict__ class_count /*[3]*/, const GjkCarry *__restrict__ carry /*[npairs]*/)
 {
     uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     int c = 0; // class lists back to back: thread w works on entry w of their concatenation
@@ -325,7 +383,41 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
     ShapeView A = load_shape(bodies, ia);
     ShapeView B = load_shape(bodies, ib);
     Simplex s;
-    bool h = gjk_collision(A, B, s);
+    bool h;
+    {
+        if constexpr (CARRY)
+        {
+            const double2 *cv = reinterpret_cast<const double2 *>(carry + k);
+            const double2 c0 = cv[0], c1 = cv[1], c2 = cv[2], c3 = cv[3];
+            s.pt[0].pa = d3{c0.x, c0.y, c1.x};
+            s.pt[0].pb = d3{c1.y, c2.x, c2.y};
+            s.n = 1;
+            h = true;
+            if (c3.x == c3.x)
+            {
+                const double2 c4 = cv[4], c5 = cv[5];
+                s.pt[1].pa = d3{c3.x, c3.y, c4.x};
+                s.pt[1].pb = d3{c4.y, c5.x, c5.y};
+                s.n = 2;
+                h = gjk_resume(A, B, s);
+            }
+        }
+        else
+        {
+            // cheap supports (spheres, boxes): evaluating the first two again costs less than carrying 96 bytes per
+            // survivor through HBM (measured: C3 2.44 against 2.67 ms)
+            s.pt[0] = minkowski_support(A, B, d3{1.0, 0.0, 0.0});
+            s.n = 1;
+            h = true;
+            const d3 p0 = P(s.pt[0]);
+            if (!(sqnorm(p0) < 1e-12))
+            {
+                s.pt[1] = minkowski_support(A, B, -normalized(p0)); // passed the separation test in the prefilter
+                s.n = 2;
+                h = gjk_resume(A, B, s);
+            }
+        }
+    }
     hit[k] = h ? 1 : 0;
     if (h)
     {

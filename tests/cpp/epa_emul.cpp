@@ -65,8 +65,33 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, const double *verts, uint64_t
         const uint64_t k = seq[q];
         ShapeView A = load_shape(ba, pa[k]);
         ShapeView B = load_shape(ba, pb[k]);
+        // gjk_prefilter_kernel + gjk_kernel: the first two supports, the separation test, then gjk_resume
         Simplex s;
-        const bool h = gjk_collision(A, B, s);
+        bool h;
+        {
+            const SupportPt s0 = minkowski_support(A, B, d3{1.0, 0.0, 0.0});
+            const d3 p0 = P(s0);
+            if (sqnorm(p0) < 1e-12)
+            {
+                s.pt[0] = s0; // the one-point simplex of collision.cpp:174
+                s.n = 1;
+                h = true;
+            }
+            else
+            {
+                const d3 dir = -normalized(p0);
+                const SupportPt s1 = minkowski_support(A, B, dir);
+                if (dot(P(s1), dir) <= 0.0)
+                    h = false;
+                else
+                {
+                    s.pt[0] = s0;
+                    s.pt[1] = s1;
+                    s.n = 2;
+                    h = gjk_resume(A, B, s);
+                }
+            }
+        }
         hit[k] = h ? 1 : 0;
         if (!h) continue;
         const unsigned long long slot = counters[0]++;

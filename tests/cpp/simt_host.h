@@ -150,6 +150,12 @@ inline float __double2float_ru(double d)
     if (static_cast<double>(f) < d) f = std::nextafterf(f, INFINITY);
     return f;
 }
+inline double __longlong_as_double(long long x)
+{
+    double d;
+    std::memcpy(&d, &x, 8);
+    return d;
+}
 inline double __drcp_rn(double x) { return 1.0 / x; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
