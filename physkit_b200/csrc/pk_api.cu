@@ -17,6 +17,8 @@
 #include "pk_solver.cuh"
 #include "pk_sort.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -273,6 +275,16 @@ __global__ void division_selftest_kernel(uint64_t seed, uint32_t per_thread, uns
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// NVTX range over the host side of a call (the spans a timeline tool shows above the kernels they
+// enqueue; header-only NVTX 3, a no-op without a profiler attached)
+struct PkRange
+{
+    explicit PkRange(const char *name) { nvtxRangePushA(name); }
+    ~PkRange() { nvtxRangePop(); }
+    PkRange(const PkRange &) = delete;
+    PkRange &operator=(const PkRange &) = delete;
+};
+
 #define PK_CUDA(call)                                                                                     \
     do                                                                                                    \
     {                                                                                                     \
@@ -388,6 +400,7 @@ BodyArrays body_arrays(pk_ctx *ctx)
 int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, const uint32_t *d_b, uint64_t npairs,
                     bool timed, ContactRec *mirror = nullptr)
 {
+    PkRange range("pk: narrowphase (GJK, hit scan, EPA)");
     if (timed) cudaEventRecord(ctx->ev[ST_GJK], ctx->stream);
     if (npairs)
     {
@@ -448,10 +461,9 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
         ep.restart_count = ctx->d_counters + C_EPA_FALLBACK;
         ep.init = ctx->d_epa_init;
         ep.contacts_host = mirror;
-        if (mirror)
-            epa_coop_kernel<true><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(ep);
-        else
-            epa_coop_kernel<false><<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(ep);
+        auto coop = ctx->has_big_hulls ? (mirror ? epa_coop_kernel<true, true> : epa_coop_kernel<false, true>)
+                                       : (mirror ? epa_coop_kernel<true, false> : epa_coop_kernel<false, false>);
+        coop<<<ctx->epa_scan_blocks, ES_THREADS, 0, ctx->stream>>>(ep);
         epa_kernel<<<ctx->epa_blocks, EPA_THREADS, 0, ctx->stream>>>(
             body_arrays(ctx), d_keys, d_a, d_b, ctx->d_simplices, ctx->d_counters + C_EPA_FALLBACK + 1, ctx->max_contacts,
             ctx->d_out_index, ctx->d_epa_fallback2, ctx->d_contacts[0], ctx->d_valid, ctx->d_slabs,
@@ -552,10 +564,12 @@ static int alloc_pair_buffers(pk_ctx *ctx)
         ctx->epa_blocks = static_cast<uint32_t>(threads / EPA_THREADS);
         A(ctx->d_slabs, threads * EPA_SLAB_BYTES);
         // epa_coop_kernel: 43 KB of shared memory per 64-thread block, as many blocks per SM as fit
-        cudaFuncSetAttribute(epa_coop_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(epa_coop_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_coop_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_coop_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_coop_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_coop_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int es_per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_coop_kernel<false>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&es_per_sm, epa_coop_kernel<false, true>, ES_THREADS, 0) != cudaSuccess || es_per_sm < 1)
             es_per_sm = 1;
 #ifdef PK_ES_BLOCKS_PER_SM
         es_per_sm = std::min(es_per_sm, PK_ES_BLOCKS_PER_SM);
@@ -949,6 +963,7 @@ int pk_bodies_update_pose(pk_ctx *ctx, const double *pos, const double *quat, co
 int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
 {
     if (!ctx) return PK_E_INVALID;
+    PkRange range("pk_collide_resident");
     cudaSetDevice(ctx->cfg.device);
     if (ctx->pairs_in_flight)
     {
@@ -978,6 +993,15 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
     while (static_cast<uint64_t>(wt.grid) * wt.grid * wt.grid < wt.num_worlds) ++wt.grid;
     const uint32_t *d_world = (ctx->cfg.num_worlds > 1 && ctx->have_world) ? ctx->d_world : nullptr;
 
+    nvtxRangePushA("pk: broadphase (bounds, LBVH, overlap, pair sort)");
+    struct PopRange
+    {
+        bool armed = true;
+        ~PopRange()
+        {
+            if (armed) nvtxRangePop();
+        }
+    } broad_range;
     cudaEventRecord(ctx->ev[ST_BOUNDS], s);
     scene_reset_kernel<<<1, 64, 0, s>>>(ctx->d_scene, ctx->d_counters, C_COUNT);
     ctx->launches += 1;
@@ -1052,6 +1076,8 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
     }
     ctx->d_pairs_sorted = ctx->d_pkeys[pair_buf];
     ctx->pairs_in_flight = false;
+    nvtxRangePop();
+    broad_range.armed = false;
     if (ctx->want_host_results && npairs)
     {
         // pk_collide: the sorted pair keys are final here; ship them to the host on a second stream while
@@ -1153,6 +1179,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
 int pk_fetch_results(pk_ctx *ctx)
 {
     if (!ctx) return PK_E_INVALID;
+    PkRange range("pk_fetch_results");
     if (!ctx->have_results) return PK_E_STATE;
     if (ctx->fetched) return PK_OK;
     if (!ctx->device_results) return PK_E_STATE;
@@ -2081,6 +2108,7 @@ int pk_comm_pose_slice(pk_ctx *ctx, uint32_t *first, uint32_t *count)
 int pk_comm_allgather_poses(pk_ctx *ctx, int what)
 {
     if (!ctx) return PK_E_INVALID;
+    PkRange range("pk_comm_allgather_poses");
     if (!ctx->comm) return PK_E_STATE;
     cudaSetDevice(ctx->cfg.device);
     NcclApi &api = nccl_api();
@@ -2118,6 +2146,7 @@ int pk_comm_allgather_poses(pk_ctx *ctx, int what)
 int pk_comm_allgather_contacts(pk_ctx *ctx, pk_gathered_contacts *out)
 {
     if (!ctx || !out) return PK_E_INVALID;
+    PkRange range("pk_comm_allgather_contacts");
     if (!ctx->comm) return PK_E_STATE;
     if (!ctx->have_results || !ctx->device_results) return PK_E_STATE;
     cudaSetDevice(ctx->cfg.device);

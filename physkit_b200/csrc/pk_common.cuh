@@ -195,20 +195,88 @@ __device__ __forceinline__ ShapeView load_shape(const BodyArrays &ba, uint32_t b
 // hull differ by ≈1e-2, the threshold is ≈1e-6).  Otherwise a second pass compares the candidates with the
 // reference's exact expression, lowest index first (strict '>', src/mesh.cpp:341-358).
 // Measured dead end (profiles/r1_c4_hull_support_ab.json): letting the lanes that arrive here together
-// scan one hull at a time with consecutive 16-byte loads and a redux.sync maximum is bit-exact too but
-// slower (C4, 2 M pairs: 109.5 ms vs 76.3 ms) — the scan is bound by issued instructions, not by L1 lines,
-// and serving the group's queries one after the other adds a fixed cost per query.
+// scan one hull at a time with consecutive 16-byte loads and a redux.sync maximum for EVERY query is bit-exact
+// too but slower (C4, 2 M pairs: 109.5 ms vs 76.3 ms) — the first pass is bound by issued instructions, not by L1
+// lines, and serving the group's queries one after the other adds a fixed cost per query.  Only the second pass
+// (below) is shared.
 __device__ __forceinline__ float pk_hull_fdot(float4 w, float lx, float ly, float lz) { return fmaf(w.x, lx, fmaf(w.y, ly, w.z * lz)); }
+__device__ __forceinline__ double pk_shfl_f64(unsigned mask, double x, int src)
+{
+    unsigned long long b;
+    memcpy(&b, &x, 8);
+    const unsigned lo = __shfl_sync(mask, static_cast<unsigned>(b), src), hi = __shfl_sync(mask, static_cast<unsigned>(b >> 32), src);
+    b = (static_cast<unsigned long long>(hi) << 32) | lo;
+    memcpy(&x, &b, 8);
+    return x;
+}
+__device__ __forceinline__ unsigned long long pk_shfl_u64(unsigned mask, unsigned long long x, int src)
+{
+    const unsigned lo = __shfl_sync(mask, static_cast<unsigned>(x), src), hi = __shfl_sync(mask, static_cast<unsigned>(x >> 32), src);
+    return (static_cast<unsigned long long>(hi) << 32) | lo;
+}
+
+// The exact comparison among the vertices within 2E of the float maximum, for the lanes `todo` of the coalesced group
+// `group` (see hull_argmax), served one after the other by the whole group.  Out of line: it must not cost the
+// callers registers (sphere / box scenes never get here).
+__device__ __noinline__ uint32_t hull_exact_pass(const float4 *__restrict__ vf, const double *__restrict__ v, uint32_t nverts, float lx, float ly,
+                                                 float lz, float thr_own, double ldx, double ldy, double ldz, unsigned group, unsigned todo,
+                                                 uint32_t best)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t g = static_cast<uint32_t>(__popc(group));
+    const uint32_t r = static_cast<uint32_t>(__popc(group & ((1u << lane) - 1u)));
+    uint32_t result = best;
+    for (; todo; todo &= todo - 1u)
+    {
+        const int src = __ffs(static_cast<int>(todo)) - 1;
+        const float4 *__restrict__ q = reinterpret_cast<const float4 *>(pk_shfl_u64(group, reinterpret_cast<unsigned long long>(vf), src));
+        const double *__restrict__ qv = reinterpret_cast<const double *>(pk_shfl_u64(group, reinterpret_cast<unsigned long long>(v), src));
+        const uint32_t n = __shfl_sync(group, nverts, src);
+        const float qx = __shfl_sync(group, lx, src), qy = __shfl_sync(group, ly, src), qz = __shfl_sync(group, lz, src);
+        const float thr = __shfl_sync(group, thr_own, src);
+        const double dx = pk_shfl_f64(group, ldx, src), dy = pk_shfl_f64(group, ldy, src), dz = pk_shfl_f64(group, ldz, src);
+        double my_dot = 0.0;
+        uint32_t my_i = 0;
+        bool have = false;
+        for (uint32_t i = r; i < n; i += g) // ascending: the first of equal dots this lane meets has the lowest index
+        {
+            if (pk_hull_fdot(__ldg(q + i), qx, qy, qz) >= thr)
+            {
+                const double t = (qv[3 * i] * dx + qv[3 * i + 1] * dy) + qv[3 * i + 2] * dz;
+                if (!have || t > my_dot)
+                {
+                    my_dot = t;
+                    my_i = i;
+                    have = true;
+                }
+            }
+        }
+        unsigned cand = __ballot_sync(group, have);
+        double gd = 0.0;
+        uint32_t gi = 0;
+        bool ghave = false;
+        for (; cand; cand &= cand - 1u)
+        {
+            const int c = __ffs(static_cast<int>(cand)) - 1;
+            const double t = pk_shfl_f64(group, my_dot, c);
+            const uint32_t i = __shfl_sync(group, my_i, c);
+            if (!ghave || t > gd || (t == gd && i < gi))
+            {
+                gd = t;
+                gi = i;
+                ghave = true;
+            }
+        }
+        if (static_cast<int>(lane) == src) result = gi;
+    }
+    return result;
+}
 
 __device__ __forceinline__ uint32_t hull_argmax(const float4 *__restrict__ vf, const double *__restrict__ v, uint32_t nverts, float hull_r, d3 l)
 {
     const float lx = static_cast<float>(l.x), ly = static_cast<float>(l.y), lz = static_cast<float>(l.z);
     const float E = 1e-6f * hull_r * (fabsf(lx) + fabsf(ly) + fabsf(lz)) + 1e-37f;
     uint32_t best = 0;
-#ifdef PK_HULL_TWO_PASS
-    float f1 = -3.4e38f;
-    for (uint32_t i = 0; i < nverts; ++i) f1 = fmaxf(f1, pk_hull_fdot(__ldg(vf + i), lx, ly, lz));
-#else
     float f1 = -3.4e38f, f2 = -3.4e38f; // largest, second largest (equal values count twice)
     // ncu (C4): the scan saturates the L1 data stage (72–89 % of its peak) — every lane walks its own hull, so
     // a 16-byte load is one wavefront per lane.  Two vertices per 32-byte load (LDG.256, sm_100) halve the
@@ -238,30 +306,27 @@ __device__ __forceinline__ uint32_t hull_argmax(const float4 *__restrict__ vf, c
         track(b, 2 * k + 1);
     }
     if (nverts & 1u) track(__ldg(vf + nverts - 1), nverts - 1);
-    if (f2 < f1 - 2.0f * E) return best; // a single candidate
-    best = 0;
-#endif
-    const float thr = f1 - 2.0f * E;
-    double best_dot = 0.0;
-    bool have = false;
-    for (uint32_t i = 0; i < nverts; ++i)
-    {
-        if (pk_hull_fdot(__ldg(vf + i), lx, ly, lz) >= thr)
-        {
-            double t = (v[3 * i] * l.x + v[3 * i + 1] * l.y) + v[3 * i + 2] * l.z;
-            if (!have || t > best_dot)
-            {
-                best_dot = t;
-                best = i;
-                have = true;
-            }
-        }
-    }
-    return best;
+    // Several candidates within 2E of the maximum: the exact comparison.  This is not the rare case it looks like:
+    // EPA asks along face normals, which are perpendicular to edges between hull vertices, so the vertices behind
+    // the current face tie to within rounding in most queries.  One lane scanning its whole hull again while the
+    // rest of the warp waits was half of the support instructions of BASELINE C4 (ncu: 1.3 of 32 lanes on these
+    // lines); instead the lanes that arrive here together serve the ambiguous queries among them one after the
+    // other — the query is broadcast, lane r of g scans vertices r, r+g, … (consecutive 16-byte loads), and the
+    // candidates' exact dots are merged: largest first, lowest index among equals (strict '>', src/mesh.cpp:341-358).
+    // Correct for any group the hardware happens to form; a group of one is the serial second pass.
+    const float thr_own = f1 - 2.0f * E;
+    const bool ambiguous = !(f2 < thr_own);
+    const unsigned group = __activemask();
+    const unsigned todo = __ballot_sync(group, ambiguous);
+    if (todo == 0u) return best;
+    return hull_exact_pass(vf, v, nverts, lx, ly, lz, thr_own, l.x, l.y, l.z, group, todo, best);
 }
 
-// Farthest point of the shape along d.
-__device__ __forceinline__ d3 support(const ShapeView &s, d3 d)
+// Farthest point of the shape along d.  BIG = false: an instance for contexts that hold no hull above
+// HULL_PREFILTER_MIN vertices (the host knows: pk_shape_hull), compiled without the float-prefiltered scan and its
+// shared exact pass — sphere / box scenes then do not pay for that code in registers and instruction cache.  (Such
+// an instance would still be correct on a big hull: it takes the plain FP64 scan, which is the reference's loop.)
+template <bool BIG = true> __device__ __forceinline__ d3 support(const ShapeView &s, d3 d)
 {
     if (s.kind == KIND_OBB)
     {
@@ -304,7 +369,7 @@ __device__ __forceinline__ d3 support(const ShapeView &s, d3 d)
     }
     const double *v = s.verts;
     uint32_t best = 0;
-    if (s.nverts <= HULL_PREFILTER_MIN)
+    if (!BIG || s.nverts <= HULL_PREFILTER_MIN)
     {
         double best_dot = (v[0] * l.x + v[1] * l.y) + v[2] * l.z;
         for (uint32_t i = 1; i < s.nverts; ++i)

@@ -34,11 +34,11 @@ struct SupportPt
 __device__ __forceinline__ d3 P(const SupportPt &s) { return s.pa - s.pb; }
 
 // collision.h:41-49
-__device__ __forceinline__ SupportPt minkowski_support(const ShapeView &a, const ShapeView &b, d3 d)
+template <bool BIG = true> __device__ __forceinline__ SupportPt minkowski_support(const ShapeView &a, const ShapeView &b, d3 d)
 {
     SupportPt s;
-    s.pa = support(a, d);
-    s.pb = support(b, -d);
+    s.pa = support<BIG>(a, d);
+    s.pb = support<BIG>(b, -d);
     return s;
 }
 
@@ -205,14 +205,14 @@ static_assert(sizeof(GjkCarry) == 96, "GjkCarry layout");
 // gjk_collision (collision.cpp:165-189) from its third support on: the simplex holds the first two points, the
 // second of which passed the separation test against direction −normalized(p0).  Written without early returns
 // (one exit flag): lanes of a warp meet again at the head of every iteration.
-__device__ __forceinline__ bool gjk_resume(const ShapeView &A, const ShapeView &B, Simplex &s)
+template <bool BIG = true> __device__ __forceinline__ bool gjk_resume(const ShapeView &A, const ShapeView &B, Simplex &s)
 {
     d3 dir{0.0, 0.0, 0.0};
     bool hit = handle_simplex(s, dir); // the line case of iteration 0
     bool alive = !hit;
     for (int iter = 1; alive && iter < 100; ++iter)
     {
-        const SupportPt np = minkowski_support(A, B, dir);
+        const SupportPt np = minkowski_support<BIG>(A, B, dir);
         if (dot(P(np), dir) <= 0.0)
             alive = false;
         else
@@ -318,7 +318,7 @@ gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const
         ShapeView A = load_shape(bodies, ia);
         ShapeView B = load_shape(bodies, ib);
         cls = (A.kind == KIND_SPHERE ? 1u : 0u) | (B.kind == KIND_SPHERE ? 2u : 0u);
-        const SupportPt s0 = minkowski_support(A, B, d3{1.0, 0.0, 0.0});
+        const SupportPt s0 = minkowski_support<CARRY>(A, B, d3{1.0, 0.0, 0.0});
         const d3 p0 = P(s0);
         double2 *c = reinterpret_cast<double2 *>(carry + k);
         if (sqnorm(p0) < 1e-12)
@@ -335,7 +335,7 @@ gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const
         else
         {
             const d3 dir = -normalized(p0);
-            const SupportPt s1 = minkowski_support(A, B, dir);
+            const SupportPt s1 = minkowski_support<CARRY>(A, B, dir);
             survive = !(dot(P(s1), dir) <= 0.0); // collision.cpp:181-182
             if (CARRY && survive)
             {
@@ -399,22 +399,22 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                 s.pt[1].pa = d3{c3.x, c3.y, c4.x};
                 s.pt[1].pb = d3{c4.y, c5.x, c5.y};
                 s.n = 2;
-                h = gjk_resume(A, B, s);
+                h = gjk_resume<true>(A, B, s);
             }
         }
         else
         {
             // cheap supports (spheres, boxes): evaluating the first two again costs less than carrying 96 bytes per
             // survivor through HBM (measured: C3 2.44 against 2.67 ms)
-            s.pt[0] = minkowski_support(A, B, d3{1.0, 0.0, 0.0});
+            s.pt[0] = minkowski_support<false>(A, B, d3{1.0, 0.0, 0.0});
             s.n = 1;
             h = true;
             const d3 p0 = P(s.pt[0]);
             if (!(sqnorm(p0) < 1e-12))
             {
-                s.pt[1] = minkowski_support(A, B, -normalized(p0)); // passed the separation test in the prefilter
+                s.pt[1] = minkowski_support<false>(A, B, -normalized(p0)); // passed the separation test in the prefilter
                 s.n = 2;
-                h = gjk_resume(A, B, s);
+                h = gjk_resume<false>(A, B, s);
             }
         }
     }

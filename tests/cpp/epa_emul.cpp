@@ -5,11 +5,7 @@
 // Not linked into, nor reachable from, the product library.
 #include "simt_host.h"
 
-inline unsigned __activemask()
-{
-    std::abort(); // kernels that need it (gjk_kernel, epa_order_kernel) are not emulated
-}
-template <class T> inline unsigned __match_any_sync(unsigned, T) { std::abort(); }
+template <class T> inline unsigned __match_any_sync(unsigned, T) { std::abort(); } // gjk_kernel, epa_order_kernel: not emulated
 
 #define PK_EC_STATS
 namespace pk
@@ -29,13 +25,15 @@ extern "C" void emu_stats(unsigned long long *out, int reset)
     }
 }
 
-extern "C" int emu_gjk_epa(const ShapeRec *shapes, const double *verts, uint64_t nverts_pool, const double *pos, const double *quat,
+extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const double *verts, uint64_t nverts_pool, const double *pos, const double *quat,
                            const uint32_t *shape_id, const uint32_t *pa, const uint32_t *pb, uint64_t n, uint64_t capacity,
                            ContactRec *out, uint8_t *hit_out, int mirror, int arrival, int nblocks, uint64_t *stats /*[8]*/)
 {
     std::vector<float4> vf(nverts_pool + 2);
     for (uint64_t i = 0; i < nverts_pool; ++i)
         vf[i] = make_float4(static_cast<float>(verts[3 * i]), static_cast<float>(verts[3 * i + 1]), static_cast<float>(verts[3 * i + 2]), 0.f);
+    bool big_hulls = false;
+    for (uint64_t k = 0; k < nshapes; ++k) big_hulls = big_hulls || (shapes[k].kind == KIND_HULL && shapes[k].nverts > HULL_PREFILTER_MIN);
     BodyArrays ba;
     ba.shapes = shapes;
     ba.verts = verts;
@@ -163,10 +161,15 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, const double *verts, uint64_t
         ep.init = init.data();
         ep.contacts_host = mir;
         // blocks run one after the other (see simt_host.h): the first takes the whole list, later blocks find it drained
-        if (mirror)
-            simt::launch(nblocks, block, [&]() { epa_coop_kernel<true>(ep); });
+        // the instance the library would pick: HULLS when a hull above HULL_PREFILTER_MIN vertices is registered
+        if (mirror && big_hulls)
+            simt::launch(nblocks, block, [&]() { epa_coop_kernel<true, true>(ep); });
+        else if (mirror)
+            simt::launch(nblocks, block, [&]() { epa_coop_kernel<true, false>(ep); });
+        else if (big_hulls)
+            simt::launch(nblocks, block, [&]() { epa_coop_kernel<false, true>(ep); });
         else
-            simt::launch(nblocks, block, [&]() { epa_coop_kernel<false>(ep); });
+            simt::launch(nblocks, block, [&]() { epa_coop_kernel<false, false>(ep); });
         simt::launch(1, EPA_THREADS,
                      [&]()
                      {

@@ -88,8 +88,13 @@ template <class K> void launch(unsigned grid, unsigned block, K &&kernel)
 
 constexpr unsigned SIMT_FULL = 0xFFFFFFFFu;
 
+// Opportunistic groups (__activemask) are groups of ONE here: every thread is its own coalesced group, which the
+// kernels must (and do) handle like any other group size.  Votes and shuffles over that one-lane mask are local.
+inline unsigned __activemask() { return 1u << simt::tl_lane; }
+
 inline unsigned __ballot_sync(unsigned mask, int pred)
 {
+    if (mask == (1u << simt::tl_lane)) return pred ? mask : 0u;
     assert(mask == SIMT_FULL);
     simt::Warp &w = *simt::tl_warp;
     w.buf[simt::tl_lane] = pred ? 1u : 0u;
@@ -101,6 +106,7 @@ inline unsigned __ballot_sync(unsigned mask, int pred)
 }
 template <class T> inline T simt_exchange(unsigned mask, T v, int src)
 {
+    if (mask == (1u << simt::tl_lane)) return v;
     assert(mask == SIMT_FULL);
     static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
     simt::Warp &w = *simt::tl_warp;
@@ -160,6 +166,7 @@ inline double __drcp_rn(double x) { return 1.0 / x; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long expected, unsigned long long desired)
 {

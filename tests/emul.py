@@ -88,7 +88,7 @@ def gjk_epa_pairs(specs, pos, quat, shape_id, pair_a, pair_b, capacity=None, mir
     hit = np.zeros(n, dtype=np.uint8)
     stats = np.zeros(8, dtype=np.uint64)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.emu_gjk_epa(p(tab), p(pool), C.c_uint64(len(pool)), p(pos), p(quat), p(sid), p(pa), p(pb), C.c_uint64(n), C.c_uint64(cap),
+    rc = lib.emu_gjk_epa(p(tab), C.c_uint64(len(tab)), p(pool), C.c_uint64(len(pool)), p(pos), p(quat), p(sid), p(pa), p(pb), C.c_uint64(n), C.c_uint64(cap),
                          p(out), p(hit), C.c_int(1 if mirror else 0), C.c_int(arrival), C.c_int(nblocks), p(stats))
     if rc != 0:
         raise RuntimeError(f"emu_gjk_epa failed: {rc}")
