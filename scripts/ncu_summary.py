@@ -3,6 +3,7 @@
 
   python scripts/ncu_summary.py launches <launches.csv> <out.md>
   python scripts/ncu_summary.py kernel <report.ncu-rep> <kernel-substr> <out.md> [lib.so]
+  python scripts/ncu_summary.py table <report.ncu-rep> <out.md>
   python scripts/ncu_summary.py traffic <report.ncu-rep> <kernel-substr> <stage> <workload> [profiles/ncu_traffic.json]
 
 `kernel` needs ncu, cuobjdump and nvdisasm (all in the CUDA toolkit; no GPU).  Per-line stall
@@ -160,8 +161,45 @@ def traffic(rep, kern, stage, workload, out):
     print(json.dumps(rec))
 
 
+def table(rep, out):
+    """One row per profiled launch of an `ncu --set full` report with the figures the roofline discussion uses."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rr[0], rr[1]
+
+    def val(row, name, scale=None):
+        if name not in hdr:
+            return float("nan")
+        i = hdr.index(name)
+        v = float(row[i].replace(",", "")) if row[i] not in ("", "n/a") else float("nan")
+        if scale:
+            v *= scale.get(units[i], 1.0)
+        return v
+
+    B = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    T = {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3, "msecond": 1.0, "usecond": 1e-3, "nsecond": 1e-6, "second": 1e3}
+    lines = [f"# ncu --set full, one steady-state step: {os.path.basename(rep)}\n\n",
+             "Cold-cache, serialised launches (`--clock-control none`): compare shares and per-kernel figures, not the sum.\n\n",
+             "| kernel | grid × block | ms | regs | lanes / 32 | warps active % | issue active % | DRAM read MB | DRAM write MB | DRAM % of peak | L2 hit % | FP64 pipe % |\n",
+             "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n"]
+    for row in rr[2:]:
+        if len(row) < 10:
+            continue
+        name = re.sub(r"\((?:bool|int)\)", "", row[4].split("(")[0] if "<" not in row[4] else row[4][:row[4].index(">") + 1]).replace("void ", "").replace("pk::", "")
+        lines.append(
+            f"| `{name}` | {row[8]} × {row[7]} | {val(row, 'gpu__time_duration.sum', T):.3f} | {val(row, 'launch__registers_per_thread'):.0f} | "
+            f"{val(row, 'smsp__thread_inst_executed_per_inst_executed.ratio'):.1f} | {val(row, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | "
+            f"{val(row, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | {val(row, 'dram__bytes_read.sum', B) / 1e6:.1f} | "
+            f"{val(row, 'dram__bytes_write.sum', B) / 1e6:.1f} | {val(row, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+            f"{val(row, 'lts__t_sector_hit_rate.pct'):.1f} | {val(row, 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'):.1f} |\n")
+    open(out, "w").write("".join(lines))
+    print("".join(lines))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "table":
+        table(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     elif sys.argv[1] == "traffic":
         traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5], sys.argv[6] if len(sys.argv) > 6 else os.path.join(ROOT, "profiles", "ncu_traffic.json"))
