@@ -405,6 +405,8 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
     if (npairs)
     {
         // contexts with many-vertex hulls carry the first two support points from the prefilter to gjk_kernel
+        if (ctx->has_big_hulls && !ctx->d_gjk_carry)
+            PK_TRY(dev_alloc(ctx, &ctx->d_gjk_carry, ctx->cfg.max_pairs)); // 96 B per pair of capacity: only contexts that use it
         if (ctx->has_big_hulls)
         {
             gjk_prefilter_kernel<true><<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit, ctx->d_gjk_work,
@@ -545,7 +547,6 @@ static int alloc_pair_buffers(pk_ctx *ctx)
     A(ctx->d_valid_index, nc);
     A(ctx->d_epa_order, nc);
     A(ctx->d_gjk_work, 4 * np); // one survivor list per shape-kind class
-    A(ctx->d_gjk_carry, np);
     // persistent EPA grid: enough resident threads to fill the machine, never more than the work
     {
         int gjk_per_sm = 0;
@@ -622,7 +623,7 @@ int pk_destroy(pk_ctx *ctx)
                    ctx->d_merge_flag,  ctx->d_pkeys[0],     ctx->d_pkeys[1],    ctx->d_hit,          ctx->d_out_index,
                    ctx->d_scan_tiles,  ctx->d_simplices,    ctx->d_contacts[0], ctx->d_contacts[1],  ctx->d_valid,
                    ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order,    ctx->d_gjk_work,
-                   ctx->d_epa_spill,   ctx->d_epa_fallback2, ctx->d_epa_init};
+                   ctx->d_epa_spill,   ctx->d_epa_fallback2, ctx->d_epa_init,     ctx->d_gjk_carry};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
