@@ -154,10 +154,12 @@ struct EsSlab
         double2 *q = reinterpret_cast<double2 *>(vpos + 4 * i);
         q[0] = make_double2(p.x, p.y);
         q[1] = make_double2(p.z, 0.0);
+#ifndef PK_EC_EXPERIMENT_NO_VAB // timing experiment only (results wrong): what do the pa / pb stores cost in L2 footprint
         double2 *v = reinterpret_cast<double2 *>(vab + 6 * i);
         v[0] = make_double2(s.pa.x, s.pa.y);
         v[1] = make_double2(s.pa.z, s.pb.x);
         v[2] = make_double2(s.pb.y, s.pb.z);
+#endif
     }
     __device__ __forceinline__ void set_adj(int f, int e, int to) const
     {
@@ -840,7 +842,9 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                         for (int c = mc; 4 * c < hi; ++c)
                         {
                             const float4 k4 = c < ES_KEYS / 4 ? kq[c] : reinterpret_cast<const float4 *>(sl.gkey)[c - ES_KEYS / 4];
-                            if (!(k4.x == m || k4.y == m || k4.z == m || k4.w == m)) continue; // most chunks
+#ifdef PK_EC_CAND_SKIP // A/B: skipping chunks without a match up front measured no faster (12.86 vs 13.00 ms without)
+                            if (!(k4.x == m || k4.y == m || k4.z == m || k4.w == m)) continue;
+#endif
                             const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
@@ -996,7 +1000,11 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                         {
                             const bool is_b = (w == 1) != swapped;
                             const ShapeView S = es_get_shape(shm, w, bodies);
+#ifdef PK_EC_SUPPORT_BIG_ALWAYS
+                            const d3 q = support<true>(S, is_b ? -mn : mn);
+#else
                             const d3 q = support<false>(S, is_b ? -mn : mn);
+#endif
                             if (is_b)
                                 sp.pb = q;
                             else
@@ -1119,7 +1127,8 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
                 shm.meta[t] = static_cast<uint32_t>(nverts) | (static_cast<uint32_t>(nfaces) << 8) | (heap ? EC_META_HEAP : 0u);
                 shm.bad[t] = 0u;
                 ++nverts;
-                // slots of the new faces in horizon (= push) order
+                // slots of the new faces in horizon (= push) order.  (A shorter loop for SCAN lanes — clear the lowest set
+                // bit of the first non-empty word — measured slower: EPA 12.9 → 14.2 ms.)
                 for (int e = 0; e < nh; ++e)
                 {
                     const int slot = take_slot();
