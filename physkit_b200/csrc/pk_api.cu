@@ -66,14 +66,14 @@ enum Counter
     C_EPA_OVERFLOW,
     C_SCAN_TOTAL,
     C_GJK_CURSOR,
-    C_CLASS_COUNT, // [3]
-    C_CLASS_FILL = C_CLASS_COUNT + 3, // [3]
-    C_EPA_FALLBACK = C_CLASS_FILL + 3, // [0] SCAN pairs started again in HEAP mode, [1] pairs epa_coop_kernel handed to epa_kernel
+    C_EPA_FALLBACK, // [0] SCAN pairs started again in HEAP mode, [1] pairs epa_coop_kernel handed to epa_kernel
     C_EPA_SCAN_CURSOR = C_EPA_FALLBACK + 3, // work cursor of epa_coop_kernel
     C_EPA_FB_CURSOR = C_EPA_SCAN_CURSOR + 3, // work cursor of epa_kernel on the second fallback list
     C_EPA_REASONS = C_EPA_FALLBACK + 10, // [6] debug builds (PK_ES_REASONS)
-    C_GJK_CLASS = 32, // [4] GJK prefilter survivors per shape-kind class
-    C_COUNT = 40
+    C_GJK_CLASS = 32,   // [4] GJK prefilter survivors per shape-kind class
+    C_CLASS_COUNT = 40, // [EPA_CLASSES] GJK hits per EPA cost class
+    C_CLASS_FILL = 50,  // [EPA_CLASSES]
+    C_COUNT = 60
 };
 
 } // namespace

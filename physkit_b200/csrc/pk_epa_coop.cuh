@@ -425,7 +425,7 @@ epa_init_kernel(const SimplexRec *__restrict__ simplices, const unsigned long lo
         }
         o.topo[f] = w | (static_cast<unsigned long long>(f) << 48); // creation serial
     }
-    o.flags = (bad ? EPA_INIT_BAD : 0u) | (((r->n >> 8) & 3u) == 0u ? EPA_INIT_POLY : 0u);
+    o.flags = (bad ? EPA_INIT_BAD : 0u) | (((r->n >> 8) & 0xFu) == 0u ? EPA_INIT_POLY : 0u);
     init[s] = o;
 }
 

@@ -293,6 +293,18 @@ __device__ __forceinline__ void load_pair(const uint64_t *__restrict__ keys, con
     }
 }
 
+constexpr uint32_t EPA_CLASSES = 9;
+__device__ __forceinline__ uint32_t epa_cost_class(const ShapeView &A, const ShapeView &B)
+{
+    const bool big_a = A.kind == KIND_HULL && A.nverts > HULL_PREFILTER_MIN, big_b = B.kind == KIND_HULL && B.nverts > HULL_PREFILTER_MIN;
+    const uint32_t smooth = (A.kind == KIND_SPHERE || big_a ? 1u : 0u) + (B.kind == KIND_SPHERE || big_b ? 1u : 0u);
+    if (smooth == 0u) return 0u;
+    const uint32_t nva = big_a ? A.nverts : 0u, nvb = big_b ? B.nverts : 0u;
+    const uint32_t nv = nva > nvb ? nva : nvb;
+    const uint32_t bucket = nv <= 48u ? 0u : (nv <= 96u ? 1u : (nv <= 192u ? 2u : 3u));
+    return 1u + 4u * (smooth - 1u) + bucket;
+}
+
 // K7a-0: the first two support evaluations of gjk_collision for every pair (collision.cpp:170-182).
 // 59 % of C3's candidate pairs end right there (second support makes no progress ⇒ separated); they get
 // hit = 0 and never reach the divergent part.  All lanes do identical work, so this kernel runs at full
@@ -371,7 +383,7 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
            const uint32_t *__restrict__ pair_b, const uint32_t *__restrict__ work, uint64_t work_stride,
            const unsigned long long *__restrict__ work_count /*[4]*/, uint8_t *__restrict__ hit,
            SimplexRec *__restrict__ simplices, unsigned long long *__restrict__ hit_count, uint64_t hit_capacity,
-           unsigned long long *__restrict__ class_count /*[3]*/, const GjkCarry *__restrict__ carry /*[npairs]*/)
+           unsigned long long *__restrict__ class_count /*[EPA_CLASSES]*/, const GjkCarry *__restrict__ carry /*[npairs]*/)
 {
     uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     int c = 0; // class lists back to back: thread w works on entry w of their concatenation
@@ -435,12 +447,11 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
                     d[2] = make_double2(s.pt[i].pb.y, s.pt[i].pb.z);
                 }
             }
-            // EPA cost class = number of "smooth" shapes of the pair: spheres and hulls with many vertices
-            // need many more EPA iterations than boxes, and their face distances practically never tie
-            // (epa_scan_kernel: classes 1-2 heap-free pop, class 0 exact heap)
-            const bool smooth_a = A.kind == KIND_SPHERE || (A.kind == KIND_HULL && A.nverts > HULL_PREFILTER_MIN);
-            const bool smooth_b = B.kind == KIND_SPHERE || (B.kind == KIND_HULL && B.nverts > HULL_PREFILTER_MIN);
-            const uint32_t cls = (smooth_a ? 1u : 0u) + (smooth_b ? 1u : 0u);
+            // EPA cost class: 0 = no "smooth" shape (spheres and many-vertex hulls need many more EPA iterations than
+            // boxes, and their face distances practically never tie: epa_coop_kernel pops those heap-free, class 0
+            // from the exact heap); 1-4 = one smooth shape, 5-8 = two, within each by the size of the largest hull
+            // (spheres: none), so that the lanes of a warp scan hulls of similar length
+            const uint32_t cls = epa_cost_class(A, B);
             {
                 const unsigned peers = __match_any_sync(__activemask(), cls);
                 if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(class_count + cls, static_cast<unsigned long long>(__popc(peers)));
@@ -773,20 +784,29 @@ epa_order_kernel(const SimplexRec *__restrict__ simplices, const unsigned long l
 {
     unsigned long long nhits = *hit_count_ptr;
     if (nhits > hit_capacity) nhits = hit_capacity;
-    const unsigned long long c2 = class_count[2], c1 = class_count[1];
+    __shared__ unsigned long long base[EPA_CLASSES]; // heaviest class first
+    if (threadIdx.x == 0)
+    {
+        unsigned long long run = 0;
+        for (int c = static_cast<int>(EPA_CLASSES) - 1; c >= 0; --c)
+        {
+            base[c] = run;
+            run += class_count[c];
+        }
+    }
+    __syncthreads();
     for (unsigned long long s = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; s < nhits;
          s += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
     {
-        const uint32_t cls = (simplices[s].n >> 8) & 3u;
-        const unsigned long long base = (cls == 2) ? 0ull : (cls == 1 ? c2 : c2 + c1);
-        // one atomic per (warp, class) instead of one per hit: three hot addresses would serialise
+        const uint32_t cls = (simplices[s].n >> 8) & 0xFu;
+        // one atomic per (warp, class) instead of one per hit: a few hot addresses would serialise
         const unsigned peers = __match_any_sync(__activemask(), cls);
         const int lane = threadIdx.x & 31;
         const int leader = __ffs(peers) - 1;
         unsigned long long first = 0;
         if (lane == leader) first = atomicAdd(class_fill + cls, static_cast<unsigned long long>(__popc(peers)));
         first = __shfl_sync(peers, first, leader);
-        const unsigned long long pos = base + first + __popc(peers & ((1u << lane) - 1u));
+        const unsigned long long pos = base[cls] + first + __popc(peers & ((1u << lane) - 1u));
         if (pos < hit_capacity) order[pos] = static_cast<uint32_t>(s);
     }
 }

@@ -46,7 +46,8 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const doubl
     // order; `arrival` picks pair order (0), reversed (1) or a fixed pseudo-random permutation (2)
     std::vector<uint8_t> hit(n, 0);
     std::vector<SimplexRec> simplices(capacity + 1);
-    unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // [0] hits, [1..3] class counts, [4] valid, [5] dropped
+    unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // [0] hits, [4] valid, [5] dropped
+    unsigned long long class_counts[EPA_CLASSES] = {};
     std::vector<uint64_t> seq(n);
     for (uint64_t k = 0; k < n; ++k) seq[k] = arrival == 1 ? n - 1 - k : k;
     if (arrival == 2)
@@ -101,10 +102,8 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const doubl
             r.v[i][0] = s.pt[i].pa.x; r.v[i][1] = s.pt[i].pa.y; r.v[i][2] = s.pt[i].pa.z;
             r.v[i][3] = s.pt[i].pb.x; r.v[i][4] = s.pt[i].pb.y; r.v[i][5] = s.pt[i].pb.z;
         }
-        const bool smooth_a = A.kind == KIND_SPHERE || (A.kind == KIND_HULL && A.nverts > HULL_PREFILTER_MIN);
-        const bool smooth_b = B.kind == KIND_SPHERE || (B.kind == KIND_HULL && B.nverts > HULL_PREFILTER_MIN);
-        const uint32_t cls = (smooth_a ? 1u : 0u) + (smooth_b ? 1u : 0u);
-        counters[1 + cls]++;
+        const uint32_t cls = epa_cost_class(A, B);
+        class_counts[cls]++;
         r.n = static_cast<uint32_t>(s.n) | (cls << 8);
         r.pair = static_cast<uint32_t>(k);
     }
@@ -121,10 +120,16 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const doubl
     }
     std::vector<uint32_t> order(nhits + 1);
     {
-        uint64_t fill[3] = {counters[3] + counters[2], counters[3], 0}; // class 0 after 2 and 1; class 1 after 2
+        uint64_t fill[EPA_CLASSES]; // heaviest class first, as epa_order_kernel
+        uint64_t run = 0;
+        for (int c = static_cast<int>(EPA_CLASSES) - 1; c >= 0; --c)
+        {
+            fill[c] = run;
+            run += class_counts[c];
+        }
         for (uint64_t s = 0; s < nhits; ++s)
         {
-            const uint32_t cls = (simplices[s].n >> 8) & 3u;
+            const uint32_t cls = (simplices[s].n >> 8) & 0xFu;
             if (fill[cls] < nhits) order[fill[cls]] = static_cast<uint32_t>(s);
             fill[cls]++;
         }
@@ -204,9 +209,9 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const doubl
         stats[2] = fbc[1];      // handed to epa_kernel
         stats[3] = counters[4]; // valid contacts
         stats[4] = counters[5]; // dropped: no room for the contact
-        stats[5] = counters[1];
-        stats[6] = counters[2];
-        stats[7] = counters[3];
+        stats[5] = class_counts[0]; // no smooth shape
+        stats[6] = class_counts[1] + class_counts[2] + class_counts[3] + class_counts[4]; // one
+        stats[7] = class_counts[5] + class_counts[6] + class_counts[7] + class_counts[8]; // two
     }
     return 0;
 }
