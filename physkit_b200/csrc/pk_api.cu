@@ -11,6 +11,7 @@
 #include "pk_common.cuh"
 #include "pk_narrowphase.cuh"
 #include "pk_epa_coop.cuh"
+#include "pk_gjk_filter.cuh"
 #include "pk_manifold.cuh"
 #include "pk_dynamics.cuh"
 #include "pk_ray.cuh"
@@ -85,6 +86,13 @@ struct pk_ctx
     cudaStream_t copy_stream = nullptr; // pk_collide: pair keys go to the host while the narrowphase runs
     cudaEvent_t ev_sorted = nullptr, ev_pairs_copied = nullptr;
     bool want_host_results = false, pairs_in_flight = false;
+    // pk_collide_resident sizes the grids of the pair sort and the narrowphase from the previous step's pair count and
+    // lets the kernels read the count itself on the device (no host round trip in the middle of the step); a step
+    // whose count outgrew the guess is run again with the count read back
+    bool exact_prefilter = false; // PK_GJK_EXACT_PREFILTER at pk_create
+    int filter_iters = PK_GJK_FILTER_ITERS; // PK_GJK_FILTER_ITERS at pk_create
+    uint64_t pair_guess = 0;
+    bool pair_guess_valid = false, pairs_read_back = false;
     bool contacts_mirrored = false; // pk_collide: the EPA kernels stored this step's contact records into h_contacts as well
     std::string last_error;
     int sm_count = 0;
@@ -319,7 +327,9 @@ int bits_for(uint64_t n) // bits needed to represent values < n
 }
 
 // LSD radix sort over the listed byte shifts; returns the index (0/1) of the buffer holding the result.
-int radix_sort(pk_ctx *ctx, uint64_t *keys[2], uint32_t *vals[2], uint64_t n, const std::vector<int> &shifts, int *result, int lowbits = 0)
+// n_dev != nullptr: the element count lives on the device (≤ n, for which the grid is sized).
+int radix_sort(pk_ctx *ctx, uint64_t *keys[2], uint32_t *vals[2], uint64_t n, const std::vector<int> &shifts, int *result, int lowbits = 0,
+               const unsigned long long *n_dev = nullptr)
 {
     int cur = 0;
     uint32_t ntiles = div_up(n, SORT_TILE);
@@ -330,14 +340,14 @@ int radix_sort(pk_ctx *ctx, uint64_t *keys[2], uint32_t *vals[2], uint64_t n, co
     }
     for (int shift : shifts)
     {
-        radix_hist_kernel<<<ntiles, SORT_THREADS, 0, ctx->stream>>>(keys[cur], n, shift, lowbits, ctx->d_tile_hist, ntiles);
+        radix_hist_kernel<<<ntiles, SORT_THREADS, 0, ctx->stream>>>(keys[cur], n, n_dev, shift, lowbits, ctx->d_tile_hist, ntiles);
         radix_scan_kernel<<<256, SORT_THREADS, 0, ctx->stream>>>(ctx->d_tile_hist, ntiles, ctx->d_digit_total);
         if (vals)
             radix_scatter_kernel<true><<<ntiles, SORT_THREADS, 0, ctx->stream>>>(
-                keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, lowbits, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
+                keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, n_dev, shift, lowbits, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
         else
             radix_scatter_kernel<false><<<ntiles, SORT_THREADS, 0, ctx->stream>>>(
-                keys[cur], nullptr, keys[cur ^ 1], nullptr, n, shift, lowbits, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
+                keys[cur], nullptr, keys[cur ^ 1], nullptr, n, n_dev, shift, lowbits, ctx->d_tile_hist, ntiles, ctx->d_digit_total);
         ctx->launches += 3;
         cur ^= 1;
     }
@@ -397,31 +407,45 @@ BodyArrays body_arrays(pk_ctx *ctx)
 
 // GJK → scan → EPA over npairs pairs given either as sorted keys or as explicit index arrays.
 // Leaves contacts (slot order = pair order among GJK hits) in ctx->d_contacts[0], validity in d_valid.
+// npairs_dev != nullptr: the pair count lives on the device (≤ npairs, for which the grids are sized).
 int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, const uint32_t *d_b, uint64_t npairs,
-                    bool timed, ContactRec *mirror = nullptr)
+                    bool timed, ContactRec *mirror = nullptr, const unsigned long long *npairs_dev = nullptr)
 {
     PkRange range("pk: narrowphase (GJK, hit scan, EPA)");
     if (timed) cudaEventRecord(ctx->ev[ST_GJK], ctx->stream);
     if (npairs)
     {
-        // contexts with many-vertex hulls carry the first two support points from the prefilter to gjk_kernel
-        if (ctx->has_big_hulls && !ctx->d_gjk_carry)
-            PK_TRY(dev_alloc(ctx, &ctx->d_gjk_carry, ctx->cfg.max_pairs)); // 96 B per pair of capacity: only contexts that use it
-        if (ctx->has_big_hulls)
+        const uint32_t pair_blocks = div_up(npairs, 128);
+        auto gjk = [&](auto kernel, const GjkCarry *carry)
         {
-            gjk_prefilter_kernel<true><<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit, ctx->d_gjk_work,
-                                                                                    ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, ctx->d_gjk_carry);
-            gjk_kernel<true><<<div_up(npairs, PK_GJK_THREADS), PK_GJK_THREADS, 0, ctx->stream>>>(
+            kernel<<<div_up(npairs, PK_GJK_THREADS), PK_GJK_THREADS, 0, ctx->stream>>>(
                 body_arrays(ctx), d_keys, d_a, d_b, ctx->d_gjk_work, ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, ctx->d_hit, ctx->d_simplices,
-                ctx->d_counters + C_HITS, ctx->max_contacts, ctx->d_counters + C_CLASS_COUNT, ctx->d_gjk_carry);
+                ctx->d_counters + C_HITS, ctx->max_contacts, ctx->d_counters + C_CLASS_COUNT, carry);
+        };
+        if (!ctx->exact_prefilter && !ctx->has_big_hulls)
+        {
+            // misses are settled in FP32 with a certificate (pk_gjk_filter.cuh); what is left runs the reference's
+            // iteration from its first support
+            gjk_filter_kernel<<<pair_blocks, 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, npairs_dev, ctx->d_hit, ctx->d_gjk_work,
+                                                                    ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, ctx->filter_iters);
+            gjk(gjk_kernel<false, false>, nullptr);
+        }
+        else if (ctx->has_big_hulls)
+        {
+            // many-vertex hulls: the reference's first two supports for every pair in FP64, carried to gjk_kernel (see
+            // gjk_prefilter_kernel); pairs of analytic shapes are filtered in FP32 all the same
+            if (!ctx->d_gjk_carry) PK_TRY(dev_alloc(ctx, &ctx->d_gjk_carry, ctx->cfg.max_pairs)); // 96 B per pair of capacity
+            auto pre = ctx->exact_prefilter ? gjk_prefilter_kernel<true, false> : gjk_prefilter_kernel<true, true>;
+            pre<<<pair_blocks, 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, npairs_dev, ctx->d_hit, ctx->d_gjk_work, ctx->cfg.max_pairs,
+                                                      ctx->d_counters + C_GJK_CLASS, ctx->d_gjk_carry);
+            gjk(gjk_kernel<true, true>, ctx->d_gjk_carry);
         }
         else
         {
-            gjk_prefilter_kernel<false><<<div_up(npairs, 128), 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, ctx->d_hit, ctx->d_gjk_work,
-                                                                                     ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, nullptr);
-            gjk_kernel<false><<<div_up(npairs, PK_GJK_THREADS), PK_GJK_THREADS, 0, ctx->stream>>>(
-                body_arrays(ctx), d_keys, d_a, d_b, ctx->d_gjk_work, ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, ctx->d_hit, ctx->d_simplices,
-                ctx->d_counters + C_HITS, ctx->max_contacts, ctx->d_counters + C_CLASS_COUNT, nullptr);
+            // PK_GJK_EXACT_PREFILTER=1: round 1's form, kept for A/B runs
+            gjk_prefilter_kernel<false><<<pair_blocks, 128, 0, ctx->stream>>>(body_arrays(ctx), d_keys, d_a, d_b, npairs, npairs_dev, ctx->d_hit, ctx->d_gjk_work,
+                                                                              ctx->cfg.max_pairs, ctx->d_counters + C_GJK_CLASS, nullptr);
+            gjk(gjk_kernel<false, false>, nullptr);
         }
         ctx->launches += 2;
     }
@@ -429,9 +453,9 @@ int run_narrowphase(pk_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_a, co
     if (npairs)
     {
         uint32_t nt = div_up(npairs, SCAN_TILE);
-        flag_tile_sum_kernel<<<nt, 256, 0, ctx->stream>>>(ctx->d_hit, npairs, ctx->d_scan_tiles);
+        flag_tile_sum_kernel<<<nt, 256, 0, ctx->stream>>>(ctx->d_hit, npairs, npairs_dev, ctx->d_scan_tiles);
         tile_sum_scan_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_scan_tiles, nt, ctx->d_counters + C_SCAN_TOTAL);
-        flag_scan_apply_kernel<<<nt, 256, 0, ctx->stream>>>(ctx->d_hit, npairs, ctx->d_scan_tiles, ctx->d_out_index);
+        flag_scan_apply_kernel<<<nt, 256, 0, ctx->stream>>>(ctx->d_hit, npairs, npairs_dev, ctx->d_scan_tiles, ctx->d_out_index);
         ctx->launches += 3;
     }
     if (timed) cudaEventRecord(ctx->ev[ST_EPA], ctx->stream);
@@ -495,6 +519,23 @@ int read_counters(pk_ctx *ctx)
                             cudaMemcpyDeviceToHost, ctx->stream));
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     return PK_OK;
+}
+
+// The step can be repeated after pk_reserve_pairs: the pair set is a function of the per-body state (stored box,
+// last_move, create), which this attempt has already brought up to date for this epoch; a second pass over the
+// same poses in the same epoch leaves it as it is (every true box lies inside its stored box now), so only
+// num_moved of the repeated step differs (0).
+int pair_overflow(pk_ctx *ctx, pk_step_result *out, uint64_t npairs)
+{
+    if (out)
+    {
+        std::memset(out, 0, sizeof(*out));
+        out->pairs_required = npairs;
+        out->num_moved = ctx->h_counters[C_MOVED];
+        out->step_index = static_cast<uint32_t>(ctx->epoch);
+    }
+    ctx->last_error = "candidate pairs exceed pk_config.max_pairs (pk_reserve_pairs, then repeat the step)";
+    return PK_E_PAIR_OVERFLOW;
 }
 
 } // namespace
@@ -700,6 +741,8 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
         return PK_E_INVALID;
     }
     ctx->max_contacts = cfg->max_contacts ? cfg->max_contacts : cfg->max_pairs;
+    ctx->exact_prefilter = getenv("PK_GJK_EXACT_PREFILTER") != nullptr;
+    if (const char *e = getenv("PK_GJK_FILTER_ITERS")) ctx->filter_iters = atoi(e);
     auto fail = [&](int s)
     {
         pk_destroy(ctx);
@@ -1016,7 +1059,9 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
     cudaEventRecord(ctx->ev[ST_MORTON], s);
     ctx->tree_m = 0;
     ctx->tree_valid = true;
-    uint64_t npairs = 0;
+    uint64_t npairs = 0; // the pair count, or (speculate) the bound the grids are sized for
+    const unsigned long long *pairs_dev = nullptr;
+    const bool speculate = !ctx->want_host_results && ctx->pair_guess_valid && !ctx->pairs_read_back && !getenv("PK_SYNC_PAIRS");
     int pair_buf = 0;
     if (m >= 2)
     {
@@ -1044,23 +1089,17 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         ctx->launches += 4;
         PK_CUDA(cudaGetLastError());
         cudaEventRecord(ctx->ev[ST_PAIR_SORT], s);
-        PK_TRY(read_counters(ctx));
-        npairs = ctx->h_counters[C_PAIRS];
-        if (npairs > ctx->cfg.max_pairs)
+        if (speculate)
         {
-            if (out)
-            {
-                std::memset(out, 0, sizeof(*out));
-                out->pairs_required = npairs;
-                out->num_moved = ctx->h_counters[C_MOVED];
-                out->step_index = static_cast<uint32_t>(ctx->epoch);
-            }
-            // The step can be repeated after pk_reserve_pairs: the pair set is a function of the per-body state
-            // (stored box, last_move, create), which this attempt has already brought up to date for this epoch; a
-            // second pass over the same poses in the same epoch leaves it as it is (every true box lies inside its
-            // stored box now), so only num_moved of the repeated step differs (0).
-            ctx->last_error = "candidate pairs exceed pk_config.max_pairs (pk_reserve_pairs, then repeat the step)";
-            return PK_E_PAIR_OVERFLOW;
+            // grids for 1/8 more pairs than last step found (+64 Ki); the kernels read the count on the device
+            npairs = std::min<uint64_t>(ctx->cfg.max_pairs, ctx->pair_guess + ctx->pair_guess / 8 + 65536);
+            pairs_dev = ctx->d_counters + C_PAIRS;
+        }
+        else
+        {
+            PK_TRY(read_counters(ctx));
+            npairs = ctx->h_counters[C_PAIRS];
+            if (npairs > ctx->cfg.max_pairs) return pair_overflow(ctx, out, npairs);
         }
         if (npairs)
         {
@@ -1068,7 +1107,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
             int idbits = bits_for(n);
             std::vector<int> shifts;
             for (int b = 0; b < 2 * idbits; b += 8) shifts.push_back(b);
-            PK_TRY(radix_sort(ctx, ctx->d_pkeys, nullptr, npairs, shifts, &pair_buf, idbits));
+            PK_TRY(radix_sort(ctx, ctx->d_pkeys, nullptr, npairs, shifts, &pair_buf, idbits, pairs_dev));
         }
     }
     else
@@ -1109,8 +1148,32 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         mirror = reinterpret_cast<ContactRec *>(ctx->h_contacts);
         ctx->contacts_mirrored = true;
     }
-    PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true, mirror));
+    PK_TRY(run_narrowphase(ctx, ctx->d_pairs_sorted, nullptr, nullptr, npairs, true, mirror, pairs_dev));
     PK_TRY(read_counters(ctx));
+    if (getenv("PK_DEBUG"))
+        fprintf(stderr, "[pk] pairs %llu, to gjk_kernel %llu (%llu %llu %llu %llu), hits %llu\n", ctx->h_counters[C_PAIRS],
+                ctx->h_counters[C_GJK_CLASS] + ctx->h_counters[C_GJK_CLASS + 1] + ctx->h_counters[C_GJK_CLASS + 2] + ctx->h_counters[C_GJK_CLASS + 3],
+                ctx->h_counters[C_GJK_CLASS], ctx->h_counters[C_GJK_CLASS + 1], ctx->h_counters[C_GJK_CLASS + 2], ctx->h_counters[C_GJK_CLASS + 3],
+                ctx->h_counters[C_HITS]);
+    if (pairs_dev)
+    {
+        const uint64_t found = ctx->h_counters[C_PAIRS];
+        if (found > ctx->cfg.max_pairs) return pair_overflow(ctx, out, found);
+        if (found > npairs)
+        {
+            // more pairs than the grids were sized for: the same step again with the count read back (the pair set
+            // is a function of the per-body state, which this pass has brought up to date: see pair_overflow)
+            const unsigned long long moved = ctx->h_counters[C_MOVED];
+            ctx->pairs_read_back = true;
+            const int rc = pk_collide_resident(ctx, out);
+            ctx->pairs_read_back = false;
+            if (out) out->num_moved = moved;
+            return rc;
+        }
+        npairs = found;
+    }
+    ctx->pair_guess = npairs;
+    ctx->pair_guess_valid = true;
     uint64_t hits = ctx->h_counters[C_HITS];
     uint64_t valid = ctx->h_counters[C_VALID];
     uint64_t over = ctx->h_counters[C_EPA_OVERFLOW];
@@ -1127,9 +1190,9 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
     {
         // some GJK hits ended without a value in EPA (degenerate pad / exhausted heap / overflow)
         uint32_t nt = div_up(hits, SCAN_TILE);
-        flag_tile_sum_kernel<<<nt, 256, 0, s>>>(ctx->d_valid, hits, ctx->d_scan_tiles);
+        flag_tile_sum_kernel<<<nt, 256, 0, s>>>(ctx->d_valid, hits, nullptr, ctx->d_scan_tiles);
         tile_sum_scan_kernel<<<1, 256, 0, s>>>(ctx->d_scan_tiles, nt, nullptr);
-        flag_scan_apply_kernel<<<nt, 256, 0, s>>>(ctx->d_valid, hits, ctx->d_scan_tiles, ctx->d_valid_index);
+        flag_scan_apply_kernel<<<nt, 256, 0, s>>>(ctx->d_valid, hits, nullptr, ctx->d_scan_tiles, ctx->d_valid_index);
         compact_records_kernel<<<div_up(hits, 256), 256, 0, s>>>(ctx->d_valid, ctx->d_valid_index, hits,
                                                                  reinterpret_cast<const unsigned char *>(ctx->d_contacts[0]),
                                                                  reinterpret_cast<unsigned char *>(ctx->d_contacts[1]),
@@ -1622,9 +1685,9 @@ int pk_contact_rows_setup(pk_ctx *ctx, double dt, double gravity_norm, uint64_t 
         const ManifoldRec *man = ctx->d_man[ctx->man_cur];
         const uint32_t nt = div_up(slots, SCAN_TILE);
         solver_valid_kernel<<<div_up(slots, 256), 256, 0, s>>>(man, nman, ctx->d_pos, ctx->d_quat, ctx->d_sol_valid);
-        flag_tile_sum_kernel<<<nt, 256, 0, s>>>(ctx->d_sol_valid, slots, ctx->d_sol_tiles);
+        flag_tile_sum_kernel<<<nt, 256, 0, s>>>(ctx->d_sol_valid, slots, nullptr, ctx->d_sol_tiles);
         tile_sum_scan_kernel<<<1, 256, 0, s>>>(ctx->d_sol_tiles, nt, ctx->d_sol_total);
-        flag_scan_apply_kernel<<<nt, 256, 0, s>>>(ctx->d_sol_valid, slots, ctx->d_sol_tiles, ctx->d_sol_index);
+        flag_scan_apply_kernel<<<nt, 256, 0, s>>>(ctx->d_sol_valid, slots, nullptr, ctx->d_sol_tiles, ctx->d_sol_index);
         solver_compact_kernel<<<div_up(slots, 256), 256, 0, s>>>(ctx->d_sol_valid, ctx->d_sol_index, slots, ctx->d_sol_slot);
         // one thread per row; the grid covers the point count of the manifolds (≥ rows), surplus threads leave at once
         solver_rows_kernel<<<div_up(slots, 128), 128, 0, s>>>(man, ctx->d_sol_total, ctx->d_pos, ctx->d_quat, ctx->dyn, ctx->d_material,

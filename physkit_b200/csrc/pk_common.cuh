@@ -388,6 +388,15 @@ template <bool BIG = true> __device__ __forceinline__ d3 support(const ShapeView
     return rotate(s.q, bv) + s.p;
 }
 
+// An element count that lives on the device (a counter an earlier kernel of the step filled), bounded by the number
+// the grid was sized for; nullptr: the bound is the count.
+__device__ __forceinline__ uint64_t device_count(const unsigned long long *count, uint64_t cap)
+{
+    if (!count) return cap;
+    const unsigned long long v = *count;
+    return v < cap ? v : cap;
+}
+
 // 88-byte contact record, mirrors pk_contact of include/pk_collide.h.
 struct ContactRec
 {

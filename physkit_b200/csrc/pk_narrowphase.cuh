@@ -305,79 +305,12 @@ __device__ __forceinline__ uint32_t epa_cost_class(const ShapeView &A, const Sha
     return 1u + 4u * (smooth - 1u) + bucket;
 }
 
-// K7a-0: the first two support evaluations of gjk_collision for every pair (collision.cpp:170-182).
-// 59 % of C3's candidate pairs end right there (second support makes no progress ⇒ separated); they get
-// hit = 0 and never reach the divergent part.  All lanes do identical work, so this kernel runs at full
-// lane efficiency; survivors are appended to a work list and redone from scratch by gjk_kernel (the
-// two redundant supports cost less than carrying 120 bytes of state per survivor through HBM).
-// Survivors are listed per shape-kind class (bit 0: A is a sphere, bit 1: B is a sphere) so that the
-// lanes of a gjk_kernel warp run the same support code: with the pair list in key order a warp held a
-// random mix of sphere and box supports and executed both paths for every call.
-template <bool CARRY>
-__global__ void __launch_bounds__(128)
-gjk_prefilter_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
-                     const uint32_t *__restrict__ pair_b, uint64_t npairs, uint8_t *__restrict__ hit,
-                     uint32_t *__restrict__ work /*[4][work_stride]*/, uint64_t work_stride,
-                     unsigned long long *__restrict__ work_count /*[4]*/, GjkCarry *__restrict__ carry /*[npairs]*/)
-{
-    const uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    bool survive = false;
-    uint32_t cls = 0;
-    if (k < npairs)
-    {
-        uint32_t ia, ib;
-        load_pair(keys, pair_a, pair_b, k, ia, ib);
-        ShapeView A = load_shape(bodies, ia);
-        ShapeView B = load_shape(bodies, ib);
-        cls = (A.kind == KIND_SPHERE ? 1u : 0u) | (B.kind == KIND_SPHERE ? 2u : 0u);
-        const SupportPt s0 = minkowski_support<CARRY>(A, B, d3{1.0, 0.0, 0.0});
-        const d3 p0 = P(s0);
-        double2 *c = reinterpret_cast<double2 *>(carry + k);
-        if (sqnorm(p0) < 1e-12)
-        {
-            survive = true; // origin hit on the first point: a hit with a one-point simplex (collision.cpp:174)
-            if constexpr (CARRY)
-            {
-                c[0] = make_double2(s0.pa.x, s0.pa.y);
-                c[1] = make_double2(s0.pa.z, s0.pb.x);
-                c[2] = make_double2(s0.pb.y, s0.pb.z);
-                c[3] = make_double2(__longlong_as_double(0x7FF8000000000000ll), 0.0);
-            }
-        }
-        else
-        {
-            const d3 dir = -normalized(p0);
-            const SupportPt s1 = minkowski_support<CARRY>(A, B, dir);
-            survive = !(dot(P(s1), dir) <= 0.0); // collision.cpp:181-182
-            if (CARRY && survive)
-            {
-                c[0] = make_double2(s0.pa.x, s0.pa.y);
-                c[1] = make_double2(s0.pa.z, s0.pb.x);
-                c[2] = make_double2(s0.pb.y, s0.pb.z);
-                c[3] = make_double2(s1.pa.x, s1.pa.y);
-                c[4] = make_double2(s1.pa.z, s1.pb.x);
-                c[5] = make_double2(s1.pb.y, s1.pb.z);
-            }
-        }
-        if (!survive) hit[k] = 0;
-    }
-    // one atomic per (warp, class); dead lanes take a class of their own
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, survive ? cls : 4u);
-    if (survive)
-    {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(peers) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(work_count + cls, static_cast<unsigned long long>(__popc(peers)));
-        base = __shfl_sync(peers, base, leader);
-        work[cls * work_stride + base + __popc(peers & ((1u << lane) - 1u))] = static_cast<uint32_t>(k);
-    }
-}
-
 // One thread per surviving pair.  (A persistent-lane variant with per-lane refill was measured in r1
 // and lost: with a mean of 1.9 iterations per pair half the lanes refill every round and the set-up
 // path — two gathered body loads — then sits on the critical path of every round.)
-template <bool CARRY>
+// CARRY: resume from the two support points gjk_prefilter_kernel<true> left; otherwise from the first support.
+// BIG: the context holds hulls above HULL_PREFILTER_MIN vertices (support<BIG>).
+template <bool CARRY, bool BIG = CARRY>
 __global__ void __launch_bounds__(PK_GJK_THREADS, PK_GJK_MIN_BLOCKS)
 gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pair_a,
            const uint32_t *__restrict__ pair_b, const uint32_t *__restrict__ work, uint64_t work_stride,
@@ -416,17 +349,18 @@ gjk_kernel(BodyArrays bodies, const uint64_t *__restrict__ keys, const uint32_t 
         }
         else
         {
-            // cheap supports (spheres, boxes): evaluating the first two again costs less than carrying 96 bytes per
-            // survivor through HBM (measured: C3 2.44 against 2.67 ms)
-            s.pt[0] = minkowski_support<false>(A, B, d3{1.0, 0.0, 0.0});
+            // gjk_collision from its first support (after gjk_filter_kernel; after gjk_prefilter_kernel<false>, where
+            // evaluating two cheap supports again costs less than carrying 96 bytes per survivor through HBM)
+            s.pt[0] = minkowski_support<BIG>(A, B, d3{1.0, 0.0, 0.0});
             s.n = 1;
             h = true;
             const d3 p0 = P(s.pt[0]);
             if (!(sqnorm(p0) < 1e-12))
             {
-                s.pt[1] = minkowski_support<false>(A, B, -normalized(p0)); // passed the separation test in the prefilter
+                const d3 dir = -normalized(p0);
+                s.pt[1] = minkowski_support<BIG>(A, B, dir);
                 s.n = 2;
-                h = gjk_resume<false>(A, B, s);
+                h = !(dot(P(s.pt[1]), dir) <= 0.0) && gjk_resume<BIG>(A, B, s); // collision.cpp:181-182
             }
         }
     }

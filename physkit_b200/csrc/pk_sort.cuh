@@ -11,6 +11,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "pk_common.cuh"
+
 namespace pk
 {
 
@@ -18,6 +20,7 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 keys per block
+
 
 // Digit of a pass.  Pair keys are (min id << 32) | max id with ids below 2^b: their 2b significant bits sit in
 // two fields.  With lowbits = b the fields are packed next to each other before the digit is taken, so that
@@ -35,9 +38,10 @@ __device__ __forceinline__ uint64_t sort_index(uint64_t tile_base, int warp, int
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift, int lowbits, uint32_t *__restrict__ tile_hist,
-                  uint32_t ntiles)
+radix_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n_cap, const unsigned long long *__restrict__ n_dev, int shift, int lowbits,
+                  uint32_t *__restrict__ tile_hist, uint32_t ntiles)
 {
+    const uint64_t n = device_count(n_dev, n_cap);
     __shared__ uint32_t hist[256];
     hist[threadIdx.x] = 0;
     __syncthreads();
@@ -101,9 +105,11 @@ radix_scan_kernel(uint32_t *__restrict__ tile_hist, uint32_t ntiles, uint32_t *_
 template <bool HAS_VALS>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint64_t n, int shift, int lowbits,
-                     const uint32_t *__restrict__ tile_hist, uint32_t ntiles, const uint32_t *__restrict__ digit_total)
+                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint64_t n_cap,
+                     const unsigned long long *__restrict__ n_dev, int shift, int lowbits, const uint32_t *__restrict__ tile_hist,
+                     uint32_t ntiles, const uint32_t *__restrict__ digit_total)
 {
+    const uint64_t n = device_count(n_dev, n_cap);
     __shared__ uint32_t warp_cnt[SORT_WARPS][256];
     __shared__ uint32_t warp_sums[SORT_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -170,8 +176,10 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
 constexpr int SCAN_TILE = 4096;
 
 __global__ void __launch_bounds__(256)
-flag_tile_sum_kernel(const uint8_t *__restrict__ flags, uint64_t n, uint32_t *__restrict__ tile_sum)
+flag_tile_sum_kernel(const uint8_t *__restrict__ flags, uint64_t n_cap, const unsigned long long *__restrict__ n_dev,
+                     uint32_t *__restrict__ tile_sum)
 {
+    const uint64_t n = device_count(n_dev, n_cap);
     __shared__ uint32_t warp_sums[8];
     const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_TILE + threadIdx.x * 16ull;
     uint32_t c = 0;
@@ -206,9 +214,10 @@ tile_sum_scan_kernel(uint32_t *__restrict__ tile_sum, uint32_t ntiles, unsigned 
 }
 
 __global__ void __launch_bounds__(256)
-flag_scan_apply_kernel(const uint8_t *__restrict__ flags, uint64_t n, const uint32_t *__restrict__ tile_sum,
-                       uint32_t *__restrict__ out_index)
+flag_scan_apply_kernel(const uint8_t *__restrict__ flags, uint64_t n_cap, const unsigned long long *__restrict__ n_dev,
+                       const uint32_t *__restrict__ tile_sum, uint32_t *__restrict__ out_index)
 {
+    const uint64_t n = device_count(n_dev, n_cap);
     __shared__ uint32_t warp_sums[8];
     const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_TILE + threadIdx.x * 16ull;
     uint8_t f[16];

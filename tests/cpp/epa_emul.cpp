@@ -13,6 +13,7 @@ namespace pk
 unsigned long long g_ec_stats[16];
 }
 #include "../../physkit_b200/csrc/pk_epa_coop.cuh"
+#include "../../physkit_b200/csrc/pk_gjk_filter.cuh"
 
 using namespace pk;
 
@@ -23,6 +24,25 @@ extern "C" void emu_stats(unsigned long long *out, int reset)
         out[i] = pk::g_ec_stats[i];
         if (reset) pk::g_ec_stats[i] = 0;
     }
+}
+
+// certainly_separated (pk_gjk_filter.cuh) per pair on the host: out[k] = 1 when the FP32 filter would drop pair k
+extern "C" int emu_filter(const ShapeRec *shapes, uint64_t nshapes, const double *verts, uint64_t nverts_pool, const double *pos, const double *quat,
+                          const uint32_t *shape_id, const uint32_t *pa, const uint32_t *pb, uint64_t n, int iters, uint8_t *out)
+{
+    (void)nshapes;
+    std::vector<float4> vf(nverts_pool + 2);
+    for (uint64_t i = 0; i < nverts_pool; ++i)
+        vf[i] = make_float4(static_cast<float>(verts[3 * i]), static_cast<float>(verts[3 * i + 1]), static_cast<float>(verts[3 * i + 2]), 0.f);
+    BodyArrays ba;
+    ba.shapes = shapes;
+    ba.verts = verts;
+    ba.verts_f = vf.data();
+    ba.pos = pos;
+    ba.quat = quat;
+    ba.shape_id = shape_id;
+    for (uint64_t k = 0; k < n; ++k) out[k] = certainly_separated(load_shape(ba, pa[k]), load_shape(ba, pb[k]), iters) ? 1 : 0;
+    return 0;
 }
 
 extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const double *verts, uint64_t nverts_pool, const double *pos, const double *quat,

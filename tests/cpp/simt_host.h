@@ -134,6 +134,7 @@ inline void __syncwarp(unsigned mask = SIMT_FULL)
 inline void __syncthreads() { std::abort(); } // not used by the kernels under test
 
 template <class T> inline T __ldg(const T *p) { return *p; }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }

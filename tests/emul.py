@@ -27,7 +27,7 @@ def available() -> bool:
 
 def build(force: bool = False) -> str:
     deps = [SRC, os.path.join(ROOT, "tests", "cpp", "simt_host.h")] + [
-        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_narrowphase.cuh", "pk_epa_coop.cuh")
+        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_narrowphase.cuh", "pk_epa_coop.cuh", "pk_gjk_filter.cuh")
     ]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
@@ -94,3 +94,21 @@ def gjk_epa_pairs(specs, pos, quat, shape_id, pair_a, pair_b, capacity=None, mir
         raise RuntimeError(f"emu_gjk_epa failed: {rc}")
     names = ["gjk_hits", "restarted_in_heap_mode", "handed_to_epa_kernel", "valid", "dropped", "class0", "class1", "class2"]
     return hit, out, dict(zip(names, (int(x) for x in stats)))
+
+
+def filter_pairs(specs, pos, quat, shape_id, pair_a, pair_b, iters=2):
+    """→ dropped[n] u8: 1 where gjk_filter_kernel's per-pair decision (certainly_separated, FP32) is "separated"."""
+    lib = C.CDLL(build())
+    tab, pool = shape_table(specs)
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+    quat = np.ascontiguousarray(quat, dtype=np.float64).reshape(-1, 4)
+    sid = np.ascontiguousarray(shape_id, dtype=np.uint32)
+    pa = np.ascontiguousarray(pair_a, dtype=np.uint32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.uint32)
+    out = np.zeros(len(pa), dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emu_filter(p(tab), C.c_uint64(len(tab)), p(pool), C.c_uint64(len(pool)), p(pos), p(quat), p(sid), p(pa), p(pb), C.c_uint64(len(pa)),
+                        C.c_int(iters), p(out))
+    if rc != 0:
+        raise RuntimeError(f"emu_filter failed: {rc}")
+    return out

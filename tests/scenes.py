@@ -264,3 +264,71 @@ def random_pairs_scene(n_pairs, seed, kinds=("obb", "sphere", "hull", "aabb"), s
             shapes.append(("hull", pts))
     sc = Scene(shapes, pos, quat, np.arange(2 * n_pairs))
     return sc, np.arange(0, 2 * n_pairs, 2, dtype=np.uint32), np.arange(1, 2 * n_pairs, 2, dtype=np.uint32)
+
+
+def _quat_matrix(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def near_touching_scene(n_pairs, seed, kinds=("obb", "sphere", "hull", "bighull", "meshbox", "aabb"), scales=(1e-3, 1.0, 1e3),
+                        far=1e4):
+    """Pairs (2k, 2k+1) whose gap along a random axis u — B's centre is put at cA + u·(h_A(u) + h_B(−u) + gap) — runs
+    through 0, ±1e-12 … ±1e-1 times the pair's size: grazing contacts and grazing misses, which a filter with a margin
+    must hand to the exact iteration.  Pairs live up to `far` from the origin at three size scales."""
+    rng = SplitMix64(seed)
+    gaps = np.concatenate([[0.0], *[[g, -g] for g in 10.0 ** np.arange(-12, 0)]])
+    quat = rng.quats(2 * n_pairs)
+    kind_pick = rng.randint(2 * n_pairs, len(kinds))
+    centre = rng.uniform(-far, far, n_pairs, 3)
+    axis = rng.uniform(-1.0, 1.0, n_pairs, 3)
+    axis /= np.linalg.norm(axis, axis=1)[:, None]
+    axis[::5] = np.eye(3)[np.arange(len(axis[::5])) % 3]  # every fifth pair along a coordinate axis,
+    for p in range(1, n_pairs, 3):  # every third along a local axis of A (a face normal, if A is a box: vertex-face contacts)
+        axis[p] = _quat_matrix(quat[2 * p])[:, p % 3]
+    par = rng.uniform(0.2, 0.8, 2 * n_pairs, 3)
+    scale_pick = rng.randint(n_pairs, len(scales))
+    shapes, pos = [], np.zeros((2 * n_pairs, 3))
+    hval = np.zeros(2 * n_pairs)
+    for i in range(2 * n_pairs):
+        k = kinds[kind_pick[i]]
+        s = scales[scale_pick[i // 2]]
+        u = axis[i // 2] if i % 2 == 0 else -axis[i // 2]
+        R = _quat_matrix(quat[i])
+        if k == "aabb":
+            R = np.eye(3)
+        l = R.T @ u
+        if k in ("obb", "aabb", "meshbox"):
+            h = par[i] * s
+            hval[i] = np.abs(l) @ h
+            if k == "obb":
+                shapes.append(("obb", h))
+            elif k == "meshbox":
+                shapes.append(("hull", np.array([[h[0] if (0x66 >> j) & 1 else -h[0], h[1] if (0xCC >> j) & 1 else -h[1], h[2] if j >= 4 else -h[2]] for j in range(8)])))
+            else:
+                shapes.append(("aabb", h))  # corners filled in below, once the centre is known
+        elif k == "sphere":
+            hval[i] = par[i, 0] * s
+            shapes.append(("sphere", par[i, 0] * s))
+        else:
+            sub = SplitMix64(seed * 7919 + i)
+            nv = 4 + int(sub.randint(1, 29)[0]) if k == "hull" else 40 + int(sub.randint(1, 160)[0])
+            uu = sub.u01(nv, 2)
+            z = 2.0 * uu[:, 0] - 1.0
+            t = 2.0 * math.pi * uu[:, 1]
+            sq = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+            pts = np.stack([sq * np.cos(t), sq * np.sin(t), z], axis=1) * par[i] * s
+            hval[i] = (pts @ l).max()
+            shapes.append(("hull", pts))
+    for p in range(n_pairs):
+        size = hval[2 * p] + hval[2 * p + 1]
+        pos[2 * p] = centre[p]
+        pos[2 * p + 1] = centre[p] + axis[p] * (size + gaps[(p * 7 + p // 25) % len(gaps)] * size)
+    for i in range(2 * n_pairs):
+        if shapes[i][0] == "aabb":
+            h = shapes[i][1]
+            shapes[i] = ("aabb", pos[i] - h, pos[i] + h)
+    sc = Scene(shapes, pos, quat, np.arange(2 * n_pairs))
+    return sc, np.arange(0, 2 * n_pairs, 2, dtype=np.uint32), np.arange(1, 2 * n_pairs, 2, dtype=np.uint32)

@@ -349,3 +349,32 @@ def test_pair_overflow_is_recoverable():
     assert total_tries >= 2  # the pairs overflowed, then the contacts
     big.close()
     small.close()
+
+
+def test_resident_steps_without_the_mid_step_read_back():
+    """pk_collide_resident sizes the pair sort and the narrowphase from the previous step's pair count and reads the
+    count on the device.  Pair counts that grow slowly, jump by far more than the 1/8 + 64 Ki of slack (the step is run
+    again with the count read back), shrink and drop to nothing must give what pk_collide gives, step after step."""
+    from gpu_util import make_context
+
+    sc = scene_c3(side=44)  # 85 k bodies, ~1.2 M pairs at spacing 0.8
+    ref = make_context(sc, max_pairs=12_000_000, mode=pk.MODE_WORLD)
+    res = make_context(sc, max_pairs=12_000_000, mode=pk.MODE_WORLD)
+    centre = sc.pos.mean(axis=0)
+    counts = []
+    for step, scale in enumerate([1.0, 1.0, 0.99, 0.98, 0.62, 0.63, 1.0, 1.0, 40.0, 1.0]):
+        pos = centre + (sc.pos - centre) * scale + 0.01 * step
+        disp = np.zeros_like(pos)
+        for c in (ref, res):
+            c.upload(pos, sc.quat, disp, sc.shape_id, sc.flags)
+        r0 = ref.collide(allow_epa_overflow=True)
+        r1 = res.collide_resident(allow_epa_overflow=True)
+        counts.append(int(r1.num_pairs))
+        assert (r1.num_pairs, r1.num_contacts, r1.num_moved, r1.step_index) == (r0.num_pairs, r0.num_contacts, r0.num_moved, r0.step_index)
+        res.fetch()
+        assert np.array_equal(res.pairs(), ref.pairs())
+        assert np.array_equal(res.contacts().view(np.uint8), ref.contacts().view(np.uint8))
+    assert counts[0] == 0 and counts[1] > 1_000_000  # (the first step of a world reports no pairs)
+    assert counts[4] > 2 * counts[3] + 65536 and counts[8] == 0 and counts[9] > 1_000_000, counts
+    ref.close()
+    res.close()

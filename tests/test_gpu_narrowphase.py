@@ -223,3 +223,37 @@ def test_prefiltered_hull_support_with_exact_ties_bit_exact():
     pa, pb = np.arange(0, 2 * n, 2, dtype=np.uint32), np.arange(1, 2 * n, 2, dtype=np.uint32)
     hit, out, st = _batch_vs_oracle(sc, pa, pb)
     assert 0.2 < hit.mean() < 0.95
+
+
+@pytest.mark.parametrize("seed,far", [(31, 1e2), (32, 1e4), (33, 1e6)])
+def test_grazing_pairs_bit_exact(seed, far):
+    """Misses are settled in FP32 with a margin (pk_gjk_filter.cuh); whatever is closer than the margin must reach the
+    exact iteration.  Pairs whose gap runs through 0, ±1e-12 … ±1e-1 of their size, all shape kinds, sizes 1e-3 … 1e3,
+    up to `far` from the origin (where FP32 world coordinates would be off by far more than the gap): hit flags and
+    contacts as the oracle's."""
+    from scenes import near_touching_scene
+
+    sc, pa, pb = near_touching_scene(20_000, seed, far=far)
+    hit, out, st = _batch_vs_oracle(sc, pa, pb)
+    assert 0.03 < hit.mean() < 0.5
+
+
+def test_filter_and_exact_prefilter_agree_on_c3(monkeypatch):
+    """The FP32 filter against round 1's FP64 two-support prefilter (PK_GJK_EXACT_PREFILTER=1) on a C3 step: same pair
+    set, same contacts, bit for bit."""
+    from gpu_util import make_context
+    import physkit_b200 as pk
+
+    sc = scene_c3(side=40)
+    a = make_context(sc, max_pairs=2_000_000, mode=pk.MODE_WORLD)
+    monkeypatch.setenv("PK_GJK_EXACT_PREFILTER", "1")
+    b = make_context(sc, max_pairs=2_000_000, mode=pk.MODE_WORLD)
+    monkeypatch.delenv("PK_GJK_EXACT_PREFILTER")
+    for c in (a, b):
+        c.collide()  # (the first step of a world reports no pairs)
+        c.update_pose(sc.pos + 0.05)
+    ra, rb = a.collide(), b.collide()
+    assert ra.num_pairs == rb.num_pairs > 500_000 and ra.num_contacts == rb.num_contacts > 50_000
+    assert np.array_equal(a.contacts().view(np.uint8), b.contacts().view(np.uint8))
+    a.close()
+    b.close()
