@@ -74,6 +74,7 @@ enum Counter
     C_GJK_CLASS = 32,   // [4] GJK prefilter survivors per shape-kind class
     C_CLASS_COUNT = 40, // [EPA_CLASSES] GJK hits per EPA cost class
     C_CLASS_FILL = 50,  // [EPA_CLASSES]
+    C_ROW_OVERFLOW = 59, // pairs that found the row of their lower id full (overlap_kernel<ROWS>)
     C_COUNT = 60
 };
 
@@ -129,6 +130,9 @@ struct pk_ctx
     NodeF *d_nodes = nullptr;
     uint32_t *d_right = nullptr, *d_range_last = nullptr, *d_root = nullptr;
     int32_t *d_merge_flag = nullptr;
+    // pair rows (overlap_kernel<ROWS>): partners with a larger id, per body; rows_off: a row overflowed once, LIST form from then on
+    uint32_t *d_row_count = nullptr, *d_rows = nullptr, *d_row_tiles = nullptr;
+    bool rows_off = false;
     uint64_t *d_pkeys[2] = {nullptr, nullptr};
     uint64_t *d_pairs_sorted = nullptr; // points into d_pkeys
 
@@ -538,6 +542,20 @@ int pair_overflow(pk_ctx *ctx, pk_step_result *out, uint64_t npairs)
     return PK_E_PAIR_OVERFLOW;
 }
 
+// The same step once more, with the pair count read back in the middle and (rows_off) the pairs as a sorted list: the
+// pair set is a function of the per-body state, which the first pass has brought up to date (see pair_overflow), so the
+// second pass finds the same pairs; only its num_moved (0) is not the step's.
+int repeat_step(pk_ctx *ctx, pk_step_result *out, bool rows_off)
+{
+    const unsigned long long moved = ctx->h_counters[C_MOVED];
+    if (rows_off) ctx->rows_off = true;
+    ctx->pairs_read_back = true;
+    const int rc = pk_collide_resident(ctx, out);
+    ctx->pairs_read_back = false;
+    if (out) out->num_moved = moved;
+    return rc;
+}
+
 } // namespace
 
 extern "C"
@@ -664,7 +682,8 @@ int pk_destroy(pk_ctx *ctx)
                    ctx->d_merge_flag,  ctx->d_pkeys[0],     ctx->d_pkeys[1],    ctx->d_hit,          ctx->d_out_index,
                    ctx->d_scan_tiles,  ctx->d_simplices,    ctx->d_contacts[0], ctx->d_contacts[1],  ctx->d_valid,
                    ctx->d_valid_index, ctx->d_slabs,       ctx->d_epa_order,    ctx->d_gjk_work,
-                   ctx->d_epa_spill,   ctx->d_epa_fallback2, ctx->d_epa_init,     ctx->d_gjk_carry};
+                   ctx->d_epa_spill,   ctx->d_epa_fallback2, ctx->d_epa_init,     ctx->d_gjk_carry,
+                   ctx->d_row_count,   ctx->d_rows,         ctx->d_row_tiles};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -789,6 +808,10 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     A(ctx->d_range_last, nb);
     A(ctx->d_root, 1);
     A(ctx->d_merge_flag, nb);
+    A(ctx->d_row_count, nb);
+    A(ctx->d_rows, nb * PAIR_ROW);
+    A(ctx->d_row_tiles, div_up(nb, ROWS_TILE) + 1);
+    ctx->rows_off = getenv("PK_PAIR_RADIX") != nullptr;
     if ((s = alloc_pair_buffers(ctx)) != PK_OK) return fail(s);
 #undef A
     if (cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_counters), C_COUNT * sizeof(unsigned long long),
@@ -1082,10 +1105,21 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
         cudaEventRecord(ctx->ev[ST_OVERLAP], s);
         uint32_t p_begin = static_cast<uint32_t>(static_cast<uint64_t>(m) * ctx->cfg.shard_rank / ctx->cfg.shard_count);
         uint32_t p_end = static_cast<uint32_t>(static_cast<uint64_t>(m) * (ctx->cfg.shard_rank + 1) / ctx->cfg.shard_count);
+        const bool use_rows = !ctx->rows_off;
         if (p_end > p_begin)
-            overlap_kernel<<<div_up(p_end - p_begin, OVERLAP_THREADS), OVERLAP_THREADS, 0, s>>>(ctx->d_nodes, ctx->d_leaves, m, p_begin, p_end, mode_query,
-                                                                       ctx->d_pkeys[0], ctx->cfg.max_pairs,
-                                                                       ctx->d_counters + C_PAIRS);
+        {
+            const uint32_t blocks = div_up(p_end - p_begin, OVERLAP_THREADS);
+            PairRows pr{ctx->d_row_count, ctx->d_rows, ctx->d_counters + C_ROW_OVERFLOW};
+            if (use_rows)
+            {
+                cudaMemsetAsync(ctx->d_row_count, 0, static_cast<size_t>(n) * sizeof(uint32_t), s);
+                overlap_kernel<true><<<blocks, OVERLAP_THREADS, 0, s>>>(ctx->d_nodes, ctx->d_leaves, m, p_begin, p_end, mode_query, ctx->d_pkeys[0],
+                                                                        ctx->cfg.max_pairs, ctx->d_counters + C_PAIRS, pr);
+            }
+            else
+                overlap_kernel<false><<<blocks, OVERLAP_THREADS, 0, s>>>(ctx->d_nodes, ctx->d_leaves, m, p_begin, p_end, mode_query, ctx->d_pkeys[0],
+                                                                         ctx->cfg.max_pairs, ctx->d_counters + C_PAIRS, pr);
+        }
         ctx->launches += 4;
         PK_CUDA(cudaGetLastError());
         cudaEventRecord(ctx->ev[ST_PAIR_SORT], s);
@@ -1100,8 +1134,20 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
             PK_TRY(read_counters(ctx));
             npairs = ctx->h_counters[C_PAIRS];
             if (npairs > ctx->cfg.max_pairs) return pair_overflow(ctx, out, npairs);
+            if (ctx->h_counters[C_ROW_OVERFLOW]) return repeat_step(ctx, out, true);
         }
-        if (npairs)
+        if (npairs && use_rows && p_end > p_begin)
+        {
+            // the rows one after the other, each sorted: ascending keys (pk_broadphase.cuh, K6 ROWS)
+            const uint32_t nt = div_up(n, ROWS_TILE);
+            pair_rows_sum_kernel<<<nt, ROWS_TILE, 0, s>>>(ctx->d_row_count, n, ctx->d_row_tiles);
+            tile_sum_scan_kernel<<<1, 256, 0, s>>>(ctx->d_row_tiles, nt, nullptr);
+            pair_rows_emit_kernel<<<nt, ROWS_TILE, 0, s>>>(ctx->d_row_count, ctx->d_rows, n, ctx->d_row_tiles, ctx->d_pkeys[1], ctx->cfg.max_pairs);
+            ctx->launches += 4;
+            pair_buf = 1;
+            PK_CUDA(cudaGetLastError());
+        }
+        else if (npairs)
         {
             // (min id, max id) fields packed to 2·idbits significant bits: ceil(2·idbits / 8) passes
             int idbits = bits_for(n);
@@ -1159,17 +1205,8 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
     {
         const uint64_t found = ctx->h_counters[C_PAIRS];
         if (found > ctx->cfg.max_pairs) return pair_overflow(ctx, out, found);
-        if (found > npairs)
-        {
-            // more pairs than the grids were sized for: the same step again with the count read back (the pair set
-            // is a function of the per-body state, which this pass has brought up to date: see pair_overflow)
-            const unsigned long long moved = ctx->h_counters[C_MOVED];
-            ctx->pairs_read_back = true;
-            const int rc = pk_collide_resident(ctx, out);
-            ctx->pairs_read_back = false;
-            if (out) out->num_moved = moved;
-            return rc;
-        }
+        // more pairs than the grids were sized for, or a full row: the same step again with the count read back
+        if (found > npairs || ctx->h_counters[C_ROW_OVERFLOW]) return repeat_step(ctx, out, ctx->h_counters[C_ROW_OVERFLOW] != 0);
         npairs = found;
     }
     ctx->pair_guess = npairs;

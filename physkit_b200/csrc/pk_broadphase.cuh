@@ -24,6 +24,7 @@
 #pragma once
 
 #include "pk_common.cuh"
+#include "pk_sort.cuh"
 
 namespace pk
 {
@@ -456,10 +457,54 @@ rope_kernel(uint32_t m, NodeF *nodes, const uint32_t *__restrict__ right_child, 
 constexpr int OVERLAP_THREADS = 128;
 constexpr int OVERLAP_STAGE = 128; // pair keys staged per warp before one reservation in the global list
 
+// Where the pairs go.  LIST: appended to out_keys in the order they are found; a radix sort brings them into key order
+// (K6).  ROWS: the pair (lo id, hi id) is dropped into the row of its lo id — row_count[lo] is bumped, rows[lo][slot] =
+// hi — and pair_rows_emit_kernel writes the rows out one after the other, each sorted: key order without a sort of the
+// whole list, because a body has a few dozen partners at most.  A row that overflows (PAIR_ROW partners with a larger
+// id) is counted in row_overflow; the host then repeats the step in LIST form.
+constexpr uint32_t PAIR_ROW = 64;
+struct PairRows
+{
+    uint32_t *row_count;              // [n], zeroed before the launch
+    uint32_t *rows;                   // [n][PAIR_ROW]
+    unsigned long long *row_overflow; // pairs that found their row full
+};
+
+template <bool ROWS>
+__device__ __forceinline__ void overlap_flush(const uint64_t *my_stage, int fill, int lane, uint64_t *__restrict__ out_keys, uint64_t capacity,
+                                              unsigned long long *__restrict__ pair_counter, const PairRows &pr)
+{
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(pair_counter, static_cast<unsigned long long>(fill));
+    if constexpr (ROWS)
+    {
+        unsigned over = 0;
+        for (int i = lane; i < fill; i += 32)
+        {
+            const uint64_t key = my_stage[i];
+            const uint32_t lo = static_cast<uint32_t>(key >> 32);
+            const uint32_t slot = atomicAdd(pr.row_count + lo, 1u);
+            if (slot < PAIR_ROW)
+                pr.rows[static_cast<uint64_t>(lo) * PAIR_ROW + slot] = static_cast<uint32_t>(key);
+            else
+                ++over;
+        }
+        if (__any_sync(FULL, over != 0u) && over) atomicAdd(pr.row_overflow, static_cast<unsigned long long>(over));
+    }
+    else
+    {
+        base = __shfl_sync(FULL, base, 0);
+        for (int i = lane; i < fill; i += 32)
+            if (base + i < capacity) out_keys[base + i] = my_stage[i];
+    }
+}
+
+template <bool ROWS>
 __global__ void __launch_bounds__(OVERLAP_THREADS)
 overlap_kernel(const NodeF *__restrict__ nodes, const LeafRec *__restrict__ leaves, uint32_t m, uint32_t p_begin,
                uint32_t p_end, int mode_query, uint64_t *__restrict__ out_keys, uint64_t capacity,
-               unsigned long long *__restrict__ pair_counter)
+               unsigned long long *__restrict__ pair_counter, PairRows pr)
 {
     // Emission: a single global counter bumped once per pair was 71 % of this kernel's stall samples
     // (ncu r1).  Pairs are staged per warp in shared memory and the list is reserved in chunks.
@@ -533,11 +578,7 @@ overlap_kernel(const NodeF *__restrict__ nodes, const LeafRec *__restrict__ leav
             if (fill > OVERLAP_STAGE - 32)
             {
                 __syncwarp();
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(pair_counter, static_cast<unsigned long long>(fill));
-                base = __shfl_sync(FULL, base, 0);
-                for (int i = lane; i < fill; i += 32)
-                    if (base + i < capacity) out_keys[base + i] = my_stage[i];
+                overlap_flush<ROWS>(my_stage, fill, lane, out_keys, capacity, pair_counter, pr);
                 __syncwarp();
                 fill = 0;
             }
@@ -546,12 +587,66 @@ overlap_kernel(const NodeF *__restrict__ nodes, const LeafRec *__restrict__ leav
     if (fill)
     {
         __syncwarp();
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(pair_counter, static_cast<unsigned long long>(fill));
-        base = __shfl_sync(FULL, base, 0);
-        for (int i = lane; i < fill; i += 32)
-            if (base + i < capacity) out_keys[base + i] = my_stage[i];
+        overlap_flush<ROWS>(my_stage, fill, lane, out_keys, capacity, pair_counter, pr);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 (ROWS): the rows written out in id order, each sorted — the pair keys in ascending order.
+//   pair_rows_sum_kernel   partners per tile of 256 bodies   → tile_sum_scan_kernel (pk_sort.cuh)
+//   pair_rows_emit_kernel  one thread per body: its row into local memory, insertion sort (a row holds 14 ids on
+//                          average in BASELINE C3), keys (id << 32 | partner) from the body's offset on
+// ---------------------------------------------------------------------------------------------
+constexpr int ROWS_TILE = 256;
+static_assert(ROWS_TILE == SORT_THREADS, "block_exclusive_scan_256");
+
+__global__ void __launch_bounds__(ROWS_TILE)
+pair_rows_sum_kernel(const uint32_t *__restrict__ row_count, uint32_t n, uint32_t *__restrict__ tile_sum)
+{
+    __shared__ uint32_t warp_sums[ROWS_TILE / 32];
+    const uint32_t i = blockIdx.x * ROWS_TILE + threadIdx.x;
+    uint32_t c = i < n ? row_count[i] : 0u;
+    c = c < PAIR_ROW ? c : PAIR_ROW;
+    uint32_t tot;
+    block_exclusive_scan_256(c, warp_sums, &tot);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(ROWS_TILE)
+pair_rows_emit_kernel(const uint32_t *__restrict__ row_count, const uint32_t *__restrict__ rows, uint32_t n,
+                      const uint32_t *__restrict__ tile_sum /* scanned */, uint64_t *__restrict__ out_keys, uint64_t capacity)
+{
+    __shared__ uint32_t warp_sums[ROWS_TILE / 32];
+    const uint32_t i = blockIdx.x * ROWS_TILE + threadIdx.x;
+    uint32_t c = i < n ? row_count[i] : 0u;
+    c = c < PAIR_ROW ? c : PAIR_ROW;
+    uint32_t tot;
+    const uint64_t off = static_cast<uint64_t>(tile_sum[blockIdx.x]) + block_exclusive_scan_256(c, warp_sums, &tot);
+    if (c == 0u) return;
+    uint32_t v[PAIR_ROW];
+    const uint4 *row = reinterpret_cast<const uint4 *>(rows + static_cast<uint64_t>(i) * PAIR_ROW);
+    for (uint32_t k = 0; k < c; k += 4)
+    {
+        const uint4 q = __ldcs(row + (k >> 2));
+        v[k] = q.x;
+        v[k + 1] = q.y;
+        v[k + 2] = q.z;
+        v[k + 3] = q.w;
+    }
+    for (uint32_t k = 1; k < c; ++k)
+    {
+        const uint32_t x = v[k];
+        uint32_t j = k;
+        while (j > 0 && v[j - 1] > x)
+        {
+            v[j] = v[j - 1];
+            --j;
+        }
+        v[j] = x;
+    }
+    const uint64_t hi = static_cast<uint64_t>(i) << 32;
+    for (uint32_t k = 0; k < c; ++k)
+        if (off + k < capacity) out_keys[off + k] = hi | v[k];
 }
 
 // Static bodies never query and are never updated, so two static bodies can never pair

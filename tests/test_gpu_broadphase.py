@@ -378,3 +378,47 @@ def test_resident_steps_without_the_mid_step_read_back():
     assert counts[4] > 2 * counts[3] + 65536 and counts[8] == 0 and counts[9] > 1_000_000, counts
     ref.close()
     res.close()
+
+
+def test_pair_rows_overflow_falls_back_to_the_sorted_list(monkeypatch):
+    """The pairs of a step are collected in per-body rows of 64 partners (pk_broadphase.cuh, ROWS) and written out row by
+    row; a body with more partners of a larger id than a row holds — a ground slab under 300 bodies, with the lowest
+    id — makes the step run again with the pair list sorted by the radix sort.  Same pairs and contacts as the oracle
+    and as a context that never uses rows (PK_PAIR_RADIX=1), on the step that overflows, on the ones after it, through
+    pk_collide and through pk_collide_resident."""
+    from gpu_util import make_context
+
+    rng = SplitMix64(77)
+    nb = 300
+    shapes = [("obb", [40.0, 40.0, 0.5])] + [("sphere", 0.4), ("obb", [0.3, 0.4, 0.5])]
+    pos = np.zeros((nb + 1, 3))
+    pos[1:, :2] = rng.uniform(-30.0, 30.0, nb, 2)
+    pos[1:, 2] = 0.8
+    quat = rng.quats(nb + 1)
+    quat[0] = [0, 0, 0, 1]
+    sid = np.array([0] + [1 + (k % 2) for k in range(nb)], dtype=np.uint32)
+    sc = Scene(shapes, pos, quat, sid)
+    rows = make_context(sc, max_pairs=100_000, mode=pk.MODE_WORLD)
+    res = make_context(sc, max_pairs=100_000, mode=pk.MODE_WORLD)
+    monkeypatch.setenv("PK_PAIR_RADIX", "1")
+    radix = make_context(sc, max_pairs=100_000, mode=pk.MODE_WORLD)
+    monkeypatch.delenv("PK_PAIR_RADIX")
+    w = oracle.World(sc.shapes)
+    for step in range(4):
+        p = sc.pos + 0.02 * step
+        disp = np.zeros_like(p)
+        w.step(p, sc.quat, disp, sc.shape_id, sc.flags)
+        for c in (rows, res, radix):
+            c.upload(p, sc.quat, disp, sc.shape_id, sc.flags)
+        r0, r1 = radix.collide(), rows.collide()
+        r2 = res.collide_resident()
+        res.fetch()
+        assert (r0.num_pairs, r0.num_contacts, r0.num_moved) == (r1.num_pairs, r1.num_contacts, r1.num_moved) == (r2.num_pairs, r2.num_contacts, r2.num_moved)
+        assert np.array_equal(rows.pairs(), w.pairs())
+        if step:
+            assert r0.num_pairs > nb  # the slab against everything, and some neighbours
+        for c in (rows, res):
+            assert np.array_equal(c.pairs(), radix.pairs())
+            assert np.array_equal(c.contacts().view(np.uint8), radix.contacts().view(np.uint8))
+    for c in (rows, res, radix):
+        c.close()
