@@ -87,9 +87,9 @@ struct pk_ctx
     cudaStream_t copy_stream = nullptr; // pk_collide: pair keys go to the host while the narrowphase runs
     cudaEvent_t ev_sorted = nullptr, ev_pairs_copied = nullptr;
     bool want_host_results = false, pairs_in_flight = false;
-    // pk_collide_resident sizes the grids of the pair sort and the narrowphase from the previous step's pair count and
-    // lets the kernels read the count itself on the device (no host round trip in the middle of the step); a step
-    // whose count outgrew the guess is run again with the count read back
+    // pk_collide / pk_collide_resident size the grids of the pair sort and the narrowphase (and the copy of the pair keys
+    // to the host) from the previous step's pair count and let the kernels read the count itself on the device (no host
+    // round trip in the middle of the step); a step whose count outgrew the guess is run again with the count read back
     bool exact_prefilter = false; // PK_GJK_EXACT_PREFILTER at pk_create
     int filter_iters = PK_GJK_FILTER_ITERS; // PK_GJK_FILTER_ITERS at pk_create
     uint64_t pair_guess = 0;
@@ -1084,7 +1084,7 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
     ctx->tree_valid = true;
     uint64_t npairs = 0; // the pair count, or (speculate) the bound the grids are sized for
     const unsigned long long *pairs_dev = nullptr;
-    const bool speculate = !ctx->want_host_results && ctx->pair_guess_valid && !ctx->pairs_read_back && !getenv("PK_SYNC_PAIRS");
+    const bool speculate = ctx->pair_guess_valid && ctx->pair_guess > 0 && !ctx->pairs_read_back && !getenv("PK_SYNC_PAIRS");
     int pair_buf = 0;
     if (m >= 2)
     {
@@ -1167,7 +1167,8 @@ int pk_collide_resident(pk_ctx *ctx, pk_step_result *out)
     if (ctx->want_host_results && npairs)
     {
         // pk_collide: the sorted pair keys are final here; ship them to the host on a second stream while
-        // the narrowphase (which only reads them) runs
+        // the narrowphase (which only reads them) runs (npairs may be the bound of a count still on the device: the
+        // keys past the count are never looked at)
         PK_TRY(ensure_host_pairs(ctx, npairs));
         cudaEventRecord(ctx->ev_sorted, s);
         cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sorted, 0);
