@@ -226,6 +226,7 @@ struct pk_ctx
     unsigned long long *h_comm_counts = nullptr; // pinned
     ContactRec *d_gather = nullptr;              // room for comm_size blocks of gather_stride records
     uint64_t gather_stride = 0;
+    uint64_t gather_guess = 0; // largest per-rank count of the previous exchange (0: none yet)
     cudaEvent_t ev_comm[2]{};
 };
 
@@ -2256,12 +2257,33 @@ int pk_comm_allgather_contacts(pk_ctx *ctx, pk_gathered_contacts *out)
     cudaStream_t s = ctx->stream;
     const int N = ctx->comm_size;
     cudaEventRecord(ctx->ev_comm[0], s);
-    // (1) every rank's count.  This rank's is on the host already (the step read it); the others' come through a
-    // one-word all-gather, and the block size of (2) has to be known on the host: one small synchronisation.
+    // Every rank's count (a one-word all-gather straight from the step's counter) and the records, straight from the
+    // contact buffer the EPA kernels wrote (no staging copy), in blocks of `stride` records; what a block holds beyond
+    // its rank's count is unspecified.  The block size must be the same on every rank and known before the counts are:
+    // it is taken from the previous exchange — the largest count seen then, plus an eighth — and both all-gathers go
+    // out as one group with one synchronisation at the end.  Only when some rank outgrew the guess (or on the first
+    // exchange) are the records gathered a second time, in blocks of the largest count.
+    auto ensure_gather = [&](uint64_t records) -> int
+    {
+        if (records <= ctx->gather_stride) return PK_OK;
+        if (ctx->d_gather) cudaFree(ctx->d_gather);
+        ctx->d_gather = nullptr;
+        ctx->gather_stride = 0;
+        const uint64_t cap = std::min<uint64_t>(ctx->max_contacts, records + records / 4 + 1024);
+        PK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_gather), static_cast<size_t>(N) * cap * sizeof(ContactRec)));
+        ctx->gather_stride = cap;
+        return PK_OK;
+    };
+    const uint64_t guess = ctx->gather_guess ? std::min<uint64_t>(ctx->max_contacts, ctx->gather_guess + ctx->gather_guess / 8 + 1024) : 0;
+    if (guess) PK_TRY(ensure_gather(guess));
     ctx->h_comm_counts[N] = ctx->num_contacts;
     PK_CUDA(cudaMemcpyAsync(ctx->d_comm_counts + N, ctx->h_comm_counts + N, sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    PK_NCCL(api.GroupStart());
     PK_NCCL(api.AllGather(ctx->d_comm_counts + N, ctx->d_comm_counts, 1, ncclUint64, ctx->comm, s));
+    if (guess) PK_NCCL(api.AllGather(ctx->d_contacts_final, ctx->d_gather, guess * sizeof(ContactRec), ncclChar, ctx->comm, s));
+    PK_NCCL(api.GroupEnd());
     PK_CUDA(cudaMemcpyAsync(ctx->h_comm_counts, ctx->d_comm_counts, static_cast<size_t>(N) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    cudaEventRecord(ctx->ev_comm[1], s);
     PK_CUDA(cudaStreamSynchronize(s));
     uint64_t stride = 0, total = 0;
     for (int r = 0; r < N; ++r)
@@ -2269,25 +2291,21 @@ int pk_comm_allgather_contacts(pk_ctx *ctx, pk_gathered_contacts *out)
         stride = std::max<uint64_t>(stride, ctx->h_comm_counts[r]);
         total += ctx->h_comm_counts[r];
     }
-    // (2) the records, straight from the contact buffer the EPA kernels wrote (no staging copy), in blocks of `stride`
-    // records (the largest count; what a block holds beyond its rank's count is unspecified)
     if (stride > ctx->max_contacts)
     {
         ctx->last_error = "a rank holds more contacts than this context's max_contacts: ranks must be created with equal capacities";
         return PK_E_STATE;
     }
-    if (stride > ctx->gather_stride)
+    ctx->gather_guess = stride;
+    if (stride > guess)
     {
-        if (ctx->d_gather) cudaFree(ctx->d_gather);
-        ctx->d_gather = nullptr;
-        ctx->gather_stride = 0;
-        const uint64_t cap = std::min<uint64_t>(ctx->max_contacts, stride + stride / 4 + 1024);
-        PK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_gather), static_cast<size_t>(N) * cap * sizeof(ContactRec)));
-        ctx->gather_stride = cap;
+        PK_TRY(ensure_gather(stride));
+        PK_NCCL(api.AllGather(ctx->d_contacts_final, ctx->d_gather, stride * sizeof(ContactRec), ncclChar, ctx->comm, s));
+        cudaEventRecord(ctx->ev_comm[1], s);
+        PK_CUDA(cudaStreamSynchronize(s));
     }
-    if (stride) PK_NCCL(api.AllGather(ctx->d_contacts_final, ctx->d_gather, stride * sizeof(ContactRec), ncclChar, ctx->comm, s));
-    cudaEventRecord(ctx->ev_comm[1], s);
-    PK_CUDA(cudaStreamSynchronize(s));
+    else
+        stride = guess; // the blocks that were gathered
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev_comm[0], ctx->ev_comm[1]);
     out->d_records = ctx->d_gather;

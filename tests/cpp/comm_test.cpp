@@ -1,8 +1,11 @@
 // The exchange step of a world that spans GPUs (include/pk_collide.h, pk_comm_*), driven from C++ the way a host engine
 // would: N contexts on the N devices it finds (one host thread per rank, ranks of ONE communicator), poses uploaded by
-// slice and all-gathered, one step, contact records all-gathered.  With one device it is a communicator of one rank.
-// Checks: every rank ends up with the same N blocks; block r is rank r's own contact list; the union of the ranks'
-// pair sets has no duplicates.  Exit code: 0 ok, 3 no CUDA device / no NCCL, 1 failure.
+// slice and all-gathered, one step, contact records all-gathered — four rounds: the first exchange (block size from
+// the counts), a second of about the same size (block size guessed from the first), a much denser scene (the guess is
+// outgrown: the records go out a second time) and the first scene again (the guess is far too large).  With one device
+// it is a communicator of one rank.
+// Checks per round: every rank ends up with the same N blocks; block r is rank r's own contact list; the union of the
+// ranks' pair sets has no duplicates.  Exit code: 0 ok, 3 no CUDA device / no NCCL, 1 failure.
 #include "pk_collide.h"
 
 #include <algorithm>
@@ -58,8 +61,17 @@ int main()
         sid[i] = i & 1u;
     }
     std::vector<int> status(N, 0);
-    std::vector<std::vector<pk_contact>> own(N), gathered(N);
-    std::vector<std::vector<uint64_t>> counts(N), keys(N);
+    constexpr int ROUNDS = 4;
+    const double shift[ROUNDS] = {0.05, 0.08, 0.0, 0.05}, scale[ROUNDS] = {1.0, 1.0, 0.75, 1.0};
+    std::vector<std::vector<pk_contact>> own_r[ROUNDS], gathered_r[ROUNDS];
+    std::vector<std::vector<uint64_t>> counts_r[ROUNDS], keys_r[ROUNDS];
+    for (int k = 0; k < ROUNDS; ++k)
+    {
+        own_r[k].resize(N);
+        gathered_r[k].resize(N);
+        counts_r[k].resize(N);
+        keys_r[k].resize(N);
+    }
     auto rank_main = [&](int r)
     {
         auto fail = [&](const char *what, int s)
@@ -91,33 +103,41 @@ int main()
             return fail("pk_bodies_upload", s);
         pk_step_result res;
         if ((s = pk_collide_resident(ctx, &res)) != PK_OK) return fail("first step", s); // creates the bodies: no pairs yet
-        // the step proper: this rank moves ITS slice of the bodies, the others arrive over NVLink
+        // the steps proper: this rank moves ITS slice of the bodies, the others arrive over NVLink
         uint32_t first = 0, count = 0;
         pk_comm_pose_slice(ctx, &first, &count);
         std::vector<double> moved(3 * count);
-        for (uint32_t i = 0; i < 3 * count; ++i) moved[i] = pos[3 * first + i] + 0.05;
-        if ((s = pk_bodies_update_pose(ctx, moved.data(), nullptr, nullptr, first, count)) != PK_OK) return fail("update_pose", s);
-        if ((s = pk_comm_allgather_poses(ctx, PK_POSE_POS)) != PK_OK) return fail("allgather_poses", s);
-        if ((s = pk_collide(ctx, &res)) != PK_OK) return fail("pk_collide", s);
-        const pk_contact *recs = nullptr;
-        uint64_t nrec = 0;
-        pk_contacts(ctx, &recs, &nrec);
-        own[r].assign(recs, recs + nrec);
-        const uint64_t *pk = nullptr;
-        uint64_t npk = 0;
-        pk_pairs(ctx, &pk, &npk);
-        keys[r].assign(pk, pk + npk);
-        pk_gathered_contacts g;
-        if ((s = pk_comm_allgather_contacts(ctx, &g)) != PK_OK) return fail("allgather_contacts", s);
-        counts[r].assign(g.counts, g.counts + g.num_ranks);
-        gathered[r].resize(g.total);
-        uint64_t off = 0;
-        for (uint32_t q = 0; q < g.num_ranks; ++q)
+        for (int k = 0; k < ROUNDS; ++k)
         {
-            if (g.counts[q])
-                pk_memcpy_d2h(ctx, gathered[r].data() + off, static_cast<const pk_contact *>(g.d_records) + q * g.stride_records,
-                              g.counts[q] * sizeof(pk_contact));
-            off += g.counts[q];
+            auto &own = own_r[k];
+            auto &gathered = gathered_r[k];
+            auto &counts = counts_r[k];
+            auto &keys = keys_r[k];
+            for (uint32_t i = 0; i < 3 * count; ++i) moved[i] = pos[3 * first + i] * scale[k] + shift[k];
+            if ((s = pk_bodies_update_pose(ctx, moved.data(), nullptr, nullptr, first, count)) != PK_OK) return fail("update_pose", s);
+            if ((s = pk_comm_allgather_poses(ctx, PK_POSE_POS)) != PK_OK) return fail("allgather_poses", s);
+            if ((s = pk_collide(ctx, &res)) != PK_OK) return fail("pk_collide", s);
+            const pk_contact *recs = nullptr;
+            uint64_t nrec = 0;
+            pk_contacts(ctx, &recs, &nrec);
+            own[r].assign(recs, recs + nrec);
+            const uint64_t *pk = nullptr;
+            uint64_t npk = 0;
+            pk_pairs(ctx, &pk, &npk);
+            keys[r].assign(pk, pk + npk);
+            pk_gathered_contacts g;
+            if ((s = pk_comm_allgather_contacts(ctx, &g)) != PK_OK) return fail("allgather_contacts", s);
+            counts[r].assign(g.counts, g.counts + g.num_ranks);
+            gathered[r].resize(g.total);
+            uint64_t off = 0;
+            for (uint32_t q = 0; q < g.num_ranks; ++q)
+            {
+                if (g.counts[q] > g.stride_records) return fail("a block shorter than its count", 1);
+                if (g.counts[q])
+                    pk_memcpy_d2h(ctx, gathered[r].data() + off, static_cast<const pk_contact *>(g.d_records) + q * g.stride_records,
+                                  g.counts[q] * sizeof(pk_contact));
+                off += g.counts[q];
+            }
         }
         pk_destroy(ctx);
     };
@@ -126,29 +146,41 @@ int main()
     for (auto &t : th) t.join();
     for (int r = 0; r < N; ++r)
         if (status[r]) return 1;
-    uint64_t total = 0;
-    std::vector<uint64_t> all_keys;
-    for (int r = 0; r < N; ++r)
+    uint64_t totals[ROUNDS];
+    for (int k = 0; k < ROUNDS; ++k)
     {
-        total += own[r].size();
-        all_keys.insert(all_keys.end(), keys[r].begin(), keys[r].end());
-        if (counts[r] != counts[0]) return std::printf("FAIL: ranks disagree about the counts\n"), 1;
-        if (counts[r][r] != own[r].size()) return std::printf("FAIL: count of rank %d\n", r), 1;
-    }
-    std::sort(all_keys.begin(), all_keys.end());
-    if (std::adjacent_find(all_keys.begin(), all_keys.end()) != all_keys.end()) return std::printf("FAIL: a pair on two ranks\n"), 1;
-    if (total < 200) return std::printf("FAIL: only %llu contacts\n", static_cast<unsigned long long>(total)), 1;
-    for (int r = 0; r < N; ++r)
-    {
-        if (gathered[r].size() != total) return std::printf("FAIL: rank %d gathered %zu of %llu\n", r, gathered[r].size(), static_cast<unsigned long long>(total)), 1;
-        uint64_t off = 0;
-        for (int q = 0; q < N; ++q)
+        auto &own = own_r[k];
+        auto &gathered = gathered_r[k];
+        auto &counts = counts_r[k];
+        auto &keys = keys_r[k];
+        uint64_t total = 0;
+        std::vector<uint64_t> all_keys;
+        for (int r = 0; r < N; ++r)
         {
-            if (own[q].size() && std::memcmp(gathered[r].data() + off, own[q].data(), own[q].size() * sizeof(pk_contact)) != 0)
-                return std::printf("FAIL: rank %d's copy of rank %d's records differs\n", r, q), 1;
-            off += own[q].size();
+            total += own[r].size();
+            all_keys.insert(all_keys.end(), keys[r].begin(), keys[r].end());
+            if (counts[r] != counts[0]) return std::printf("FAIL: ranks disagree about the counts\n"), 1;
+            if (counts[r][r] != own[r].size()) return std::printf("FAIL: count of rank %d\n", r), 1;
         }
+        std::sort(all_keys.begin(), all_keys.end());
+        if (std::adjacent_find(all_keys.begin(), all_keys.end()) != all_keys.end()) return std::printf("FAIL: a pair on two ranks\n"), 1;
+        if (total < 200) return std::printf("FAIL: only %llu contacts\n", static_cast<unsigned long long>(total)), 1;
+        for (int r = 0; r < N; ++r)
+        {
+            if (gathered[r].size() != total)
+                return std::printf("FAIL: rank %d gathered %zu of %llu\n", r, gathered[r].size(), static_cast<unsigned long long>(total)), 1;
+            uint64_t off = 0;
+            for (int q = 0; q < N; ++q)
+            {
+                if (own[q].size() && std::memcmp(gathered[r].data() + off, own[q].data(), own[q].size() * sizeof(pk_contact)) != 0)
+                    return std::printf("FAIL: round %d, rank %d's copy of rank %d's records differs\n", k, r, q), 1;
+                off += own[q].size();
+            }
+        }
+        totals[k] = total;
+        std::printf("round %d: %zu pairs, %llu contacts gathered on every rank\n", k, all_keys.size(), static_cast<unsigned long long>(total));
     }
-    std::printf("comm ok: %d rank(s), %zu pairs, %llu contacts gathered on every rank\n", N, all_keys.size(), static_cast<unsigned long long>(total));
+    if (totals[2] < 2 * totals[1]) return std::printf("FAIL: the dense round did not outgrow the guessed block size\n"), 1;
+    std::printf("comm ok: %d rank(s), %d rounds\n", N, ROUNDS);
     return 0;
 }
