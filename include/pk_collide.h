@@ -237,7 +237,14 @@ int pk_bodies_update_pose(pk_ctx *ctx, const double *pos_xyz, const double *quat
  *                      EPA kernels themselves, so no copy waits for the end of the step (the buffer holds
  *                      max_contacts records, up to 2 GB; above that, or with PK_NO_MIRROR=1 in the environment,
  *                      the records are copied after the kernels).
- * Pairs are sorted ascending by key; contacts are sorted by key as well. */
+ * Pairs are sorted ascending by key; contacts are sorted by key as well.
+ * A step reads its counters back once, at its end: the kernels behind the broadphase take the number of candidate pairs
+ * from device memory and are launched for 9/8 of the previous step's count (+ 64 Ki).  A step that finds more pairs
+ * than that — or a body with more than 64 partners of a larger id, which the per-body pair rows do not hold — is run a
+ * second time inside the same call, with the count read back in the middle (and the pair list sorted by a radix sort);
+ * results, step_index and num_moved are those of the one step.  Switches for A/B runs, read from the environment at
+ * pk_create: PK_SYNC_PAIRS=1 (always read the count back; read per step), PK_PAIR_RADIX=1 (never use pair rows),
+ * PK_GJK_EXACT_PREFILTER=1 (round 1's FP64 prefilter instead of the FP32 miss filter), PK_GJK_FILTER_ITERS=n. */
 int pk_collide_resident(pk_ctx *ctx, pk_step_result *out);
 int pk_fetch_results(pk_ctx *ctx);
 int pk_collide(pk_ctx *ctx, pk_step_result *out);

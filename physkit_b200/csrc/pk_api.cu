@@ -675,6 +675,13 @@ int pk_destroy(pk_ctx *ctx)
     if (!ctx) return PK_E_INVALID;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+#ifdef PK_EC_TIMING
+    {
+        static unsigned long long h[8192][2];
+        if (cudaMemcpyFromSymbol(h, g_ec_times, sizeof(h)) == cudaSuccess)
+            for (int w = 0; w < ctx->epa_scan_blocks * (ES_THREADS / 32); ++w) printf("[ec] %d %llu %llu\n", w, h[w][0], h[w][1]);
+    }
+#endif
     void *dev[] = {ctx->d_verts_f, ctx->d_shapes,      ctx->d_verts,        ctx->d_pos,         ctx->d_quat,         ctx->d_disp,
                    ctx->d_shape_id,    ctx->d_world,        ctx->d_flags,       ctx->st.stored,      ctx->st.last_move,
                    ctx->st.create,     ctx->st.alive,       ctx->d_scene,       ctx->d_counters,     ctx->d_bkeys[0],

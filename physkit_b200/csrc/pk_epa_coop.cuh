@@ -40,12 +40,12 @@
 #pragma once
 
 #include "pk_narrowphase.cuh"
-#ifdef PK_EC_TIMING
-#include <cstdio>
-#endif
-
 namespace pk
 {
+
+#ifdef PK_EC_TIMING // debug build: globaltimer at entry and exit of every warp of the last launch (pk_destroy prints them)
+__device__ unsigned long long g_ec_times[8192][2];
+#endif
 
 constexpr int ES_THREADS = 64;
 constexpr int ES_SLOTS = 136; // live faces = 2V − 4 ≤ 132
@@ -1200,7 +1200,8 @@ __global__ void __launch_bounds__(ES_THREADS, PK_EC_MIN_BLOCKS) epa_coop_kernel(
     {
         unsigned long long now;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-        printf("[ec] %d %llu %llu\n", static_cast<int>(tid / 32), ec_t0, now);
+        g_ec_times[(tid / 32) & 8191][0] = ec_t0;
+        g_ec_times[(tid / 32) & 8191][1] = now;
     }
 #endif
 }
