@@ -68,10 +68,12 @@ constexpr int ES_HCAP = PK_ES_HCAP;        // HEAP mode: heap entries kept in sh
 constexpr int ES_DNEW = (ES_KEYS * 4 - ES_HCAP * 12) / 8; // HEAP mode: distances of the new faces, S2 → owner's pushes
 constexpr int ES_GKEYS = (ES_SLOTS - ES_KEYS + 3) / 4 * 4; // float keys of the slots beyond shared memory
 // per-thread slab: planes, topology, vertices, float keys beyond shared memory, heap entries beyond shared memory
+// A whole number of 128-byte lines: a slab shares no L2 line with its neighbours (20 272 → 20 352 bytes: EPA 12.8 → 12.55 ms,
+// DRAM reads 4.9 → 3.8 GB, writes 5.6 → 5.1 GB per launch).
 __host__ __device__ constexpr size_t es_slab_bytes()
 {
-    return static_cast<size_t>(ES_SLOTS) * (32 + 8) + static_cast<size_t>(ES_VERTS) * (32 + 48) + static_cast<size_t>(ES_GKEYS) * 4 +
-           static_cast<size_t>(ES_HEAP_MAX) * (8 + 4);
+    return (static_cast<size_t>(ES_SLOTS) * (32 + 8) + static_cast<size_t>(ES_VERTS) * (32 + 48) + static_cast<size_t>(ES_GKEYS) * 4 +
+            static_cast<size_t>(ES_HEAP_MAX) * (8 + 4) + 127) / 128 * 128;
 }
 
 // per-thread pop area: ES_KEYS floats (SCAN) or the top of the heap + the new faces' distances (HEAP)
