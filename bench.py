@@ -51,13 +51,23 @@ def measured_peak():
 class ClockSampler:
     """nvidia-smi clocks/throttle-reason sampling during the timed region (recipe's clocks line)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    # started before the warm-up (nvidia-smi needs ≈0.2 s to deliver its first line, a short timed region would see none);
+    # mark() brackets the timed region and stop() keeps the samples inside it — or, if the region was shorter than the
+    # sampling period, those of warm-up + timed region (same workload), and says so in "window"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device = device
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
+
+    def mark(self):
+        if self.t0 is None:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def start(self):
         try:
@@ -78,23 +88,34 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
+        import datetime
+
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    ts = None  # (unknown time stamp format: the sample still counts for warm-up + timed region)
+                try:
+                    rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        out["window"] = "timed region" if inside else "warm-up + timed region"
+        if not inside:
+            inside = [r for r in rows if r[0] is None or self.t1 is None or r[0] <= self.t1]
+        sm, mx, reasons = [r[1] for r in inside], [r[2] for r in inside], set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         if sm:
             out["sm_mhz"] = float(np.median(sm))
             out["sm_max_mhz"] = float(max(mx))
@@ -283,15 +304,16 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     # ---- resident (kernel-path) timing --------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         ctx.collide_resident()
         exchange()
-    sampler = ClockSampler(local_rank)
     stage_acc = {}
     launches = 0
     dev_ms = 0.0
     sync_all()
-    sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         res = ctx.collide_resident()
@@ -303,6 +325,7 @@ def run_ours(args, rank, world, local_rank):
         dev_ms += res.ms_total
     sync_all()
     t1 = time.perf_counter()
+    sampler.mark()
     clocks = sampler.stop()
     wall_ms = 1e3 * (t1 - t0) / args.steps
     pairs, hits, contacts = int(res.num_pairs), int(res.gjk_hits), int(res.num_contacts)
@@ -592,12 +615,13 @@ def run_c5(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         ctx.collide_resident()
-    sampler = ClockSampler(local_rank)
     stage_acc, launches, dev_ms = {}, 0, 0.0
     sync_all()
-    sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = ctx.collide_resident()
@@ -608,6 +632,7 @@ def run_c5(args, rank, world, local_rank):
         dev_ms += r.ms_total
     sync_all()
     ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    sampler.mark()
     clocks = sampler.stop()
     pairs, hits, contacts = int(r.num_pairs), int(r.gjk_hits), int(r.num_contacts)
     # end to end: every rank uploads the poses of ITS worlds from pinned host memory and reads its pair keys and
