@@ -58,3 +58,81 @@ def test_filter_leaves_non_unit_quaternions_to_the_exact_path():
     assert drop.sum() == 0
     sc.quat[0::2] /= 1.01
     assert emul.filter_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb).sum() > 1_000
+
+
+def _adversarial(seed, mutate):
+    sc, pa, pb = random_pairs_scene(6_000, seed, kinds=("obb", "sphere", "hull", "aabb"))
+    mutate(sc)
+    hit, _, _ = oracle.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb, stats=True, nthreads=8)
+    drop = emul.filter_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb)
+    wrong = np.nonzero((drop == 1) & (hit == 1))[0]
+    assert len(wrong) == 0, f"filter dropped hits: pairs {wrong[:10]}"
+    return hit, drop
+
+
+def test_filter_with_non_finite_poses():
+    """NaN / inf positions and quaternions: whatever the reference's iteration makes of them (it can end in "hit": every
+    comparison against NaN is false, and an all-false tetrahedron test encloses the origin), the filter must not have
+    an opinion — the margin is NaN, no gap exceeds it."""
+
+    def mutate(sc):
+        sc.pos[0::7, 0] = np.nan
+        sc.pos[3::11, 2] = np.inf
+        sc.quat[5::13, 1] = np.nan
+
+    kinds = {}
+
+    def mutate_and_note(sc):
+        mutate(sc)
+        kinds["k"] = [s[0] for s in sc.shapes]
+
+    hit, drop = _adversarial(41, mutate_and_note)
+    kind = np.array(kinds["k"])  # (shape i belongs to body i in this scene)
+    n = len(kind)
+    bad = np.zeros(n, bool)
+    idx = np.arange(n)
+    bad |= ((idx % 7 == 0) | (idx % 11 == 3)) & (kind != "aabb")  # a world box does not look at the body's position,
+    bad |= (idx % 13 == 5) & ((kind == "obb") | (kind == "hull"))  # nor a sphere at its orientation
+    bad_pair = bad[0::2] | bad[1::2]
+    assert bad_pair.sum() > 1_000 and drop[bad_pair].sum() == 0
+
+
+def test_filter_with_negative_and_zero_extents():
+    """support() picks among the corners (±hx, ±hy, ±hz) / the points p ± r·d whatever the signs stored, and a shape of
+    size zero is a point: the filter works with |h| and |r| and keeps its absolute floor of 2e-6."""
+
+    def mutate(sc):
+        for i, s in enumerate(sc.shapes):
+            if s[0] == "obb" and i % 3 == 0:
+                sc.shapes[i] = ("obb", -np.asarray(s[1]))
+            elif s[0] == "sphere" and i % 3 == 0:
+                sc.shapes[i] = ("sphere", -s[1])
+            elif s[0] == "sphere" and i % 3 == 1:
+                sc.shapes[i] = ("sphere", 0.0)
+            elif s[0] == "obb" and i % 3 == 1:
+                sc.shapes[i] = ("obb", np.zeros(3))
+
+    hit, drop = _adversarial(42, mutate)
+    assert drop.sum() > 1_000  # still filtering
+
+
+def test_filter_far_from_the_origin_and_at_extreme_sizes():
+    """Coordinates of 1e9 (FP32 could not tell the bodies of a pair apart: the centres are subtracted in FP64 first) and
+    scenes scaled by 1e-6 and 1e6."""
+    for k, scale in enumerate((1e-6, 1.0, 1e6)):
+
+        def mutate(sc, scale=scale):
+            sc.pos *= scale
+            sc.pos += 1e9 * scale
+            for i, s in enumerate(sc.shapes):
+                if s[0] == "sphere":
+                    sc.shapes[i] = ("sphere", s[1] * scale)
+                elif s[0] == "aabb":
+                    sc.shapes[i] = ("aabb", sc.pos[i] - (np.asarray(s[2]) - np.asarray(s[1])) * 0.5 * scale,
+                                    sc.pos[i] + (np.asarray(s[2]) - np.asarray(s[1])) * 0.5 * scale)
+                else:
+                    sc.shapes[i] = (s[0], np.asarray(s[1]) * scale)
+
+        hit, drop = _adversarial(43 + k, mutate)
+        if scale >= 1.0:
+            assert drop.sum() > 1_000
