@@ -374,7 +374,10 @@ typedef struct pk_comm_id
 typedef struct pk_gathered_contacts
 {
     const void *d_records;   /* DEVICE pointer: num_ranks blocks of stride_records pk_contact each; block r holds   */
-    uint64_t stride_records; /* counts[r] records sorted by key, the ranks' key ranges interleave                    */
+    uint64_t stride_records; /* counts[r] ≤ stride_records records sorted by key (the rest of a block is unspecified),*/
+                             /* the ranks' key ranges interleave.  The block size is the same on every rank: the      */
+                             /* largest count of the previous exchange plus an eighth, or — first exchange, or a rank */
+                             /* outgrew that — the largest count of this one (the records then travel twice)          */
     const uint64_t *counts;  /* host, ctx-owned, valid until the next call                                          */
     uint32_t num_ranks;
     uint64_t total;          /* sum of counts */
