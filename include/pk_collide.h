@@ -89,6 +89,18 @@ typedef struct pk_contact
     double depth;
 } pk_contact;
 
+/* Closest-distance record of pk_gjk_distance_batch: 64 bytes.  The reference has no such query — gjk_collision
+ * (src/collision.cpp:165-189) answers yes / no and gjk_epa returns std::nullopt for a separated pair (:511-518);
+ * BASELINE.json's north_star asks for "batched GJK intersection/distance", so this is the distance half, over the same
+ * support mappings (bounds.h:164-174, :328-329, :539-548, src/mesh.cpp:341-358, :442-448). */
+typedef struct pk_distance
+{
+    uint64_t key;      /* (a << 32) | b as given */
+    double distance;   /* > 0 when the shapes are separated; 0 when they touch or overlap (depth: pk_gjk_epa_batch) */
+    double point_a[3]; /* closest points in the world frame, |point_a - point_b| = distance; zeros when not separated */
+    double point_b[3];
+} pk_distance;
+
 /* contact_point (collision_phases.h:75-88) minus the fields pk_contact already has: the witness points in
  * the bodies' own frames, local = orientation.conjugate() * (world - pos) (core/particle.h:107-108).  This
  * is what narrow_phase::calculate keeps in its manifolds. */
@@ -400,6 +412,20 @@ int pk_gjk_epa_batch(pk_ctx *ctx, const uint32_t *pair_a, const uint32_t *pair_b
  * PK_E_STATE); host copies already fetched, the pair keys and the tree (pk_raycast) stay valid. */
 int pk_gjk_epa_batch_device(pk_ctx *ctx, const uint32_t *d_pair_a, const uint32_t *d_pair_b, uint64_t n,
                             pk_contact *d_out, uint8_t *d_hit, float *ms);
+
+/* ---- narrowphase only: closest distance over an explicit pair list --------------------------------------------
+ * The distance form of GJK for every pair (a = pair_a[k], b = pair_b[k]): out[k].distance and the closest points for
+ * separated pairs (separated[k] = 1), distance 0 and separated[k] = 0 for pairs that touch or overlap (their depth and
+ * normal are pk_gjk_epa_batch's).  Spheres enter as centre + radius, so sphere distances are exact; polytope pairs end
+ * on the exact optimum of their vertices' arithmetic (relative gap of the bounds <= 1e-12).  Agrees with
+ * gjk_collision's yes / no outside its 1e-6 m margin.  Uses no buffer of the step: results of the last pk_collide*
+ * stay valid.  Host pointers; indices >= the number of uploaded bodies return PK_E_INVALID. */
+int pk_gjk_distance_batch(pk_ctx *ctx, const uint32_t *pair_a, const uint32_t *pair_b, uint64_t n,
+                          pk_distance *out, uint8_t *separated);
+/* Same with the pair list and outputs resident in HBM (device pointers); returns device ms.  An index beyond the
+ * uploaded bodies yields distance 0, separated 0 for that pair. */
+int pk_gjk_distance_batch_device(pk_ctx *ctx, const uint32_t *d_pair_a, const uint32_t *d_pair_b, uint64_t n,
+                                 pk_distance *d_out, uint8_t *d_separated, float *ms);
 
 /* Raw device allocation helpers so a host language without CUDA bindings can stage buffers. */
 int pk_device_alloc(pk_ctx *ctx, size_t bytes, void **dptr);

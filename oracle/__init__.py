@@ -61,6 +61,8 @@ def lib():
         L.pko_support.argtypes = [vp, vp, vp, vp, u32, vp, vp]
         L.pko_gjk_epa_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp, i32]
         L.pko_gjk_epa_pairs.restype = u64
+        L.pko_distance_brute_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, u32, vp, i32]
+        L.pko_distance_brute_pairs.restype = None
         L.pko_contact_points.argtypes = [vp, vp, vp, vp, vp, u64, vp]
         L.pko_man_create.restype = vp
         L.pko_man_destroy.argtypes = [vp]
@@ -211,6 +213,20 @@ def gjk_epa_pairs(shapes, pos, quat, shape_id, pair_a, pair_b, stats=False, nthr
         _p(t.tab), _p(t.verts), _p(pos), _p(quat), _p(sid), _p(pa), _p(pb), n, _p(out), _p(hit), _p(st), int(nthreads)
     )
     return hit, out, st
+
+
+def distance_brute_pairs(shapes, pos, quat, shape_id, pair_a, pair_b, max_verts=16, nthreads=8):
+    """Closest distance of every pair by brute force over all vertex / edge / triangle combinations (pk_oracle.hpp
+    brute_distance: the checker of pk_gjk_distance_batch) → d[n]; meaningful for disjoint bodies, NaN above max_verts."""
+    t = _table(shapes)
+    pos = _f64(pos, (-1, 3))
+    quat = _f64(quat, (-1, 4))
+    sid = np.ascontiguousarray(shape_id, dtype=np.uint32)
+    pa = np.ascontiguousarray(pair_a, dtype=np.uint32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.uint32)
+    out = np.empty(len(pa))
+    lib().pko_distance_brute_pairs(_p(t.tab), _p(t.verts), _p(pos), _p(quat), _p(sid), _p(pa), _p(pb), len(pa), int(max_verts), _p(out), int(nthreads))
+    return out
 
 
 def contact_points(pos, quat, pair_a, pair_b, contacts10):

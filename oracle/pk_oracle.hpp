@@ -1154,6 +1154,106 @@ inline std::optional<collision_info> gjk_epa(const shape &a, const shape &b, gjk
 }
 
 // ---------------------------------------------------------------------------------------------
+// Closest distance between two convex bodies by brute force — the checker of pk_gjk_distance_batch.
+// The reference has no distance query (gjk_collision is boolean, src/collision.cpp:165-189), so there is nothing to
+// restate; this is an independent method that shares no step with GJK: a polytope is the hull of its vertices
+// (box: its 8 corners through the same rotate() the support mapping uses, hull: mesh vertices, sphere: its centre
+// with a margin of r), and the closest pair of two disjoint polytopes is vertex–face, edge–edge or a degenerate
+// form of those.  Every face is covered by triangles of vertex triples and every edge is a vertex pair, and any
+// triple or pair spans points OF the hull, so
+//     min( point–triangle over all vertices × all triples of the other body, both ways;
+//          segment–segment over all vertex pairs × all vertex pairs )
+// is the distance (O(n⁴): for the ≤ 16-vertex bodies of the tests).  Meaningful for disjoint bodies only.
+// ---------------------------------------------------------------------------------------------
+inline double brute_point_segment_sq(v3 p, v3 a, v3 b)
+{
+    const v3 ab = b - a;
+    const double den = sqnorm(ab);
+    double t = den > 0.0 ? dot(p - a, ab) / den : 0.0;
+    t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    return sqnorm(p - (a + t * ab));
+}
+inline double brute_point_triangle_sq(v3 p, v3 a, v3 b, v3 c)
+{
+    // foot of the perpendicular in the triangle's plane by its 2×2 normal equations; inside → that, else the border
+    const v3 e0 = b - a, e1 = c - a, d = p - a;
+    const double a00 = dot(e0, e0), a01 = dot(e0, e1), a11 = dot(e1, e1), b0 = dot(d, e0), b1 = dot(d, e1);
+    const double det = a00 * a11 - a01 * a01;
+    double best = std::min({brute_point_segment_sq(p, a, b), brute_point_segment_sq(p, b, c), brute_point_segment_sq(p, c, a)});
+    if (det > 1e-14 * a00 * a11)
+    {
+        const double u = (a11 * b0 - a01 * b1) / det, w = (a00 * b1 - a01 * b0) / det;
+        if (u >= 0.0 && w >= 0.0 && u + w <= 1.0) best = std::min(best, sqnorm(d - (u * e0 + w * e1)));
+    }
+    return best;
+}
+inline double brute_segment_segment_sq(v3 p1, v3 q1, v3 p2, v3 q2)
+{
+    // a convex quadratic over the unit square: the stationary point if it lies inside, else the border
+    const v3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+    const double a = dot(d1, d1), e = dot(d2, d2), b = dot(d1, d2), c = dot(d1, r), f = dot(d2, r);
+    double best = std::min({brute_point_segment_sq(p1, p2, q2), brute_point_segment_sq(q1, p2, q2), brute_point_segment_sq(p2, p1, q1),
+                            brute_point_segment_sq(q2, p1, q1)});
+    const double den = a * e - b * b;
+    if (den > 1e-14 * a * e)
+    {
+        const double s = (b * f - c * e) / den, t = (a * f - b * c) / den;
+        if (s >= 0.0 && s <= 1.0 && t >= 0.0 && t <= 1.0) best = std::min(best, sqnorm((p1 + s * d1) - (p2 + t * d2)));
+    }
+    return best;
+}
+// world-frame vertices of a body's core and its margin
+inline double brute_core(const shape &s, std::vector<v3> &out)
+{
+    out.clear();
+    switch (s.kind)
+    {
+    case KIND_SPHERE:
+        out.push_back(s.a);
+        return s.b.x;
+    case KIND_AABB:
+        for (int i = 0; i < 8; ++i) out.push_back({(i & 1) ? s.b.x : s.a.x, (i & 2) ? s.b.y : s.a.y, (i & 4) ? s.b.z : s.a.z});
+        return 0.0;
+    case KIND_OBB:
+        for (int i = 0; i < 8; ++i)
+            out.push_back(s.a + rotate(s.q, v3{(i & 1) ? s.b.x : -s.b.x, (i & 2) ? s.b.y : -s.b.y, (i & 4) ? s.b.z : -s.b.z}));
+        return 0.0;
+    default:
+        for (uint32_t i = 0; i < s.nverts; ++i) out.push_back(rotate(s.q, s.verts[i]) + s.a);
+        return 0.0;
+    }
+}
+// → distance of the two bodies if they are disjoint (negative or zero: the margins overlap); NaN above max_verts
+inline double brute_distance(const shape &sa, const shape &sb, uint32_t max_verts = 16)
+{
+    std::vector<v3> A, B;
+    const double ra = brute_core(sa, A), rb = brute_core(sb, B);
+    if (A.size() > max_verts || B.size() > max_verts) return std::numeric_limits<double>::quiet_NaN();
+    double best = std::numeric_limits<double>::infinity();
+    auto point_vs = [&](const std::vector<v3> &P, const std::vector<v3> &Q)
+    {
+        const std::size_t n = Q.size();
+        for (const v3 &p : P)
+        {
+            if (n == 1) best = std::min(best, sqnorm(p - Q[0]));
+            for (std::size_t i = 0; i < n; ++i)
+                for (std::size_t j = i + 1; j < n; ++j)
+                {
+                    if (n == 2) best = std::min(best, brute_point_segment_sq(p, Q[i], Q[j]));
+                    for (std::size_t k = j + 1; k < n; ++k) best = std::min(best, brute_point_triangle_sq(p, Q[i], Q[j], Q[k]));
+                }
+        }
+    };
+    point_vs(A, B);
+    point_vs(B, A);
+    for (std::size_t i = 0; i < A.size(); ++i)
+        for (std::size_t j = i + 1; j < A.size(); ++j)
+            for (std::size_t k = 0; k < B.size(); ++k)
+                for (std::size_t l = k + 1; l < B.size(); ++l) best = std::min(best, brute_segment_segment_sq(A[i], A[j], B[k], B[l]));
+    return std::sqrt(best) - ra - rb;
+}
+
+// ---------------------------------------------------------------------------------------------
 // dynamic_bvh — include/physkit/collision/bvh.h:270-535, src/bvh.cpp:239-514
 // ---------------------------------------------------------------------------------------------
 class dynamic_bvh

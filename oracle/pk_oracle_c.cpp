@@ -115,6 +115,36 @@ void pko_support(const pko_shape_desc *shapes, const double *verts, const double
     st3(out3, support(s, ld3(dir)));
 }
 
+// brute_distance(body pair_a[k], body pair_b[k]) for every k (checker of pk_gjk_distance_batch; NaN for bodies with more
+// than max_verts vertices).  Independent pairs over std::thread workers.
+void pko_distance_brute_pairs(const pko_shape_desc *shapes, const double *verts, const double *pos, const double *quat_xyzw,
+                              const uint32_t *shape_id, const uint32_t *pair_a, const uint32_t *pair_b, uint64_t npairs,
+                              uint32_t max_verts, double *out, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<uint64_t> next{0};
+    auto worker = [&]()
+    {
+        for (;;)
+        {
+            const uint64_t k0 = next.fetch_add(64);
+            if (k0 >= npairs) break;
+            const uint64_t k1 = std::min<uint64_t>(npairs, k0 + 64);
+            for (uint64_t k = k0; k < k1; ++k)
+            {
+                const uint32_t ia = pair_a[k], ib = pair_b[k];
+                shape a = make_shape(shapes[shape_id[ia]], verts, pos + 3 * ia, quat_xyzw + 4 * ia);
+                shape b = make_shape(shapes[shape_id[ib]], verts, pos + 3 * ib, quat_xyzw + 4 * ib);
+                out[k] = brute_distance(a, b, max_verts);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+}
+
 // gjk_epa(a = body pair_a[k], b = body pair_b[k]) for every k.
 //   out10[k] = normal(3) world_a(3) world_b(3) depth ; hit[k] ∈ {0,1} ; stats8[k] optional.
 // nthreads > 1 uses std::thread workers over independent pairs (courtesy all-cores figure; the reference

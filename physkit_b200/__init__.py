@@ -16,6 +16,7 @@ from .api import (  # noqa: F401
     MultiContext,
     PkError,
     contact_dtype,
+    distance_dtype,
     ray_hit_dtype,
     solver_point_dtype,
     gjk_epa,

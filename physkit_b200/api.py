@@ -27,6 +27,8 @@ contact_dtype = np.dtype(
     [("key", np.uint64), ("normal", np.float64, 3), ("world_a", np.float64, 3), ("world_b", np.float64, 3), ("depth", np.float64)]
 )
 assert contact_dtype.itemsize == 88
+distance_dtype = np.dtype([("key", np.uint64), ("distance", np.float64), ("point_a", np.float64, 3), ("point_b", np.float64, 3)])
+assert distance_dtype.itemsize == 64
 solver_row_dtype = np.dtype([("J_v", "<f8", (3,)), ("J_w_a", "<f8", (3,)), ("J_w_b", "<f8", (3,)), ("M_eff", "<f8"), ("bias", "<f8")])
 solver_point_dtype = np.dtype([("key", "<u8"), ("manifold", "<u4"), ("point", "<u4"), ("normal", solver_row_dtype),
                                ("tangent1", solver_row_dtype), ("tangent2", solver_row_dtype), ("friction_coeff", "<f8"),
@@ -103,7 +105,7 @@ EXPORTS = [
     "pk_comm_get_id", "pk_comm_init", "pk_comm_pose_slice", "pk_comm_allgather_poses", "pk_comm_allgather_contacts",
     "pk_collide_resident", "pk_fetch_results", "pk_collide", "pk_pairs", "pk_contacts",
     "pk_pairs_device", "pk_contacts_device", "pk_stored_bounds", "pk_stage_times_get", "pk_stream",
-    "pk_gjk_epa_batch", "pk_gjk_epa_batch_device", "pk_raycast", "pk_raycast_device_ms",
+    "pk_gjk_epa_batch", "pk_gjk_epa_batch_device", "pk_gjk_distance_batch", "pk_gjk_distance_batch_device", "pk_raycast", "pk_raycast_device_ms",
     "pk_dynamics_enable", "pk_dynamics_upload", "pk_dynamics_set_velocities", "pk_dynamics_set_forces",
     "pk_integrate_velocities", "pk_integrate_positions", "pk_dynamics_download", "pk_displacements",
     "pk_material_upload", "pk_contact_rows_setup", "pk_contact_rows", "pk_contact_rows_device",
@@ -188,6 +190,8 @@ def load_library():
     L.pk_stream.argtypes = [vp, vp]
     L.pk_gjk_epa_batch.argtypes = [vp, vp, vp, u64, vp, vp]
     L.pk_gjk_epa_batch_device.argtypes = [vp, vp, vp, u64, vp, vp, vp]
+    L.pk_gjk_distance_batch.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.pk_gjk_distance_batch_device.argtypes = [vp, vp, vp, u64, vp, vp, vp]
     L.pk_device_alloc.argtypes = [vp, C.c_size_t, vp]
     L.pk_device_free.argtypes = [vp, vp]
     L.pk_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -577,6 +581,22 @@ class Context:
         allow = (PK_E_EPA_OVERFLOW,) if allow_epa_overflow else ()
         self._check(self.L.pk_gjk_epa_batch(self.h, _p(pa), _p(pb), n, _p(out), _p(hit)), allow)
         return hit, out
+
+    def gjk_distance_batch(self, pair_a, pair_b):
+        """→ (separated[n] u8, records[n] distance_dtype): closest distance and closest points of every pair
+        (pk_gjk_distance_batch; separated = 0, distance 0 for pairs that touch or overlap)."""
+        pa = _arr(pair_a, np.uint32)
+        pb = _arr(pair_b, np.uint32)
+        n = len(pa)
+        out = np.zeros(n, dtype=distance_dtype)
+        sep = np.zeros(n, dtype=np.uint8)
+        self._check(self.L.pk_gjk_distance_batch(self.h, _p(pa), _p(pb), n, _p(out), _p(sep)))
+        return sep, out
+
+    def gjk_distance_batch_device(self, d_a, d_b, n, d_out, d_sep):
+        ms = C.c_float()
+        self._check(self.L.pk_gjk_distance_batch_device(self.h, C.c_void_p(d_a), C.c_void_p(d_b), int(n), C.c_void_p(d_out), C.c_void_p(d_sep), C.byref(ms)))
+        return float(ms.value)
 
     def device_alloc(self, nbytes):
         p = C.c_void_p()

@@ -12,6 +12,7 @@
 #include "pk_narrowphase.cuh"
 #include "pk_epa_coop.cuh"
 #include "pk_gjk_filter.cuh"
+#include "pk_distance.cuh"
 #include "pk_manifold.cuh"
 #include "pk_dynamics.cuh"
 #include "pk_ray.cuh"
@@ -2399,6 +2400,88 @@ int pk_gjk_epa_batch(pk_ctx *ctx, const uint32_t *pair_a, const uint32_t *pair_b
     {
         cudaMemcpyAsync(out, d_out, n * sizeof(pk_contact), cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(hit, d_h, n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) status = PK_E_CUDA;
+    }
+    cleanup();
+    return status;
+}
+
+// ------------------------------------------------------------------------------------ gjk distance batch
+static_assert(sizeof(pk_distance) == sizeof(DistanceRec), "pk_distance layout");
+
+int pk_gjk_distance_batch_device(pk_ctx *ctx, const uint32_t *d_a, const uint32_t *d_b, uint64_t n, pk_distance *d_out,
+                                 uint8_t *d_separated, float *ms)
+{
+    if (!ctx || !d_a || !d_b || !d_out || !d_separated) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    PK_TRY(upload_shapes(ctx));
+    cudaStream_t s = ctx->stream;
+    // own events: the stage events of the step (pk_get_report) are left alone, like every buffer of the step
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms)
+    {
+        PK_CUDA(cudaEventCreate(&e0));
+        if (cudaEventCreate(&e1) != cudaSuccess)
+        {
+            cudaEventDestroy(e0);
+            return PK_E_CUDA;
+        }
+        cudaEventRecord(e0, s);
+    }
+    if (n)
+    {
+        nvtxRangePushA("pk:gjk_distance");
+        auto kern = ctx->has_big_hulls ? gjk_distance_kernel<true> : gjk_distance_kernel<false>;
+        kern<<<static_cast<unsigned>(div_up(n, 128)), 128, 0, s>>>(body_arrays(ctx), d_a, d_b, n, ctx->n_bodies,
+                                                                     reinterpret_cast<DistanceRec *>(d_out), d_separated);
+        nvtxRangePop();
+    }
+    int status = PK_OK;
+    if (ms)
+    {
+        cudaEventRecord(e1, s);
+        if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(ms, e0, e1) != cudaSuccess) status = PK_E_CUDA;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    else if (cudaStreamSynchronize(s) != cudaSuccess)
+        status = PK_E_CUDA;
+    if (cudaGetLastError() != cudaSuccess) status = PK_E_CUDA;
+    return status;
+}
+
+int pk_gjk_distance_batch(pk_ctx *ctx, const uint32_t *pair_a, const uint32_t *pair_b, uint64_t n, pk_distance *out, uint8_t *separated)
+{
+    if (!ctx) return PK_E_INVALID;
+    if (n == 0) return PK_OK;
+    if (!pair_a || !pair_b || !out || !separated) return PK_E_INVALID;
+    for (uint64_t k = 0; k < n; ++k)
+        if (pair_a[k] >= ctx->n_bodies || pair_b[k] >= ctx->n_bodies) return PK_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    uint32_t *d_a = nullptr, *d_b = nullptr;
+    DistanceRec *d_out = nullptr;
+    uint8_t *d_s = nullptr;
+    int status = PK_OK;
+    auto cleanup = [&]()
+    {
+        if (d_a) cudaFree(d_a);
+        if (d_b) cudaFree(d_b);
+        if (d_out) cudaFree(d_out);
+        if (d_s) cudaFree(d_s);
+    };
+    if ((status = dev_alloc(ctx, &d_a, n)) != PK_OK || (status = dev_alloc(ctx, &d_b, n)) != PK_OK ||
+        (status = dev_alloc(ctx, &d_out, n)) != PK_OK || (status = dev_alloc(ctx, &d_s, n)) != PK_OK)
+    {
+        cleanup();
+        return status;
+    }
+    cudaMemcpyAsync(d_a, pair_a, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_b, pair_b, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    status = pk_gjk_distance_batch_device(ctx, d_a, d_b, n, reinterpret_cast<pk_distance *>(d_out), d_s, nullptr);
+    if (status == PK_OK)
+    {
+        cudaMemcpyAsync(out, d_out, n * sizeof(pk_distance), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(separated, d_s, n, cudaMemcpyDeviceToHost, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) status = PK_E_CUDA;
     }
     cleanup();

@@ -14,6 +14,7 @@ unsigned long long g_ec_stats[16];
 }
 #include "../../physkit_b200/csrc/pk_epa_coop.cuh"
 #include "../../physkit_b200/csrc/pk_gjk_filter.cuh"
+#include "../../physkit_b200/csrc/pk_distance.cuh"
 
 using namespace pk;
 
@@ -42,6 +43,35 @@ extern "C" int emu_filter(const ShapeRec *shapes, uint64_t nshapes, const double
     ba.quat = quat;
     ba.shape_id = shape_id;
     for (uint64_t k = 0; k < n; ++k) out[k] = certainly_separated(load_shape(ba, pa[k]), load_shape(ba, pb[k]), iters) ? 1 : 0;
+    return 0;
+}
+
+// gjk_distance_pair (pk_distance.cuh) per pair on the host, as gjk_distance_kernel<false> runs it (support<false>: the
+// plain FP64 hull scan — the float-prefiltered scan of the <true> instance returns the same vertex, pk_common.cuh)
+extern "C" int emu_distance(const ShapeRec *shapes, uint64_t nshapes, const double *verts, uint64_t nverts_pool, const double *pos, const double *quat,
+                            const uint32_t *shape_id, const uint32_t *pa, const uint32_t *pb, uint64_t n, DistanceRec *out, uint8_t *separated)
+{
+    (void)nshapes;
+    std::vector<float4> vf(nverts_pool + 2);
+    for (uint64_t i = 0; i < nverts_pool; ++i)
+        vf[i] = make_float4(static_cast<float>(verts[3 * i]), static_cast<float>(verts[3 * i + 1]), static_cast<float>(verts[3 * i + 2]), 0.f);
+    BodyArrays ba;
+    ba.shapes = shapes;
+    ba.verts = verts;
+    ba.verts_f = vf.data();
+    ba.pos = pos;
+    ba.quat = quat;
+    ba.shape_id = shape_id;
+    for (uint64_t k = 0; k < n; ++k)
+    {
+        DistanceRec r;
+        r.key = (static_cast<uint64_t>(pa[k]) << 32) | pb[k];
+        d3 a, b;
+        separated[k] = gjk_distance_pair<false>(load_shape(ba, pa[k]), load_shape(ba, pb[k]), r.distance, a, b) ? 1 : 0;
+        r.point_a[0] = a.x; r.point_a[1] = a.y; r.point_a[2] = a.z;
+        r.point_b[0] = b.x; r.point_b[1] = b.y; r.point_b[2] = b.z;
+        out[k] = r;
+    }
     return 0;
 }
 

@@ -16,7 +16,8 @@ CUDA_INC = "/usr/local/cuda/include"
 
 SHAPE_REC = np.dtype([("a", "<f8", 3), ("b", "<f8", 3), ("kind", "<i4"), ("vert_off", "<u4"), ("nverts", "<u4"), ("mesh_box", "<u4")])
 CONTACT = np.dtype([("key", "<u8"), ("normal", "<f8", 3), ("world_a", "<f8", 3), ("world_b", "<f8", 3), ("depth", "<f8")])
-assert SHAPE_REC.itemsize == 64 and CONTACT.itemsize == 88
+DISTANCE = np.dtype([("key", "<u8"), ("distance", "<f8"), ("point_a", "<f8", 3), ("point_b", "<f8", 3)])
+assert SHAPE_REC.itemsize == 64 and CONTACT.itemsize == 88 and DISTANCE.itemsize == 64
 
 KIND = {"aabb": 0, "obb": 1, "sphere": 2, "hull": 3}
 
@@ -27,7 +28,7 @@ def available() -> bool:
 
 def build(force: bool = False) -> str:
     deps = [SRC, os.path.join(ROOT, "tests", "cpp", "simt_host.h")] + [
-        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_narrowphase.cuh", "pk_epa_coop.cuh", "pk_gjk_filter.cuh")
+        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_narrowphase.cuh", "pk_epa_coop.cuh", "pk_gjk_filter.cuh", "pk_distance.cuh")
     ]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
@@ -112,3 +113,23 @@ def filter_pairs(specs, pos, quat, shape_id, pair_a, pair_b, iters=2):
     if rc != 0:
         raise RuntimeError(f"emu_filter failed: {rc}")
     return out
+
+
+def distance_pairs(specs, pos, quat, shape_id, pair_a, pair_b):
+    """→ (separated[n] u8, records[n] DISTANCE): gjk_distance_pair (pk_distance.cuh) per pair, the source
+    gjk_distance_kernel runs on the device."""
+    lib = C.CDLL(build())
+    tab, pool = shape_table(specs)
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+    quat = np.ascontiguousarray(quat, dtype=np.float64).reshape(-1, 4)
+    sid = np.ascontiguousarray(shape_id, dtype=np.uint32)
+    pa = np.ascontiguousarray(pair_a, dtype=np.uint32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.uint32)
+    out = np.zeros(len(pa), dtype=DISTANCE)
+    sep = np.zeros(len(pa), dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emu_distance(p(tab), C.c_uint64(len(tab)), p(pool), C.c_uint64(len(pool)), p(pos), p(quat), p(sid), p(pa), p(pb), C.c_uint64(len(pa)),
+                          p(out), p(sep))
+    if rc != 0:
+        raise RuntimeError(f"emu_distance failed: {rc}")
+    return sep, out
