@@ -45,6 +45,12 @@ struct collision_info // collision.h:52-59
     double depth{};
 };
 
+struct distance_info // no upstream counterpart: gjk_collision is boolean (src/collision.cpp:165-189); pk_gjk_distance_batch
+{
+    double distance{};
+    vec3 closest_a{}, closest_b{};
+};
+
 struct contact_point // collision_phases.h:75-88
 {
     vec3 normal{}, local_a{}, local_b{};
@@ -288,6 +294,24 @@ public:
         collision_info r;
         for (int k = 0; k < 3; ++k) r.normal[k] = c.normal[k], r.world_a[k] = c.world_a[k], r.world_b[k] = c.world_b[k];
         r.depth = c.depth;
+        return r;
+    }
+
+    // closest distance and closest points of two bodies of this world; nullopt when they touch or overlap (then gjk_epa
+    // has the depth).  The reference has no such query; BASELINE.json's north_star names it.
+    std::optional<distance_info> distance(handle a, handle b)
+    {
+        pk_distance d{};
+        std::uint8_t sep = 0;
+        check(pk_bodies_resize(ctx_, static_cast<std::uint32_t>(flags_.size())), "pk_bodies_resize");
+        check(pk_bodies_upload(ctx_, pos_.data(), quat_.data(), disp_.data(), shape_.data(), flags_.data(), nullptr, 0,
+                               static_cast<std::uint32_t>(flags_.size())),
+              "pk_bodies_upload");
+        check(pk_gjk_distance_batch(ctx_, &a, &b, 1, &d, &sep), "pk_gjk_distance_batch");
+        if (!sep) return std::nullopt;
+        distance_info r;
+        r.distance = d.distance;
+        for (int k = 0; k < 3; ++k) r.closest_a[k] = d.point_a[k], r.closest_b[k] = d.point_b[k];
         return r;
     }
 

@@ -20,7 +20,6 @@ int main()
         auto a = w.create_rigid(box, {-2.0, 0.0, 0.0});
         auto b = w.create_rigid(box, {2.0, 0.0, 0.0});
         auto ground = w.create_rigid(w.shape_box({50.0, 0.5, 50.0}), {0.0, -5.0, 0.0}, {0, 0, 0, 1}, true);
-        (void)ground;
         const double dt = 1.0 / 60.0, v = 3.0;
         bool seen_pair = false, seen_contact = false, seen_begin = false;
         std::size_t max_points = 0;
@@ -66,6 +65,12 @@ int main()
         if (!w.raycast({-30.0, 20.0, 0.0}, {1.0, 0.0, 0.0}, 100.0).empty()) return std::printf("FAIL: raycast miss\n"), 1;
         auto one = w.gjk_epa(a, b);
         if (!seen_pair || !seen_contact || !one) return std::printf("FAIL: pair %d contact %d gjk %d\n", seen_pair, seen_contact, (int)one.has_value()), 1;
+        // distance query (not in the reference): box a (half 0.5, y = 0) hangs 4 m above the ground slab's top (y = −4.5);
+        // the two overlapping boxes have no distance
+        auto da = w.distance(a, ground);
+        if (!da || std::fabs(da->distance - 4.0) > 1e-12 || std::fabs(da->closest_a[1] + 0.5) > 1e-12 || std::fabs(da->closest_b[1] + 4.5) > 1e-12)
+            return std::printf("FAIL: distance %f\n", da ? da->distance : -1.0), 1;
+        if (w.distance(a, b)) return std::printf("FAIL: distance of overlapping boxes\n"), 1;
         std::printf("host shim ok\n");
         return 0;
     }
