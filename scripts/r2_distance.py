@@ -47,6 +47,9 @@ out.append(dict(workload=f"c3 side {side}", bodies=n, pairs=len(pa), contacts=in
                 pairs_per_s=len(pa) / ms * 1e3, alg_gbs=len(pa) * 313 / ms / 1e6))
 ctx.close()
 
+if os.environ.get("PK_C4_PAIRS") == "0":
+    print(json.dumps(out[0]))
+    sys.exit(0)
 sc, pa, pb = scene_c4(n_pairs=int(os.environ.get("PK_C4_PAIRS", "2000000")), n_hulls=1024)
 nh = sum(len(s[1]) for s in sc.shapes if s[0] == "hull")
 ctx = pk.Context(sc.n, 16, mode=pk.MODE_QUERY, max_shapes=len(sc.shapes), max_hull_vertices=nh + 8)
