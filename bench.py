@@ -699,6 +699,128 @@ def run_c5(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def c1_trajectory(steps, dt=1.0 / 60.0):
+    """BASELINE C1: ground + 10x10x10 unit boxes (8-vertex hulls, as every body of a physkit::world demo) dropped from a
+    lattice with 0.2 m gaps.  The sweep that would stop them is out of scope, so the drop is prescribed: free fall under
+    gravity until a box reaches its place in the settled pile (layers 0.98 m apart: resting contacts of 2 cm).
+    → scene, pos[steps, n, 3], disp[steps, n, 3] (disp = the step's motion, what world::step_impl passes as vel*dt)."""
+    from scenes import scene_c1
+
+    sc = scene_c1(side=10)
+    n = sc.n
+    layer = np.round((sc.pos[:, 1] - 1.0) / 1.2).astype(np.int64)
+    rest = 0.5 + 0.98 * layer
+    rest[0] = sc.pos[0, 1]
+    pos = np.empty((steps, n, 3))
+    disp = np.zeros((steps, n, 3))
+    y = sc.pos[:, 1].copy()
+    v = np.zeros(n)
+    for k in range(steps):
+        v[1:] -= 9.81 * dt
+        ny = np.maximum(rest, y + v * dt)
+        ny[0] = y[0]
+        v[ny <= rest] = 0.0
+        pos[k] = sc.pos
+        pos[k, :, 1] = y
+        disp[k, :, 1] = ny - y
+        y = ny
+    return sc, pos, disp
+
+
+def run_c1(args, rank, world, local_rank):
+    """BASELINE C1 (the reference's own CPU-runnable case): one 1001-body world, 600 steps at 60 Hz, every step through
+    pk_bodies_update_pose + pk_collide with host buffers, as a host engine would drive it.  N > 1: replicas."""
+    import torch
+
+    import physkit_b200 as pk
+
+    torch.cuda.set_device(local_rank)
+    steps = args.steps if args.steps != 20 else 600
+    sc, pos, disp = c1_trajectory(steps + args.warmup)
+    n = sc.n
+    ctx = pk.Context(n, 64 * n, mode=pk.MODE_WORLD, device=local_rank, max_shapes=8, max_contacts=32 * n, max_hull_vertices=64)
+    ctx.add_shapes(sc.shapes)
+    ctx.resize(n)
+    h_pos, h_disp = ctx.pinned_empty((n, 3), np.float64), ctx.pinned_empty((n, 3), np.float64)
+    ctx.upload(pos[0], sc.quat, disp[0], sc.shape_id, sc.flags)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for k in range(args.warmup):
+        h_pos[:] = pos[k]
+        h_disp[:] = disp[k]
+        ctx.update_pose(h_pos, None, h_disp)
+        ctx.collide()
+    torch.cuda.synchronize()
+    sampler.mark()
+    pairs = contacts = launches = 0
+    dev_ms = 0.0
+    stage_acc = {}
+    t0 = time.perf_counter()
+    for k in range(args.warmup, args.warmup + steps):
+        h_pos[:] = pos[k]
+        h_disp[:] = disp[k]
+        ctx.update_pose(h_pos, None, h_disp)
+        r = ctx.collide()
+        pairs += int(r.num_pairs)
+        contacts += int(r.num_contacts)
+        dev_ms += r.ms_total
+        st, ln = ctx.stage_times()
+        launches += ln
+        for key, val in st.items():
+            stage_acc[key] = stage_acc.get(key, 0.0) + val
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    sampler.mark()
+    clocks = sampler.stop()
+    last_keys = ctx.pairs()
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        stages = {k: v / steps for k, v in stage_acc.items()}
+        hits = contacts
+        table = sorted(((k, v, stage_bytes(k, n, pairs / steps, hits / steps)) for k, v in stages.items() if k != "fetch_d2h" and v > 0), key=lambda x: -x[1])
+        dom = table[0]
+        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": dom[2] / (dom[1] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": dom[2] / (dom[1] * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": dom[1],
+                    "stages_ms": {k: round(v, 4) for k, v in stages.items()},
+                    "note": "a 1001-body world is bound by launch latency (about 35 launches per step), not by any roof"}
+        cpu = None
+        if not args.no_cpu:
+            import oracle
+
+            oracle.build()
+            w = oracle.World(sc.shapes)
+            ck = min(steps + args.warmup, 120)
+            cp, tb, tn = 0, 0.0, 0.0
+            for k in range(ck):
+                c0 = time.perf_counter()
+                w.step(pos[k], sc.quat, disp[k], sc.shape_id, sc.flags)
+                keys = w.pairs()
+                c1 = time.perf_counter()
+                oracle.gjk_epa_pairs(sc.shapes, pos[k], sc.quat, sc.shape_id, (keys >> np.uint64(32)).astype(np.uint32),
+                                     (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32), nthreads=1)
+                c2 = time.perf_counter()
+                if k >= args.warmup:
+                    cp += len(keys)
+                    tb += c1 - c0
+                    tn += c2 - c1
+            cpu = {"value": cp / max(tb + tn, 1e-12), "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": (f"steps {args.warmup}..{ck - 1} of the same trajectory ({cp} pairs): oracle port of the collision stage, dynamic_bvh broadphase "
+                              f"{1e3 * tb:.1f} ms + gjk_epa {1e3 * tn:.1f} ms, single thread like the reference"),
+                   "ms_per_step": 1e3 * (tb + tn) / max(ck - args.warmup, 1)}
+        line = {"metric": "colliding-pair tests/sec (PhysKit demo world, collision stage)", "value": pairs / max(dev_ms * 1e-3, 1e-12), "unit": UNIT,
+                "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C1: ground + 1000 unit boxes (8-vertex hulls) dropped onto it, {steps} steps at 60 Hz, prescribed fall (no solver)",
+                           "pairs_total": pairs, "contacts_total": contacts, "pairs_last_step": int(len(last_keys)),
+                           "timing": "value: device time of the collision stage summed over the steps (CUDA events); e2e: wall clock of the loop "
+                                     "pk_bodies_update_pose + pk_collide with pinned host buffers"},
+                "e2e": {"value": pairs / wall, "unit": UNIT, "ms_per_step": 1e3 * wall / steps, "h2d_bytes_per_step": n * 6 * 8,
+                        "d2h_bytes_per_step": int((pairs * 8 + contacts * 88) / steps)},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -710,7 +832,7 @@ def main():
     ap.add_argument("--ref-side", type=int, default=40, help="lattice side of the --impl reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--manifolds", action="store_true", help="also time the downstream rows (manifolds, contact rows, integrator, ray casts; reported under config)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"], help="c3 is the headline; c4/c5 are extra configs")
+    ap.add_argument("--workload", default="c3", choices=["c1", "c3", "c4", "c5"], help="c3 is the headline; c1/c4/c5 are the other BASELINE configs")
     ap.add_argument("--pairs", type=int, default=2_000_000, help="c4: number of hull pairs")
     ap.add_argument("--worlds", type=int, default=4096, help="c5: number of independent worlds")
     args = ap.parse_args()
@@ -723,6 +845,8 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         log(f"bench.py: --gpus {args.gpus} without torchrun: running rank 0 of 1 (launch with torch.distributed.run for N>1)")
+    if args.workload == "c1":
+        return run_c1(args, rank, world, local_rank)
     if args.workload == "c4":
         return run_c4(args, rank, world, local_rank)
     if args.workload == "c5":
