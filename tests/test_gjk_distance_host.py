@@ -170,3 +170,22 @@ def test_degenerate_inputs():
     assert rec["distance"][4] == pytest.approx(4.0 - 0.5, abs=1e-12)             # cube – point (sphere of radius 0)
     assert rec["distance"][5] == pytest.approx(np.hypot(4.0 - 1e-9, 3.0 - 2e-9), rel=1e-9)  # plate – needle
     assert (rec["distance"][sep == 0] == 0.0).all() and np.isfinite(rec["distance"]).all()
+
+
+def test_distance_is_symmetric_and_translation_invariant():
+    """d(a, b) = d(b, a) with the witness points swapped, and moving both bodies together changes nothing beyond the
+    rounding of the moved coordinates (the iteration runs in a frame attached to the first body)."""
+    sc, pa, pb = random_pairs_scene(2_000, 77, spread=2.5)
+    sep, rec = emul.distance_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb)
+    sep2, rec2 = emul.distance_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pb, pa)
+    assert np.array_equal(sep, sep2)
+    s = sep == 1
+    assert np.abs(rec["distance"][s] - rec2["distance"][s]).max() <= 1e-12
+    # (the closest points need not be unique — parallel faces, edges —, so only each answer's own pair is compared)
+    assert np.abs(np.linalg.norm(rec2["point_a"][s] - rec2["point_b"][s], axis=1) - rec["distance"][s]).max() <= 1e-12
+    shift = np.array([1234.5, -987.25, 4321.125])
+    moved = [("aabb", np.asarray(spec[1]) + shift, np.asarray(spec[2]) + shift) if spec[0] == "aabb" else spec for spec in sc.shapes]
+    sep3, rec3 = emul.distance_pairs(moved, sc.pos + shift, sc.quat, sc.shape_id, pa, pb)
+    assert np.array_equal(sep, sep3)
+    assert np.abs(rec["distance"][s] - rec3["distance"][s]).max() <= 1e-11
+    assert np.abs(np.linalg.norm(rec3["point_a"][s] - rec3["point_b"][s], axis=1) - rec["distance"][s]).max() <= 1e-11
