@@ -104,6 +104,7 @@ struct pk_ctx
     std::vector<double> h_verts;
     bool shapes_dirty = false;
     bool has_big_hulls = false; // a hull above HULL_PREFILTER_MIN vertices is registered
+    bool no_tile_sort = false;  // PK_NO_TILE_SORT=1: sorts of up to one tile take the multi-launch path too (A/B)
     ShapeRec *d_shapes = nullptr;
     double *d_verts = nullptr;
     float4 *d_verts_f = nullptr;
@@ -339,6 +340,22 @@ int radix_sort(pk_ctx *ctx, uint64_t *keys[2], uint32_t *vals[2], uint64_t n, co
 {
     int cur = 0;
     uint32_t ntiles = div_up(n, SORT_TILE);
+    if (ntiles <= 1 && shifts.size() <= 8 && !ctx->no_tile_sort)
+    {
+        // small worlds: all passes in one launch of one block (radix_sort_tile_kernel)
+        uint64_t packed = 0;
+        for (size_t k = 0; k < shifts.size(); ++k) packed |= static_cast<uint64_t>(shifts[k] & 0xFF) << (8 * k);
+        if (vals)
+            radix_sort_tile_kernel<true><<<1, SORT_THREADS, 0, ctx->stream>>>(keys[0], vals[0], keys[1], vals[1], n, n_dev, packed,
+                                                                            static_cast<int>(shifts.size()), lowbits);
+        else
+            radix_sort_tile_kernel<false><<<1, SORT_THREADS, 0, ctx->stream>>>(keys[0], nullptr, keys[1], nullptr, n, n_dev, packed,
+                                                                             static_cast<int>(shifts.size()), lowbits);
+        ctx->launches += 1;
+        PK_CUDA(cudaGetLastError());
+        *result = static_cast<int>(shifts.size() & 1);
+        return PK_OK;
+    }
     if (static_cast<size_t>(ntiles) * 256 > ctx->tile_hist_entries)
     {
         ctx->last_error = "radix sort scratch too small";
@@ -771,6 +788,7 @@ int pk_create(const pk_config *cfg, pk_ctx **out)
     ctx->max_contacts = cfg->max_contacts ? cfg->max_contacts : cfg->max_pairs;
     ctx->exact_prefilter = getenv("PK_GJK_EXACT_PREFILTER") != nullptr;
     if (const char *e = getenv("PK_GJK_FILTER_ITERS")) ctx->filter_iters = atoi(e);
+    ctx->no_tile_sort = getenv("PK_NO_TILE_SORT") != nullptr;
     auto fail = [&](int s)
     {
         pk_destroy(ctx);

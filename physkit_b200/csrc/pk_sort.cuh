@@ -167,6 +167,81 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
     }
 }
 
+// Up to one tile of keys (4096): all passes in ONE launch of one block.  A world of a thousand bodies — the size of the
+// reference's own demos — is bound by launch latency, and its body sort was 12 launches (BASELINE C1: 0.076 of the
+// 0.37 ms of a step).  Same ranking as radix_scatter_kernel (per warp with match.any, warp-contiguous items: stable),
+// the digit bases come from the block's own counts instead of the tile histograms; the passes ping-pong between the
+// two buffers like the launches of radix_sort do, a __syncthreads between them (one block: its global writes are
+// visible to its own threads after the barrier).  shifts: one byte per pass, lowest pass first.
+template <bool HAS_VALS>
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_sort_tile_kernel(uint64_t *keys0, uint32_t *vals0, uint64_t *keys1, uint32_t *vals1,
+                       uint64_t n_cap, const unsigned long long *__restrict__ n_dev, uint64_t shifts, int npasses, int lowbits)
+{
+    const uint64_t n = device_count(n_dev, n_cap);
+    __shared__ uint32_t warp_cnt[SORT_WARPS][256];
+    __shared__ uint32_t warp_sums[SORT_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int pass = 0; pass < npasses; ++pass)
+    {
+        const int shift = static_cast<int>((shifts >> (8 * pass)) & 0xFFull);
+        const uint64_t *keys_in = (pass & 1) ? keys1 : keys0;
+        const uint32_t *vals_in = (pass & 1) ? vals1 : vals0;
+        uint64_t *keys_out = (pass & 1) ? keys0 : keys1;
+        uint32_t *vals_out = (pass & 1) ? vals0 : vals1;
+        for (int w = 0; w < SORT_WARPS; ++w) warp_cnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        uint64_t key[SORT_ITEMS];
+        uint32_t val[SORT_ITEMS];
+        uint32_t rank[SORT_ITEMS];
+#pragma unroll
+        for (int r = 0; r < SORT_ITEMS; ++r)
+        {
+            const uint64_t i = sort_index(0, warp, r, lane);
+            const bool ok = i < n;
+            key[r] = ok ? keys_in[i] : 0xFFFFFFFFFFFFFFFFull;
+            val[r] = (HAS_VALS && ok) ? vals_in[i] : 0u;
+            const uint32_t d = sort_digit(key[r], shift, lowbits);
+            const uint32_t md = ok ? d : (256u + lane); // out-of-range lanes match nobody real
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, md);
+            const uint32_t before = ok ? warp_cnt[warp][d] : 0u;
+            __syncwarp();
+            rank[r] = before + __popc(peers & lt_mask);
+            if (ok && (peers & lt_mask) == 0) warp_cnt[warp][d] = before + __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads(); // every key of this pass has been read (the other buffer is about to be overwritten) and counted
+        {
+            uint32_t c = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w) c += warp_cnt[w][threadIdx.x];
+            uint32_t tot;
+            uint32_t run = block_exclusive_scan_256(c, warp_sums, &tot); // first position of digit threadIdx.x
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w)
+            {
+                const uint32_t cw = warp_cnt[w][threadIdx.x];
+                warp_cnt[w][threadIdx.x] = run;
+                run += cw;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SORT_ITEMS; ++r)
+        {
+            const uint64_t i = sort_index(0, warp, r, lane);
+            if (i < n)
+            {
+                const uint32_t pos = warp_cnt[warp][sort_digit(key[r], shift, lowbits)] + rank[r];
+                keys_out[pos] = key[r];
+                if (HAS_VALS) vals_out[pos] = val[r];
+            }
+        }
+        __syncthreads(); // the pass is complete in global memory before the next one reads it
+    }
+}
+
 // The hist kernel must count with the same tile partition as the scatter kernel; both cover
 // [tile·4096, (tile+1)·4096), only the thread↔item mapping differs, which does not matter for counts.
 
