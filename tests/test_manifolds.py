@@ -152,3 +152,100 @@ def test_gpu_manifold_state_errors():
             ctx.manifolds_update()  # once per step
     finally:
         ctx.close()
+
+
+def _feed(points):
+    """One static pair (identity poses, so local = world), one new contact per step: (x, y, depth) on the plane z = 0."""
+    M = oracle.Manifolds()
+    key = np.array([(1 << 32) | 2], dtype=np.uint64)
+    pos = np.zeros((3, 3))
+    quat = np.tile([0.0, 0.0, 0.0, 1.0], (3, 1))
+    for x, y, d in points:
+        wa = np.array([x, y, 0.0])
+        c = np.concatenate([[0.0, 0.0, 1.0], wa, wa + [0.0, 0.0, d], [d]])[None, :]
+        M.step(key, np.array([1], np.uint8), c, pos, quat)
+    mk, mc, mp = M.get()
+    assert mc[0] == min(len(points), 4)
+    return [(round(float(p[3]), 12), round(float(p[4]), 12), round(float(p[9]), 12)) for p in mp[0, : mc[0]]]
+
+
+def test_add_reduce_known_answers_worked_out_by_hand():
+    """manifold::add_reduce (collision_phases.h:139-198) on five points whose selection was worked out on paper from the
+    reference's four rules — deepest; farthest from it; largest triangle with those two; farthest from the third —
+    and its strict '>' comparisons (the first candidate wins a tie).  Independent of oracle/: the expected lists below
+    were derived from the reference source, not produced by the restatement.
+
+    Case A.  P0 (0, 0; 0.010)  P1 (0.1, 0.02; 0.030)  P2 (0.2, 0.08; 0.020)  P3 (0.3, 0.18; 0.015)  new P4 (0.4, 0.32; 0.040)
+      deepest: P4.  |P−P4|²: P0 0.2624, P1 0.18, P2 0.0976, P3 0.0296 → P0.  edge0 = P0−P4 = (−0.4, −0.32); cross with
+      P1−P4 = (−0.3, −0.30): 0.024, P2−P4 = (−0.2, −0.24): 0.032, P3−P4 = (−0.1, −0.14): 0.024 → P2.  Of P1, P3 the one
+      farthest from P2: P1 0.0136, P3 0.02 → P3.  Kept, in this order: P4, P0, P2, P3.
+    Case B (ties).  P0 (0, 0; 0.02)  P1 (0.1, 0; 0.02)  P2 (0, 0.3; 0.01)  P3 (0.05, 0.05; 0.01)  new P4 (0.3, 0; 0.02)
+      deepest: P0 (P1, P4 are as deep, '>' keeps the first).  |P−P0|²: P1 0.01, P2 0.09, P3 0.005, P4 0.09 → P2 (P4 ties,
+      comes later).  edge0 = P2−P0 = (0, 0.3); |cross|: P1 0.03, P3 0.015, P4 0.09 → P4.  Of P1, P3 the one farthest from
+      P4: P1 0.04, P3 0.065 → P3.  Kept: P0, P2, P4, P3."""
+    a = [(0.0, 0.0, 0.010), (0.1, 0.02, 0.030), (0.2, 0.08, 0.020), (0.3, 0.18, 0.015), (0.4, 0.32, 0.040)]
+    assert _feed(a[:4]) == a[:4]  # below five points nothing is reduced or reordered (add_contact, :124-130)
+    assert _feed(a) == [a[4], a[0], a[2], a[3]]
+    b = [(0.0, 0.0, 0.02), (0.1, 0.0, 0.02), (0.0, 0.3, 0.01), (0.05, 0.05, 0.01), (0.3, 0.0, 0.02)]
+    assert _feed(b) == [b[0], b[2], b[4], b[3]]
+
+
+def test_merge_known_answers_worked_out_by_hand():
+    """narrow_phase::calculate's merge (collision_phases.h:265-318) on cases whose outcome follows from the reference's
+    constants by hand — distance2_eps = (5 mm)², contact_breaking_threshold = 5 cm, drift2_eps = 0.06 m² — for one pair
+    (a = body 1, b = body 2, identity orientations, normal +z, world_b = world_a + depth·z as the reference's comment at
+    :290 has it).  Expected values derived from the reference source, not from the restatement."""
+    key = np.array([(1 << 32) | 2], dtype=np.uint64)
+    quat = np.tile([0.0, 0.0, 0.0, 1.0], (3, 1))
+    hit1, hit0 = np.array([1], np.uint8), np.array([0], np.uint8)
+
+    def contact(x, y, d, shift_b=(0.0, 0.0, 0.0)):
+        wa = np.array([x, y, 0.0])
+        return np.concatenate([[0.0, 0.0, 1.0], wa, wa + [0.0, 0.0, d] + np.asarray(shift_b), [d]])[None, :]
+
+    def start():
+        M = oracle.Manifolds()
+        began, ended = M.step(key, hit1, contact(0.0, 0.0, 0.01), np.zeros((3, 3)), quat)
+        assert list(began) == [key[0]] and len(ended) == 0          # on_coll_beg (:309)
+        M.set_impulses(np.array([[[1.5, 0.25, -0.75], [0, 0, 0], [0, 0, 0], [0, 0, 0]]]))
+        return M
+
+    # (1) a new contact 4 mm from the old one on body a (1.6e-5 < 2.5e-5 m²): the old point is dropped, the new one
+    #     inherits its cached impulses (:272-281); result: one point, at the NEW position
+    M = start()
+    M.step(key, hit1, contact(0.004, 0.0, 0.012), np.zeros((3, 3)), quat)
+    _, mc, mp = M.get()
+    assert mc[0] == 1 and mp[0, 0, 3] == 0.004 and mp[0, 0, 9] == 0.012 and list(mp[0, 0, 10:13]) == [1.5, 0.25, -0.75]
+
+    # (2) 6 mm away on both bodies (3.6e-5 > 2.5e-5): no match; the old point is re-projected (same poses: depth 0.01
+    #     again) and kept with its impulses, the new one is appended with none (:283-303)
+    M = start()
+    M.step(key, hit1, contact(0.006, 0.0, 0.01), np.zeros((3, 3)), quat)
+    _, mc, mp = M.get()
+    assert mc[0] == 2 and mp[0, 0, 3] == 0.0 and mp[0, 1, 3] == 0.006
+    assert list(mp[0, 0, 10:13]) == [1.5, 0.25, -0.75] and not mp[0, 1, 10:13].any()
+
+    # (3) no new contact; b moved 5.5 cm away along the normal: depth = 0.01 − 0.055 = −0.045 > −0.05 → kept with that
+    #     depth; 7 cm: −0.06 → dropped, the manifold empties and the collision ends (:300, :313-314)
+    for dz, keep in ((0.055, True), (0.07, False)):
+        M = start()
+        pos = np.zeros((3, 3))
+        pos[2, 2] = -dz
+        began, ended = M.step(key, hit0, np.zeros((1, 10)), pos, quat)
+        _, mc, mp = M.get()
+        if keep:
+            assert mc[0] == 1 and abs(mp[0, 0, 9] - (0.01 - dz)) < 1e-15 and len(ended) == 0
+        else:
+            assert M.count == 0 and list(ended) == [key[0]] and len(began) == 0
+
+    # (4) no new contact; b slid 0.24 m along x: drift² = 0.0576 < 0.06 → kept, depth unchanged; 0.25 m: 0.0625 → dropped
+    for dx, keep in ((0.24, True), (0.25, False)):
+        M = start()
+        pos = np.zeros((3, 3))
+        pos[2, 0] = dx
+        began, ended = M.step(key, hit0, np.zeros((1, 10)), pos, quat)
+        _, mc, mp = M.get()
+        if keep:
+            assert mc[0] == 1 and abs(mp[0, 0, 9] - 0.01) < 1e-15 and len(ended) == 0
+        else:
+            assert M.count == 0 and list(ended) == [key[0]]
