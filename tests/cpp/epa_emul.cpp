@@ -5,7 +5,6 @@
 // Not linked into, nor reachable from, the product library.
 #include "simt_host.h"
 
-template <class T> inline unsigned __match_any_sync(unsigned, T) { std::abort(); } // gjk_kernel, epa_order_kernel: not emulated
 
 #define PK_EC_STATS
 namespace pk

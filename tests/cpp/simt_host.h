@@ -8,8 +8,8 @@
 // -ffp-contract=off for SSE2 (no FMA), which is what -fmad=false gives on the device; pk_div_by_rcp's explicit
 // fma calls go to libm's correctly rounded fma.
 //
-// Only what the EPA kernels use is provided: full-mask votes / shuffles / __syncwarp (a std::barrier over the 32
-// threads of a warp), atomicAdd on 64-bit counters, the bit and rounding intrinsics.  `__shared__` becomes a
+// Only what the kernels under test use is provided: full-mask votes / shuffles / match.any / __syncwarp (a std::barrier
+// over the 32 threads of a warp), __syncthreads (a barrier over the block), atomicAdd, the bit and rounding intrinsics.  `__shared__` becomes a
 // function-local static, so ONE block of a given kernel instance runs at a time (blocks are run one after the
 // other; the kernels under test are persistent and take their work from an atomic cursor, so a single block does
 // all of it).
@@ -54,6 +54,7 @@ struct Warp
 inline thread_local Idx tl_threadIdx, tl_blockIdx, tl_blockDim, tl_gridDim;
 inline thread_local Warp *tl_warp = nullptr;
 inline thread_local int tl_lane = 0;
+inline thread_local std::barrier<> *tl_block_bar = nullptr; // __syncthreads
 
 template <class K> void launch(unsigned grid, unsigned block, K &&kernel)
 {
@@ -62,6 +63,7 @@ template <class K> void launch(unsigned grid, unsigned block, K &&kernel)
     {
         const unsigned nwarps = (block + 31) / 32;
         std::vector<Warp> warps(nwarps);
+        std::barrier<> block_bar(static_cast<std::ptrdiff_t>(block));
         std::vector<std::thread> th;
         th.reserve(block);
         for (unsigned t = 0; t < block; ++t)
@@ -74,6 +76,7 @@ template <class K> void launch(unsigned grid, unsigned block, K &&kernel)
                     tl_gridDim = Idx{grid, 1, 1};
                     tl_warp = &warps[t / 32];
                     tl_lane = static_cast<int>(t % 32);
+                    tl_block_bar = &block_bar;
                     kernel();
                 });
         for (auto &x : th) x.join();
@@ -131,7 +134,26 @@ inline void __syncwarp(unsigned mask = SIMT_FULL)
     assert(mask == SIMT_FULL);
     simt::tl_warp->bar.arrive_and_wait();
 }
-inline void __syncthreads() { std::abort(); } // not used by the kernels under test
+// Block barrier: every thread of the block must reach it (the sort kernels; blocks must be a whole number of warps'
+// worth of threads that all stay alive until their last barrier, which the kernels under test satisfy).
+inline void __syncthreads() { simt::tl_block_bar->arrive_and_wait(); }
+// lanes of the (full) warp that hold the same value
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v)
+{
+    if (mask == (1u << simt::tl_lane)) return mask;
+    assert(mask == SIMT_FULL);
+    static_assert(sizeof(T) <= 8, "match of at most 64 bits");
+    simt::Warp &w = *simt::tl_warp;
+    uint64_t bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    w.buf[simt::tl_lane] = bits;
+    w.bar.arrive_and_wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i)
+        if (w.buf[i] == bits) r |= 1u << i;
+    w.bar.arrive_and_wait();
+    return r;
+}
 
 template <class T> inline T __ldg(const T *p) { return *p; }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
@@ -167,6 +189,7 @@ inline double __drcp_rn(double x) { return 1.0 / x; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long expected, unsigned long long desired)

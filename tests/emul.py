@@ -133,3 +133,49 @@ def distance_pairs(specs, pos, quat, shape_id, pair_a, pair_b):
     if rc != 0:
         raise RuntimeError(f"emu_distance failed: {rc}")
     return sep, out
+
+
+# ---- the radix sort and the flag scan (tests/cpp/sort_emul.cpp)
+SORT_SRC = os.path.join(ROOT, "tests", "cpp", "sort_emul.cpp")
+SORT_OUT = os.path.join(ROOT, "tests", "cpp", "_build", "libsort_emul.so")
+
+
+def build_sort(force: bool = False) -> str:
+    deps = [SORT_SRC, os.path.join(ROOT, "tests", "cpp", "simt_host.h")] + [os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_sort.cuh")]
+    if not force and os.path.exists(SORT_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(SORT_OUT) for d in deps):
+        return SORT_OUT
+    os.makedirs(os.path.dirname(SORT_OUT), exist_ok=True)
+    cmd = ["g++", "-O1", "-g", "-std=c++20", "-ffp-contract=off", "-pthread", "-fPIC", "-shared", "-I" + CUDA_INC, SORT_SRC, "-o", SORT_OUT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stderr[-4000:])
+    return SORT_OUT
+
+
+def radix_sort(keys, vals, shifts, lowbits=0, tile=True, n_dev=None):
+    """→ (keys, vals) sorted by pk_sort.cuh's kernels over the listed byte shifts (vals may be None).  tile: all passes in
+    one launch (radix_sort_tile_kernel, n ≤ 4096), else hist / scan / scatter per pass.  n_dev: the element count as a
+    device-side counter smaller than len(keys)."""
+    lib = C.CDLL(build_sort())
+    k = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+    v = None if vals is None else np.ascontiguousarray(vals, dtype=np.uint32).copy()
+    sh = np.ascontiguousarray(shifts, dtype=np.int32)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = lib.emu_radix_sort(p(k), p(v), C.c_uint64(len(k)), C.c_uint64(len(k) + 1 if n_dev is None else int(n_dev)), p(sh), C.c_int(len(sh)),
+                            C.c_int(lowbits), C.c_int(1 if tile else 0))
+    if rc != 0:
+        raise RuntimeError(f"emu_radix_sort failed: {rc}")
+    return k, v
+
+
+def flag_scan(flags, n_dev=None):
+    """→ (exclusive scan u32[n], total) by flag_tile_sum / tile_sum_scan / flag_scan_apply (the contact slots of the hits)."""
+    lib = C.CDLL(build_sort())
+    f = np.ascontiguousarray(flags, dtype=np.uint8)
+    out = np.full(len(f), 0xFFFFFFFF, dtype=np.uint32)
+    total = C.c_ulonglong(0)
+    rc = lib.emu_flag_scan(f.ctypes.data_as(C.c_void_p), C.c_uint64(len(f)), C.c_uint64(len(f) + 1 if n_dev is None else int(n_dev)),
+                           out.ctypes.data_as(C.c_void_p), C.byref(total))
+    if rc != 0:
+        raise RuntimeError(f"emu_flag_scan failed: {rc}")
+    return out, int(total.value)
