@@ -25,8 +25,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #undef __shared__
 #define __shared__ static
@@ -56,31 +59,100 @@ inline thread_local Warp *tl_warp = nullptr;
 inline thread_local int tl_lane = 0;
 inline thread_local std::barrier<> *tl_block_bar = nullptr; // __syncthreads
 
+// The OS threads that stand in for the CUDA threads of a block are kept between launches: creating them anew for every
+// block of every launch (a radix pass is a grid of 256 scan blocks of 256 threads) cost more than the kernels.
+class Pool
+{
+public:
+    static Pool &get()
+    {
+        static Pool p;
+        return p;
+    }
+    // job(t) on workers t = 0 … block−1, returns when all of them are done
+    void run(unsigned block, const std::function<void(unsigned)> &job)
+    {
+        ensure(block);
+        job_ = &job;
+        active_ = block;
+        start_->arrive_and_wait();
+        done_->arrive_and_wait();
+    }
+    ~Pool() { stop(); }
+
+private:
+    void ensure(unsigned n)
+    {
+        if (n <= size_) return;
+        stop();
+        size_ = n < 256u ? 256u : n;
+        owner_ = getpid();
+        start_ = std::make_unique<std::barrier<>>(static_cast<std::ptrdiff_t>(size_) + 1);
+        done_ = std::make_unique<std::barrier<>>(static_cast<std::ptrdiff_t>(size_) + 1);
+        quit_ = false;
+        for (unsigned t = 0; t < size_; ++t)
+            th_.emplace_back(
+                [this, t]()
+                {
+                    for (;;)
+                    {
+                        start_->arrive_and_wait();
+                        if (quit_) return;
+                        if (t < active_) (*job_)(t);
+                        done_->arrive_and_wait();
+                    }
+                });
+    }
+    void stop()
+    {
+        if (!size_) return;
+        if (getpid() != owner_)
+        {
+            // a fork()ed child (multiprocessing in the test session) inherits this object but none of its threads:
+            // nothing to wake, nothing to join
+            for (auto &x : th_) x.detach();
+            th_.clear();
+            size_ = 0;
+            return;
+        }
+        quit_ = true;
+        start_->arrive_and_wait();
+        for (auto &x : th_) x.join();
+        th_.clear();
+        size_ = 0;
+    }
+    std::vector<std::thread> th_;
+    std::unique_ptr<std::barrier<>> start_, done_;
+    const std::function<void(unsigned)> *job_ = nullptr;
+    unsigned size_ = 0, active_ = 0;
+    bool quit_ = false;
+    pid_t owner_ = 0;
+};
+
+// Blocks run one after the other (their __shared__ arrays are function-local statics), each thread of the pool playing
+// the same threadIdx in every block; the block barrier also separates consecutive blocks.
 template <class K> void launch(unsigned grid, unsigned block, K &&kernel)
 {
-    assert(block % 32 == 0 || grid * block <= 32 || true);
-    for (unsigned b = 0; b < grid; ++b)
+    assert(block % 32 == 0);
+    const unsigned nwarps = (block + 31) / 32;
+    std::vector<Warp> warps(nwarps);
+    std::barrier<> block_bar(static_cast<std::ptrdiff_t>(block));
+    const std::function<void(unsigned)> job = [&](unsigned t)
     {
-        const unsigned nwarps = (block + 31) / 32;
-        std::vector<Warp> warps(nwarps);
-        std::barrier<> block_bar(static_cast<std::ptrdiff_t>(block));
-        std::vector<std::thread> th;
-        th.reserve(block);
-        for (unsigned t = 0; t < block; ++t)
-            th.emplace_back(
-                [&, t]()
-                {
-                    tl_threadIdx = Idx{t, 0, 0};
-                    tl_blockIdx = Idx{b, 0, 0};
-                    tl_blockDim = Idx{block, 1, 1};
-                    tl_gridDim = Idx{grid, 1, 1};
-                    tl_warp = &warps[t / 32];
-                    tl_lane = static_cast<int>(t % 32);
-                    tl_block_bar = &block_bar;
-                    kernel();
-                });
-        for (auto &x : th) x.join();
-    }
+        tl_threadIdx = Idx{t, 0, 0};
+        tl_blockDim = Idx{block, 1, 1};
+        tl_gridDim = Idx{grid, 1, 1};
+        tl_warp = &warps[t / 32];
+        tl_lane = static_cast<int>(t % 32);
+        tl_block_bar = &block_bar;
+        for (unsigned b = 0; b < grid; ++b)
+        {
+            tl_blockIdx = Idx{b, 0, 0};
+            kernel();
+            block_bar.arrive_and_wait();
+        }
+    };
+    Pool::get().run(block, job);
 }
 } // namespace simt
 
@@ -129,6 +201,8 @@ template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta)
     const int src = simt::tl_lane - static_cast<int>(delta);
     return simt_exchange(mask, v, src < 0 ? simt::tl_lane : src);
 }
+template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) { return simt_exchange(mask, v, (simt::tl_lane ^ lane_mask) & 31); }
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
 inline void __syncwarp(unsigned mask = SIMT_FULL)
 {
     assert(mask == SIMT_FULL);
@@ -190,6 +264,52 @@ inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicMin(unsigned *p, unsigned v)
+{
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+inline unsigned atomicMax(unsigned *p, unsigned v)
+{
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+// loads with cache hints are plain loads here; the hierarchy kernel's hand-over reads go through an atomic load so
+// that the host's memory model gives what __threadfence + ld.cg give on the device
+template <class T> inline T __ldcg(const T *p)
+{
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    return *p;
+}
+template <class T> inline T __ldcs(const T *p) { return *p; }
+inline unsigned __float_as_uint(float f)
+{
+    unsigned u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+inline float __uint_as_float(unsigned u)
+{
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+// a + b rounded towards −inf / +inf: round to nearest, then step by the sign of the exact error (TwoSum)
+inline float simt_fadd_dir(float a, float b, bool up)
+{
+    const float s = a + b;
+    if (!(std::fabs(s) < INFINITY) || s != s) return s;
+    const float bb = s - a;
+    const float err = (a - (s - bb)) + (b - bb);
+    if (up && err > 0.f) return std::nextafterf(s, INFINITY);
+    if (!up && err < 0.f) return std::nextafterf(s, -INFINITY);
+    return s;
+}
+inline float __fadd_rd(float a, float b) { return simt_fadd_dir(a, b, false); }
+inline float __fadd_ru(float a, float b) { return simt_fadd_dir(a, b, true); }
 inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long expected, unsigned long long desired)

@@ -179,3 +179,70 @@ def flag_scan(flags, n_dev=None):
     if rc != 0:
         raise RuntimeError(f"emu_flag_scan failed: {rc}")
     return out, int(total.value)
+
+
+# ---- the broadphase (tests/cpp/broad_emul.cpp)
+BROAD_SRC = os.path.join(ROOT, "tests", "cpp", "broad_emul.cpp")
+BROAD_OUT = os.path.join(ROOT, "tests", "cpp", "_build", "libbroad_emul.so")
+
+
+def build_broad(force: bool = False) -> str:
+    deps = [BROAD_SRC, os.path.join(ROOT, "tests", "cpp", "simt_host.h")] + [
+        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_sort.cuh", "pk_broadphase.cuh")]
+    if not force and os.path.exists(BROAD_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(BROAD_OUT) for d in deps):
+        return BROAD_OUT
+    os.makedirs(os.path.dirname(BROAD_OUT), exist_ok=True)
+    cmd = ["g++", "-O1", "-g", "-std=c++20", "-ffp-contract=off", "-pthread", "-fPIC", "-shared", "-I" + CUDA_INC, BROAD_SRC, "-o", BROAD_OUT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stderr[-4000:])
+    return BROAD_OUT
+
+
+class BroadWorld:
+    """The library's broadphase kernels stepped on the host in the order pk_collide_resident launches them: the
+    counterpart of oracle.World (same step() / pairs() / stored())."""
+
+    def __init__(self, specs, max_bodies, mode_query=False, rows=True, num_worlds=1, shard=(0, 1)):
+        self.lib = C.CDLL(build_broad())
+        self.lib.emu_broad_create.restype = C.c_void_p
+        self.lib.emu_broad_step.restype = C.c_longlong
+        self.tab, _ = shape_table(specs)
+        self.h = C.c_void_p(self.lib.emu_broad_create(C.c_uint32(max_bodies)))
+        self.mode_query, self.rows, self.num_worlds, self.shard = mode_query, rows, num_worlds, shard
+        self.n = 0
+        self.npairs = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.emu_broad_destroy(self.h)
+            self.h = None
+
+    def step(self, pos, quat, disp, shape_id, flags, world_id=None):
+        """→ number of bodies re-inserted (moved); raises on a full pair row (the library repeats such a step in list form)."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        quat = np.ascontiguousarray(quat, dtype=np.float64).reshape(-1, 4)
+        disp = np.ascontiguousarray(disp, dtype=np.float64).reshape(-1, 3)
+        sid = np.ascontiguousarray(shape_id, dtype=np.uint32)
+        fl = np.ascontiguousarray(flags, dtype=np.uint8)
+        wid = None if world_id is None else np.ascontiguousarray(world_id, dtype=np.uint32)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self.n = len(pos)
+        r = self.lib.emu_broad_step(self.h, p(self.tab), p(pos), p(quat), p(disp), p(sid), p(fl), p(wid), C.c_uint32(self.num_worlds), C.c_uint32(self.n),
+                                    C.c_int(1 if self.mode_query else 0), C.c_int(1 if self.rows else 0), C.c_uint32(self.shard[0]), C.c_uint32(self.shard[1]))
+        if r < 0:
+            raise RuntimeError(f"emu_broad_step: {r}" + (" (a pair row overflowed)" if r == -1 else ""))
+        self.npairs = int(r)
+        moved = C.c_ulonglong(0)
+        self.lib.emu_broad_get(self.h, None, None, C.c_uint32(0), C.byref(moved))
+        return int(moved.value)
+
+    def pairs(self):
+        out = np.empty(self.npairs, dtype=np.uint64)
+        self.lib.emu_broad_get(self.h, out.ctypes.data_as(C.c_void_p), None, C.c_uint32(0), None)
+        return out
+
+    def stored(self):
+        out = np.empty((self.n, 6))
+        self.lib.emu_broad_get(self.h, None, out.ctypes.data_as(C.c_void_p), C.c_uint32(self.n), None)
+        return out

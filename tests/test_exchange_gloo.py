@@ -40,7 +40,7 @@ def _worker(rank, world, port, out):
 
 def test_allgather_records_world2_gloo():
     port = _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # (no fork: the session may hold the host-emulation thread pool, tests/cpp/simt_host.h)
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]

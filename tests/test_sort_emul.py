@@ -53,7 +53,7 @@ def test_pair_keys_sort_with_packed_id_fields():
 
 def test_multi_launch_pass_over_several_tiles_and_against_the_tile_sort():
     """radix_hist / radix_scan / radix_scatter: one pass over three tiles is a stable sort by that byte; on one tile it
-    gives what the single-launch form gives.  (One pass each: a grid of 256 scan blocks is 65 536 OS threads here.)"""
+    gives what the single-launch form gives."""
     rng = np.random.default_rng(3)
     keys = rng.integers(0, 1 << 16, 9000, dtype=np.uint64)
     keys[::5] = 77 << 8
