@@ -12,6 +12,7 @@ namespace pk
 unsigned long long g_ec_stats[16];
 }
 #include "../../physkit_b200/csrc/pk_epa_coop.cuh"
+#include "../../physkit_b200/csrc/pk_sort.cuh"
 #include "../../physkit_b200/csrc/pk_gjk_filter.cuh"
 #include "../../physkit_b200/csrc/pk_distance.cuh"
 
@@ -74,6 +75,9 @@ extern "C" int emu_distance(const ShapeRec *shapes, uint64_t nshapes, const doub
     return 0;
 }
 
+// arrival = 3: no host-side stand-in for the front of the stage at all — gjk_filter_kernel / gjk_prefilter_kernel,
+// gjk_kernel, the flag scan and epa_order_kernel are launched as run_narrowphase launches them (the hits then take their
+// simplex slots in whatever order the OS schedules the threads: the records must not depend on it).
 extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const double *verts, uint64_t nverts_pool, const double *pos, const double *quat,
                            const uint32_t *shape_id, const uint32_t *pa, const uint32_t *pb, uint64_t n, uint64_t capacity,
                            ContactRec *out, uint8_t *hit_out, int mirror, int arrival, int nblocks, uint64_t *stats /*[8]*/)
@@ -93,7 +97,7 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const doubl
 
     // gjk_kernel (pk_narrowphase.cuh:311-360) per pair.  On the device the hits take their simplex slots in arrival
     // order; `arrival` picks pair order (0), reversed (1) or a fixed pseudo-random permutation (2)
-    std::vector<uint8_t> hit(n, 0);
+    std::vector<uint8_t> hit(n + SCAN_TILE + 16, 0); // (the flag scan reads whole 16-byte groups)
     std::vector<SimplexRec> simplices(capacity + 1);
     unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // [0] hits, [4] valid, [5] dropped
     unsigned long long class_counts[EPA_CLASSES] = {};
@@ -108,7 +112,48 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const doubl
             std::swap(seq[k - 1], seq[x % k]);
         }
     }
-    for (uint64_t q = 0; q < n; ++q)
+    const bool kernels = arrival == 3;
+    std::vector<uint32_t> out_index(n + 1, 0);
+    std::vector<uint32_t> order(capacity + 1);
+    if (kernels && n)
+    {
+        std::vector<uint32_t> work(4 * (n + 1));
+        unsigned long long work_count[4] = {0, 0, 0, 0};
+        const unsigned pair_blocks = static_cast<unsigned>((n + 127) / 128);
+        const unsigned gjk_blocks = static_cast<unsigned>((n + PK_GJK_THREADS - 1) / PK_GJK_THREADS);
+        if (!big_hulls)
+        {
+            simt::launch(pair_blocks, 128, [&]() { gjk_filter_kernel(ba, nullptr, pa, pb, n, nullptr, hit.data(), work.data(), n + 1, work_count, PK_GJK_FILTER_ITERS); });
+            simt::launch(gjk_blocks, PK_GJK_THREADS,
+                         [&]()
+                         {
+                             gjk_kernel<false, false>(ba, nullptr, pa, pb, work.data(), n + 1, work_count, hit.data(), simplices.data(), &counters[0], capacity,
+                                                      class_counts, nullptr);
+                         });
+        }
+        else
+        {
+            std::vector<GjkCarry> carry(n + 1);
+            simt::launch(pair_blocks, 128,
+                         [&]() { gjk_prefilter_kernel<true, true>(ba, nullptr, pa, pb, n, nullptr, hit.data(), work.data(), n + 1, work_count, carry.data()); });
+            simt::launch(gjk_blocks, PK_GJK_THREADS,
+                         [&]()
+                         {
+                             gjk_kernel<true, true>(ba, nullptr, pa, pb, work.data(), n + 1, work_count, hit.data(), simplices.data(), &counters[0], capacity,
+                                                    class_counts, carry.data());
+                         });
+        }
+        const unsigned nt = static_cast<unsigned>((n + SCAN_TILE - 1) / SCAN_TILE);
+        std::vector<uint32_t> tiles(nt + 1);
+        unsigned long long scan_total = 0;
+        simt::launch(nt, 256, [&]() { flag_tile_sum_kernel(hit.data(), n, nullptr, tiles.data()); });
+        simt::launch(1, 256, [&]() { tile_sum_scan_kernel(tiles.data(), nt, &scan_total); });
+        simt::launch(nt, 256, [&]() { flag_scan_apply_kernel(hit.data(), n, nullptr, tiles.data(), out_index.data()); });
+        if (scan_total != counters[0]) return -3; // the scan counts the hits gjk_kernel counted
+        unsigned long long class_fill[EPA_CLASSES] = {};
+        simt::launch(4, 256, [&]() { epa_order_kernel(simplices.data(), &counters[0], capacity, class_counts, class_fill, order.data()); });
+    }
+    for (uint64_t q = 0; q < n && !kernels; ++q)
     {
         const uint64_t k = seq[q];
         ShapeView A = load_shape(ba, pa[k]);
@@ -158,7 +203,7 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const doubl
     }
     const uint64_t nhits = std::min<uint64_t>(counters[0], capacity);
     // contact slot = rank of the pair among the hits; order[] = hit slots grouped by class, heaviest first
-    std::vector<uint32_t> out_index(n + 1, 0);
+    if (!kernels)
     {
         uint32_t run = 0;
         for (uint64_t k = 0; k < n; ++k)
@@ -167,7 +212,7 @@ extern "C" int emu_gjk_epa(const ShapeRec *shapes, uint64_t nshapes, const doubl
             run += hit[k];
         }
     }
-    std::vector<uint32_t> order(nhits + 1);
+    if (!kernels)
     {
         uint64_t fill[EPA_CLASSES]; // heaviest class first, as epa_order_kernel
         uint64_t run = 0;

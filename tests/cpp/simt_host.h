@@ -17,6 +17,7 @@
 
 #include <cuda_runtime.h> // vector types and make_*; under g++ the __device__ / __global__ annotations vanish
 
+#include <atomic>
 #include <barrier>
 #include <cassert>
 #include <cmath>
@@ -53,6 +54,18 @@ struct Warp
 {
     std::barrier<> bar{32};
     uint64_t buf[32];
+    // sub-groups of a warp (the peers of a match.any): a rendezvous per group, keyed by its lowest lane
+    uint64_t sub_buf[32];
+    std::atomic<unsigned> sub_arrived[32];
+    std::atomic<unsigned> sub_left[32];
+    Warp()
+    {
+        for (int i = 0; i < 32; ++i)
+        {
+            sub_arrived[i].store(0);
+            sub_left[i].store(0);
+        }
+    }
 };
 inline thread_local Idx tl_threadIdx, tl_blockIdx, tl_blockDim, tl_gridDim;
 inline thread_local Warp *tl_warp = nullptr;
@@ -179,11 +192,40 @@ inline unsigned __ballot_sync(unsigned mask, int pred)
     w.bar.arrive_and_wait();
     return r;
 }
+// Exchange inside a proper sub-group of the warp (every lane of `mask`, and only those, calls with the same mask; groups
+// that are in flight at the same time are disjoint, as the peers of a match.any are): all write, the last to arrive
+// opens the gate, all read, the last to leave resets the rendezvous for the group's next exchange.
+inline uint64_t simt_subgroup_exchange(unsigned mask, uint64_t bits, int src)
+{
+    simt::Warp &w = *simt::tl_warp;
+    const int key = __builtin_ctz(mask);
+    const unsigned k = static_cast<unsigned>(__builtin_popcount(mask));
+    while (w.sub_left[key].load(std::memory_order_acquire) != 0) std::this_thread::yield(); // the previous exchange is still draining
+    w.sub_buf[simt::tl_lane] = bits;
+    w.sub_arrived[key].fetch_add(1, std::memory_order_acq_rel);
+    while (w.sub_arrived[key].load(std::memory_order_acquire) < k) std::this_thread::yield();
+    const uint64_t got = (src >= 0 && src < 32 && ((mask >> src) & 1u)) ? w.sub_buf[src] : bits;
+    if (w.sub_left[key].fetch_add(1, std::memory_order_acq_rel) + 1 == k)
+    {
+        w.sub_arrived[key].store(0, std::memory_order_release);
+        w.sub_left[key].store(0, std::memory_order_release);
+    }
+    return got;
+}
 template <class T> inline T simt_exchange(unsigned mask, T v, int src)
 {
     if (mask == (1u << simt::tl_lane)) return v;
-    assert(mask == SIMT_FULL);
     static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+    if (mask != SIMT_FULL)
+    {
+        assert((mask >> simt::tl_lane) & 1u);
+        uint64_t b = 0;
+        std::memcpy(&b, &v, sizeof(T));
+        const uint64_t got = simt_subgroup_exchange(mask, b, src);
+        T out;
+        std::memcpy(&out, &got, sizeof(T));
+        return out;
+    }
     simt::Warp &w = *simt::tl_warp;
     uint64_t bits = 0;
     std::memcpy(&bits, &v, sizeof(T));

@@ -28,7 +28,7 @@ def available() -> bool:
 
 def build(force: bool = False) -> str:
     deps = [SRC, os.path.join(ROOT, "tests", "cpp", "simt_host.h")] + [
-        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_narrowphase.cuh", "pk_epa_coop.cuh", "pk_gjk_filter.cuh", "pk_distance.cuh")
+        os.path.join(ROOT, "physkit_b200", "csrc", f) for f in ("pk_common.cuh", "pk_narrowphase.cuh", "pk_epa_coop.cuh", "pk_gjk_filter.cuh", "pk_distance.cuh", "pk_sort.cuh")
     ]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT

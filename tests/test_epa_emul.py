@@ -16,8 +16,8 @@ from scenes import IDENT, Scene, SplitMix64, random_pairs_scene, scene_c3, scene
 pytestmark = [pytest.mark.skipif(not emul.available(), reason="CUDA headers not installed"), pytest.mark.timeout(600)]
 
 
-def _check(sc, pa, pb, mirror=False, capacity=None):
-    hit, out, stats = emul.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb, capacity=capacity, mirror=mirror)
+def _check(sc, pa, pb, mirror=False, capacity=None, arrival=2):
+    hit, out, stats = emul.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb, capacity=capacity, mirror=mirror, arrival=arrival)
     hit_ref, out_ref, _ = oracle.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb, nthreads=8)
     assert np.array_equal(hit, hit_ref), f"hit flags differ at {np.nonzero(hit != hit_ref)[0][:10]}"
     m = hit_ref.astype(bool)
@@ -134,3 +134,40 @@ def test_sphere_pairs_with_exact_ties_restart_in_heap_mode():
     hit, out, stats = emul.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pa + 1, nblocks=2)
     assert stats["restarted_in_heap_mode"] > 100 and stats["valid"] == hit.sum()
     _check(sc, pa, pa + 1)
+
+
+# ---- the whole stage as run_narrowphase launches it: gjk_filter_kernel / gjk_prefilter_kernel → gjk_kernel → flag scan →
+# ---- epa_order_kernel → epa_init_kernel → epa_coop_kernel → epa_kernel (arrival=3: no host-side stand-in for the front)
+def test_whole_stage_kernels_c3_mix():
+    """Spheres and boxes: misses settled by the FP32 filter kernel, survivors listed per shape-kind class, hits appended
+    in the order the threads happen to run, contact slots from the scan, EPA order from epa_order_kernel."""
+    sc = scene_c3(side=9)
+    pa, pb = _lattice_pairs(sc, 1.0)
+    hit, stats = _check(sc, pa, pb, arrival=3)
+    assert hit.sum() > 300 and stats["class0"] > 50 and stats["class2"] > 10 and stats["class1"] > 300
+    assert stats["valid"] == hit.sum()
+
+
+def test_whole_stage_kernels_all_shape_kinds_and_hull_contexts():
+    """All kinds (the hull context takes gjk_prefilter_kernel<true, true> and carries two support points to gjk_kernel)."""
+    sc, pa, pb = random_pairs_scene(1500, 21)
+    hit, _ = _check(sc, pa, pb, arrival=3)
+    assert 0.2 < hit.mean() < 0.9
+    sc, pa, pb = scene_c4(n_pairs=400, n_hulls=16)
+    hit, _ = _check(sc, pa, pb, arrival=3)
+    assert hit.sum() > 100
+
+
+def test_whole_stage_kernels_more_hits_than_contact_records():
+    """GJK hits beyond the contact capacity are counted, not written (the contact slot was unchecked)."""
+    sc = scene_c3(side=7)
+    pa, pb = _lattice_pairs(sc, 1.0)
+    full, _, _ = emul.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb, arrival=3)
+    cap = int(full.sum()) // 2
+    hit, out, stats = emul.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb, capacity=cap, arrival=3)
+    assert stats["gjk_hits"] == full.sum() and stats["valid"] <= cap and hit.sum() == stats["valid"]
+    # the records that were written are the oracle's
+    _, out_ref, _ = oracle.gjk_epa_pairs(sc.shapes, sc.pos, sc.quat, sc.shape_id, pa, pb, nthreads=8)
+    m = hit.astype(bool)
+    got = np.concatenate([out["normal"], out["world_a"], out["world_b"], out["depth"][:, None]], axis=1)
+    assert np.array_equal(got[m].view(np.uint64), np.ascontiguousarray(out_ref[m]).view(np.uint64))
